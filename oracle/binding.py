@@ -1,0 +1,214 @@
+"""ctypes binding of the CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` (cpu_baseline / ``--impl reference``)
+may import this module.  The product package ``petar_b200`` never does.
+
+Two libraries:
+
+* ``oracle/lib/liboracle_soft_force.so`` — fp64 restatement of the reference's NoSimd functors
+  (``oracle_soft_force.c``; reference ``src/soft_force.hpp:11-34, 38-87, 125-158, 160-200``).
+* ``oracle/_ref/libpetar_ref_{avx2,avx512}.so`` — the reference's own ``PhantomGrapeQuad`` kernels
+  compiled from ``/root/reference/src/phantomquad_for_p3t_x86.hpp`` (``ref_simd.cpp``).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from petar_b200.types import EPISoft, EPJSoft, SPJQuad, ForceSoft
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_vp = C.c_void_p
+_ip = C.POINTER(C.c_int)
+
+
+def build(verbose=False):
+    """Compile the oracle (always) and oracle/_ref (only where /root/reference exists)."""
+    out = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+def _cpu_has_avx512():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    fl = set(line.split(":")[1].split())
+                    return {"avx512f", "avx512dq"} <= fl
+    except OSError:
+        pass
+    return False
+
+
+_oracle = None
+_ref = {}
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(_HERE, "lib", "liboracle_soft_force.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_search_neighbor_epep.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp]
+        L.orc_force_epep_linear_cutoff.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double, C.c_double, C.c_double]
+        L.orc_force_epsp_mono.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double, C.c_double]
+        L.orc_force_epsp_quad.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double, C.c_double]
+        L.orc_force_pp.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double]
+        L.orc_walks_index.argtypes = [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double]
+        L.orc_make_plummer.argtypes = [C.c_double, C.c_longlong, C.c_longlong, _vp, _vp, _vp, C.c_double, C.c_uint32]
+        L.orc_simdtest_inputs.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
+        L.orc_srand.argtypes = [C.c_uint]
+        L.orc_mt_init.argtypes = [_vp, C.c_uint32]
+        L.orc_mt_int32.argtypes = [_vp]
+        L.orc_mt_int32.restype = C.c_uint32
+        L.orc_mt_res53.argtypes = [_vp]
+        L.orc_mt_res53.restype = C.c_double
+        L.orc_mt_real2.argtypes = [_vp]
+        L.orc_mt_real2.restype = C.c_double
+        L.orc_calc_rsearch.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_calc_rsearch.restype = C.c_double
+        _oracle = L
+    return _oracle
+
+
+def ref_available(isa=None):
+    isa = isa or ("avx512" if _cpu_has_avx512() else "avx2")
+    return os.path.exists(os.path.join(_HERE, "_ref", f"libpetar_ref_{isa}.so"))
+
+
+def ref_lib(isa=None):
+    """The reference's own SIMD kernels; isa in {'avx2','avx512'} (default: best the CPU has)."""
+    isa = isa or ("avx512" if _cpu_has_avx512() else "avx2")
+    if isa == "avx512" and not _cpu_has_avx512():
+        raise RuntimeError("host CPU lacks AVX-512")
+    if isa not in _ref:
+        path = os.path.join(_HERE, "_ref", f"libpetar_ref_{isa}.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.ref_simd_isa.restype = C.c_char_p
+        L.ref_epep_simd.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double, C.c_double, C.c_double]
+        L.ref_epsp_quad_simd.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double, C.c_double]
+        L.ref_nb_simd.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp]
+        L.ref_walks_index.argtypes = [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.ref_walks_index.restype = C.c_double
+        _ref[isa] = L
+    return _ref[isa]
+
+
+def _chk(a, dt):
+    assert a.dtype == dt and a.flags["C_CONTIGUOUS"], (a.dtype, dt)
+    return a.ctypes.data
+
+
+def new_force(n):
+    return np.zeros(n, dtype=ForceSoft)
+
+
+# ---- functor-level wrappers (fp64 oracle) -------------------------------------------------
+def force_epep(epi, epj, eps, r_out, G, force=None):
+    f = new_force(len(epi)) if force is None else force
+    oracle_lib().orc_force_epep_linear_cutoff(_chk(epi, EPISoft), len(epi), _chk(epj, EPJSoft), len(epj), _chk(f, ForceSoft), eps, r_out, G)
+    return f
+
+
+def force_epsp_quad(epi, spj, eps, G, force=None):
+    f = new_force(len(epi)) if force is None else force
+    oracle_lib().orc_force_epsp_quad(_chk(epi, EPISoft), len(epi), _chk(spj, SPJQuad), len(spj), _chk(f, ForceSoft), eps, G)
+    return f
+
+
+def force_epsp_mono(epi, spj, eps, G, force=None):
+    f = new_force(len(epi)) if force is None else force
+    oracle_lib().orc_force_epsp_mono(_chk(epi, EPISoft), len(epi), _chk(spj, SPJQuad), len(spj), _chk(f, ForceSoft), eps, G)
+    return f
+
+
+def force_pp(epi, epj, G, force=None):
+    f = new_force(len(epi)) if force is None else force
+    oracle_lib().orc_force_pp(_chk(epi, EPISoft), len(epi), _chk(epj, EPJSoft), len(epj), _chk(f, ForceSoft), G)
+    return f
+
+
+def search_neighbor(epi, epj, force=None):
+    f = new_force(len(epi)) if force is None else force
+    oracle_lib().orc_search_neighbor_epep(_chk(epi, EPISoft), len(epi), _chk(epj, EPJSoft), len(epj), _chk(f, ForceSoft))
+    return f
+
+
+# ---- functor-level wrappers (reference SIMD kernels) --------------------------------------
+def ref_force_epep(epi, epj, eps, r_out, G, isa=None, force=None):
+    f = new_force(len(epi)) if force is None else force
+    ref_lib(isa).ref_epep_simd(_chk(epi, EPISoft), len(epi), _chk(epj, EPJSoft), len(epj), _chk(f, ForceSoft), eps, r_out, G)
+    return f
+
+
+def ref_force_epsp_quad(epi, spj, eps, G, isa=None, force=None):
+    f = new_force(len(epi)) if force is None else force
+    ref_lib(isa).ref_epsp_quad_simd(_chk(epi, EPISoft), len(epi), _chk(spj, SPJQuad), len(spj), _chk(f, ForceSoft), eps, G)
+    return f
+
+
+def ref_search_neighbor(epi, epj, isa=None, force=None):
+    f = new_force(len(epi)) if force is None else force
+    ref_lib(isa).ref_nb_simd(_chk(epi, EPISoft), len(epi), _chk(epj, EPJSoft), len(epj), _chk(f, ForceSoft))
+    return f
+
+
+# ---- multiwalk batches ---------------------------------------------------------------------
+def _walk_args(batch, force):
+    """batch: petar_b200.walks.WalkBatch; returns the pointer tables FDPS would pass."""
+    p = batch.pointer_tables(force)
+    return p
+
+
+def walks_index(batch, eps, r_out, G, walk_slice=None):
+    """fp64 oracle over a WalkBatch (optionally a slice of walks); returns ForceSoft[sum n_epi]."""
+    force = new_force(batch.n_epi_total)
+    t = batch.pointer_tables(force, walk_slice)
+    oracle_lib().orc_walks_index(
+        t.n_walk, t.epi_ptrs.ctypes.data, t.n_epi.ctypes.data, t.id_epj_ptrs.ctypes.data, t.n_epj.ctypes.data,
+        t.id_spj_ptrs.ctypes.data, t.n_spj.ctypes.data, _chk(batch.epj, EPJSoft), _chk(batch.spj, SPJQuad),
+        t.force_ptrs.ctypes.data, eps, r_out, G)
+    return force
+
+
+def ref_walks_index(batch, eps, r_out, G, isa=None, n_threads=0, walk_slice=None, force=None):
+    """Reference SIMD CPU path over a WalkBatch; returns (ForceSoft[...], seconds)."""
+    force = new_force(batch.n_epi_total) if force is None else force
+    t = batch.pointer_tables(force, walk_slice)
+    sec = ref_lib(isa).ref_walks_index(
+        t.n_walk, t.epi_ptrs.ctypes.data, t.n_epi.ctypes.data, t.id_epj_ptrs.ctypes.data, t.n_epj.ctypes.data,
+        t.id_spj_ptrs.ctypes.data, t.n_spj.ctypes.data, _chk(batch.epj, EPJSoft), _chk(batch.spj, SPJQuad),
+        t.force_ptrs.ctypes.data, eps, r_out, G, int(n_threads))
+    return force, sec
+
+
+# ---- synthetic inputs ----------------------------------------------------------------------
+def make_plummer(n, mass_glb=1.0, eng=-0.25, rank_seed=0):
+    """reference makePlummerModel (src/particle_distribution_generator.hpp:173-250)."""
+    mass = np.empty(n)
+    pos = np.empty((n, 3))
+    vel = np.empty((n, 3))
+    oracle_lib().orc_make_plummer(mass_glb, n, n, mass.ctypes.data, pos.ctypes.data, vel.ctypes.data, eng, rank_seed)
+    return mass, pos, vel
+
+
+def simdtest_inputs(n_epi=1000, n_epj=2000, n_spj=1000):
+    """The input set of reference src/simd_test.cxx (r_out=0.01, eps=1e-4, G=1)."""
+    epi = np.zeros(n_epi, dtype=EPISoft)
+    epj = np.zeros(n_epj, dtype=EPJSoft)
+    spj = np.zeros(n_spj, dtype=SPJQuad)
+    L = oracle_lib()
+    L.orc_srand(1)  # glibc default seed, as an un-seeded rand() in the reference test
+    L.orc_simdtest_inputs(n_epi, n_epj, n_spj, epi.ctypes.data, epj.ctypes.data, spj.ctypes.data)
+    return epi, epj, spj
+
+
+SIMDTEST_PARAMS = dict(eps=1e-4, r_out=0.01, G=1.0)  # reference src/simd_test.cxx:65-67

@@ -1,0 +1,36 @@
+"""numpy mirrors of the PeTar/FDPS layouts that cross the soft-force boundary.
+
+Field-for-field equal to ``include/petar_b200_types.h`` (which cites the reference layouts:
+``src/soft_ptcl.hpp:4-24, 271-278, 311-326`` and FDPS ``SPJQuadrupoleInAndOut``).
+"""
+import numpy as np
+
+F64VEC = [("x", "<f8"), ("y", "<f8"), ("z", "<f8")]
+
+EPISoft = np.dtype(
+    [("id", "<i8"), ("pos", "<f8", (3,)), ("r_search", "<f8"), ("rank_org", "<i4"), ("type", "<i4")],
+    align=True,
+)
+EPJSoft = np.dtype(
+    [
+        ("id", "<i8"),
+        ("mass", "<f8"),
+        ("pos", "<f8", (3,)),
+        ("vel", "<f8", (3,)),
+        ("r_in", "<f8"),
+        ("r_out", "<f8"),
+        ("r_search", "<f8"),
+        ("r_scale_next", "<f8"),
+        ("group_data", "<i8", (2,)),
+        ("rank_org", "<i4"),
+        ("adr_org", "<i4"),
+    ],
+    align=True,
+)
+SPJQuad = np.dtype([("mass", "<f8"), ("pos", "<f8", (3,)), ("quad", "<f8", (6,))], align=True)  # xx,yy,zz,xy,xz,yz
+ForceSoft = np.dtype([("acc", "<f8", (3,)), ("pot", "<f8"), ("n_ngb", "<i8")], align=True)
+
+assert EPISoft.itemsize == 48
+assert EPJSoft.itemsize == 120
+assert SPJQuad.itemsize == 80
+assert ForceSoft.itemsize == 40
