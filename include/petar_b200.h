@@ -1,0 +1,189 @@
+/* petar_b200.h — C ABI of the B200-native soft-force engine (libpetar_b200.so).
+ *
+ * This is the drop-in boundary for PeTar's long-range soft-force hot path: the device side of
+ * FDPS `calcForceAllAndWriteBackMultiWalkIndex(dispatch, retrieve, ...)` that the reference
+ * implements in src/force_gpu_cuda.cu.  Every entry point takes plain pointers and sizes only
+ * (no FDPS, PeTar, CUDA or torch types); particle arrays are described by base pointer +
+ * stride + field offsets (pb_layout_*) so any build of PeTar's EPISoft / EPJSoft / SPJ /
+ * ForceSoft binds without recompiling this library.
+ *
+ * Which reference interface each entry point replaces:
+ *
+ *   pb_init             device selection + lazy allocation   src/force_gpu_cuda.cu:549-571
+ *   pb_set_params       functor state eps2, rcut2, G         src/force_gpu_cuda.hpp:103-118
+ *   pb_upload_j         dispatch(..., send_flag=true)        src/force_gpu_cuda.cu:577-620
+ *   pb_dispatch_index   dispatch(..., send_flag=false)       src/force_gpu_cuda.cu:621-699
+ *   pb_dispatch_direct  CalcForceWithLinearCutoffCUDA        src/force_gpu_cuda.cu:704-827
+ *   pb_retrieve         RetrieveForceCUDA                    src/force_gpu_cuda.cu:831-880
+ *   pb_get_profile      gpu_profile / gpu_counter            src/force_gpu_cuda.hpp:8-92,
+ *                                                            src/force_gpu_cuda.cu:610-617,672-697,836-863
+ *
+ * Call protocol (same as FDPS drives the reference): once per tree step
+ * pb_upload_j; then per walk group pb_dispatch_index (returns without waiting for the GPU; all
+ * host inputs have been consumed when it returns) followed later by pb_retrieve for that
+ * dispatch.  One dispatch may be outstanding at a time (FDPS tag_max = 1).
+ *
+ * All functions return 0 on success and a negative pb_status on failure; pb_last_error() then
+ * describes it.  Nothing here falls back to a CPU path: without a usable CUDA device every
+ * call fails with PB_ERR_NO_DEVICE.
+ */
+#ifndef PETAR_B200_H
+#define PETAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ABI_VERSION 1
+
+typedef enum pb_status {
+    PB_OK = 0,
+    PB_ERR_NO_DEVICE = -1,   /* no CUDA device / driver */
+    PB_ERR_CUDA      = -2,   /* a CUDA runtime call failed (message in pb_last_error) */
+    PB_ERR_ARG       = -3,   /* invalid argument */
+    PB_ERR_PROTOCOL  = -4,   /* call order violated (e.g. dispatch before upload_j) */
+    PB_ERR_NCCL      = -5
+} pb_status;
+
+/* ---- array layouts: byte stride of one element and byte offsets of the fields used ------ */
+typedef struct pb_layout_epi {      /* i-particles: EPISoft (reference src/soft_ptcl.hpp:271-278) */
+    size_t stride;
+    size_t off_pos;                 /* 3 x double */
+    size_t off_rsearch;             /* double */
+} pb_layout_epi;
+
+typedef struct pb_layout_epj {      /* j-particles: EPJSoft (reference src/soft_ptcl.hpp:311-326) */
+    size_t stride;
+    size_t off_pos;                 /* 3 x double */
+    size_t off_mass;                /* double */
+    size_t off_rsearch;             /* double */
+} pb_layout_epj;
+
+typedef struct pb_layout_spj {      /* superparticles: PS::SPJQuadrupoleInAndOut / SPJMonopoleInAndOut */
+    size_t stride;
+    size_t off_pos;                 /* 3 x double */
+    size_t off_mass;                /* double */
+    size_t off_quad;                /* 6 x double in the order xx,yy,zz,xy,xz,yz; ignored if !has_quad */
+    int    has_quad;                /* 0: monopole only (quadrupole terms are zero) */
+} pb_layout_spj;
+
+typedef struct pb_layout_force {    /* results: ForceSoft (reference src/soft_ptcl.hpp:4-15) */
+    size_t stride;
+    size_t off_acc;                 /* 3 x double, ASSIGNED */
+    size_t off_pot;                 /* double,     ASSIGNED */
+    size_t off_nngb;                /* int64,      ASSIGNED */
+} pb_layout_force;
+
+/* ---- profile / counters: the 4 timers + 5 counters of the reference's GPUProfile/GPUCounter,
+ *      same meaning, in seconds / counts accumulated since the last reset ------------------ */
+typedef struct pb_profile {
+    double t_copy;                  /* host-side pack / unpack (gpu_profile.copy) */
+    double t_send;                  /* H2D (gpu_profile.send), device-timed */
+    double t_recv;                  /* D2H (gpu_profile.recv), device-timed */
+    double t_calc;                  /* kernels (gpu_profile.calc), device-timed */
+    long long n_walk, n_epi, n_epj, n_spj, n_call;   /* gpu_counter.* */
+    long long n_interaction_ep;     /* sum n_epi*n_epj  (PeTar Ep-Ep_sum, src/petar.hpp:943-946) */
+    long long n_interaction_sp;     /* sum n_epi*n_spj  (PeTar Ep-Sp_sum) */
+    long long n_kernel_launch;      /* kernels launched by this library */
+    long long h2d_bytes, d2h_bytes;
+} pb_profile;
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+/* device < 0 selects my_rank % cudaGetDeviceCount(), as the reference does (:550-553).
+ * Idempotent; pb_upload_j / pb_dispatch_* call it lazily with (0,-1) if it was never called. */
+int  pb_init(int my_rank, int device);
+void pb_finalize(void);
+int  pb_abi_version(void);
+const char* pb_last_error(void);
+
+/* ---- parameters --------------------------------------------------------------------------- */
+/* eps2 = EPISoft::eps^2, rcut2 = EPISoft::r_out^2, G = ForceSoft::grav_const. */
+int  pb_set_params(double eps2, double rcut2, double G);
+
+/* Options (key, value):
+ *   "coords"     0 (default): positions relative to each walk's origin (centre of its i-particles),
+ *                   formed from fp64 on the host (i) and from a hi/lo fp32 split on the device (j);
+ *                1: absolute coordinates cast to fp32 — dx = float(xj) - float(xi), the exact
+ *                   arithmetic the reference kernel and the CPU changeover correction replay use
+ *                   (src/force_gpu_cuda.cu:58-60, src/hard.hpp:1346-1351).
+ *   "streams"    number of CUDA streams one dispatch is split across (default 2, 1..8).
+ *   "jchunk"     target EP j-chunk per warp-task (default 0 = automatic).
+ *   "nr"         Newton-Raphson steps after MUFU.RSQ (0 default, or 1).
+ *   "cull"       1 (default): skip the neighbour test for j-tile segments that cannot reach any
+ *                i-particle of the walk (results identical); 0: test every pair.
+ * Returns PB_ERR_ARG for an unknown key or value. */
+int  pb_set_option(const char* key, long long value);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/* send_flag == true: publish all j of this tree step.  Replaces any previous j set. */
+int  pb_upload_j(const void* epj, int n_epj, const pb_layout_epj* lepj,
+                 const void* spj, int n_spj, const pb_layout_spj* lspj);
+
+/* send_flag == false: enqueue n_walk walks.  epi[iw] -> n_epi[iw] i-particles, id_epj[iw] /
+ * id_spj[iw] -> indices into the arrays given to pb_upload_j.  Asynchronous w.r.t. the GPU. */
+int  pb_dispatch_index(int n_walk,
+                       const void* const* epi, const int* n_epi, const pb_layout_epi* lepi,
+                       const int* const* id_epj, const int* n_epj,
+                       const int* const* id_spj, const int* n_spj);
+
+/* Non-index mode: per-walk j arrays instead of indices (reference :704-827). */
+int  pb_dispatch_direct(int n_walk,
+                        const void* const* epi, const int* n_epi, const pb_layout_epi* lepi,
+                        const void* const* epj, const int* n_epj, const pb_layout_epj* lepj,
+                        const void* const* spj, const int* n_spj, const pb_layout_spj* lspj);
+
+/* Wait for the outstanding dispatch and ASSIGN force[iw][i].{acc,pot,n_ngb}, i < ni[iw].
+ * n_walk / ni must equal those of the dispatch being retrieved. */
+int  pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_force* lforce);
+
+/* ---- profiling ---------------------------------------------------------------------------- */
+int  pb_get_profile(pb_profile* out, int reset);
+
+/* ---- device-resident replay (measurement only) --------------------------------------------
+ * Between pb_record_begin and pb_record_end every dispatch also keeps its packed inputs
+ * resident in HBM.  pb_replay re-launches the kernels of all recorded dispatches n_iter times
+ * with no host<->device traffic, timed with CUDA events on the launching stream; it returns the
+ * mean milliseconds per iteration (all recorded dispatches) in *ms_total, and the part spent in
+ * the force kernel alone in *ms_force (either pointer may be NULL). */
+int  pb_record_begin(void);
+int  pb_record_end(void);
+int  pb_replay(int n_iter, float* ms_total, float* ms_force);
+/* number of force-kernel / reduce-kernel launches one replay iteration performs */
+int  pb_replay_launches(void);
+
+/* ---- multi-GPU: local-essential-tree j exchanged in device format --------------------------
+ * The j store can be assembled from a host part (this rank's own j, packed and uploaded by
+ * the library) and device-resident parts in the library's device j format that a collective
+ * (NCCL over NVLink) wrote directly into the store.
+ *
+ * Device j formats (little-endian fp32):
+ *   EPJ: 32 B = float4{x_hi,y_hi,z_hi,mass}, float4{x_lo,y_lo,z_lo,r_search}
+ *   SPJ: 64 B = float4{x_hi,y_hi,z_hi,mass}, float4{x_lo,y_lo,z_lo,qxx},
+ *               float4{qyy,qzz,qxy,qxz},     float4{qyz,trace,0,0}
+ * with x = x_hi + x_lo (x_hi = float(x), x_lo = float(x - x_hi)). */
+#define PB_EPJ_DEV_BYTES 32
+#define PB_SPJ_DEV_BYTES 64
+
+/* Size the store for n_epj/n_spj entries and return its device pointers (valid until the next
+ * pb_reserve_j / pb_upload_j / pb_finalize). */
+int  pb_reserve_j(int n_epj, int n_spj, void** d_epj, void** d_spj);
+/* Pack host j (as pb_upload_j) into store slots [epj_first, epj_first+n_epj) and
+ * [spj_first, spj_first+n_spj) of a store sized by pb_reserve_j. */
+int  pb_upload_j_range(const void* epj, int epj_first, int n_epj, const pb_layout_epj* lepj,
+                       const void* spj, int spj_first, int n_spj, const pb_layout_spj* lspj);
+/* Make the upload stream wait until work queued so far on `cuda_stream` (a cudaStream_t, e.g.
+ * the stream a NCCL collective writing into the store was enqueued on) has completed, and mark
+ * the j store as published. */
+int  pb_publish_j(void* cuda_stream);
+/* Pack host j to the device format into caller-provided HOST buffers (for building LET send
+ * buffers). */
+int  pb_pack_epj_host(const void* epj, int n, const pb_layout_epj* l, void* out32);
+int  pb_pack_spj_host(const void* spj, int n, const pb_layout_spj* l, void* out64);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PETAR_B200_H */

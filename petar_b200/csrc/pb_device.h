@@ -1,0 +1,75 @@
+// pb_device.h — device-side data layout shared by the kernels (pb_kernels.cu) and the host
+// engine (pb_engine.cu).  Nothing here is visible through the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pb {
+
+constexpr int kWarpsPerCta  = 8;                    // 256 threads
+constexpr int kThreads      = kWarpsPerCta * 32;
+constexpr int kTileJ        = kThreads;             // j staged per tile: one per thread
+constexpr int kTilePairs    = kTileJ / 2;           // the inner loops consume j in pairs (packed fp32x2)
+constexpr int kPairUnroll   = 4;                    // pairs per unrolled inner-loop step
+
+// One walk (= FDPS i-group with its interaction lists) of a dispatch.  64 B.
+struct __align__(16) Walk {
+    int   i_off;          // first i-particle in the dispatch's epi array
+    int   ni;             // number of i-particles
+    int   ej_off;         // first entry of this walk's EP index list in the dispatch's id array
+    int   nej;
+    int   sj_off;         // first entry of this walk's SP index list
+    int   nsj;
+    float ohx, ohy, ohz;  // walk origin, hi part  (origin = oh + ol; all zero in absolute-coordinate mode)
+    float olx, oly, olz;  // walk origin, lo part
+    float hx, hy, hz;     // half extent of the i-particles' bounding box about the origin (+inf: no culling)
+    float rsi2max;        // max r_search^2 over the walk's i-particles
+};
+
+// One CTA's work: a group of `nib` 32-wide i-blocks of one walk against a chunk of one of the
+// walk's two j lists; `jsplit` warps share each i-block and split every j tile between them
+// (nib * jsplit <= kWarpsPerCta).  32 B.
+struct __align__(16) Task {
+    int walk;
+    int i_first;          // first i of the group, relative to the walk (multiple of 32)
+    int nib;
+    int jsplit;
+    int kind;             // 0: EP-EP (linear cutoff + neighbour count), 1: EP-SP (quadrupole)
+    int j_begin;          // chunk start within the walk's list
+    int j_count;
+    int part_base;        // partial-sum slot of (i-block 0, lane 0) for this task
+};
+
+// One 32-wide i-block for the reduction kernel.  32 B.
+struct __align__(16) IBlock {
+    int part_base;        // slot of (chunk 0, lane 0)
+    int n_chunks;         // EP + SP chunks that produced partials for this i-block
+    int stride;           // slots between consecutive chunks
+    int out_off;          // index of lane 0 in the dispatch's output array
+    int n_valid;          // lanes that are real particles
+    int pad0, pad1, pad2;
+};
+
+// Result record, identical to PeTar's ForceSoft (reference src/soft_ptcl.hpp:4-15) so that the
+// D2H buffer can be memcpy'd straight into FDPS's force arrays.  40 B.
+struct ForceOut {
+    double  ax, ay, az, pot;
+    int64_t n_ngb;
+};
+
+struct Params {
+    float eps2;
+    float rcut2;
+};
+
+// launchers (pb_kernels.cu)
+cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps,
+                         const Walk* walks, const Task* tasks,
+                         const float4* epi, const int* id_epj, const int* id_spj,
+                         const float4* epj, const float4* spj,
+                         double4* part4, int* partn, Params p);
+
+cudaError_t launch_reduce(cudaStream_t s, int n_iblocks, const IBlock* iblocks,
+                          const double4* part4, const int* partn, ForceOut* out, double G);
+
+} // namespace pb

@@ -1,0 +1,461 @@
+// pb_kernels.cu — hand-written sm_100a kernels of the soft-force hot path.
+//
+// What they compute is what the reference's two kernels compute
+//   force_kernel_ep_ep / dev_gravity_ep_ep   reference src/force_gpu_cuda.cu:222-273 / :50-77
+//   force_kernel_ep_sp / dev_gravity_ep_sp   reference src/force_gpu_cuda.cu:465-511 / :276-323
+// (and, in fp64, the oracle functors src/soft_force.hpp:38-87, 160-200); how they compute it is
+// new:
+//
+//  * one launch for both interaction kinds; a CTA works on a Task = (i-group of a walk) x
+//    (chunk of that walk's EP or SP list); the host sizes tasks so that every CTA runs about the
+//    same number of inner-loop steps and there are several waves of CTAs on 148 SMs;
+//  * i-particles live in registers (one per lane), relative to the walk's origin;
+//  * j tiles (256 entries) are gathered by index with coalesced index reads and 16-byte loads
+//    from the L2-resident j store, shifted to the walk origin from their hi/lo fp32 split, and
+//    written to shared memory as PAIRS so the inner loop runs on packed fp32x2 instructions
+//    (FADD2 / FMUL2 / FFMA2, Blackwell only) — two interactions per issued FP instruction;
+//    the gather of tile k+1 and the index read of tile k+2 are in flight during tile k;
+//  * reciprocal square roots come from MUFU.RSQ (optionally refined by one Newton step);
+//  * forces/potentials are accumulated in fp32 per tile and folded across tiles with a
+//    compensated (Kahan-Babuska) sum; per-task results leave the SM as exact hi+lo doubles and a
+//    second tiny kernel adds the tasks' partials in fp64 in a fixed order (deterministic, no
+//    atomics), applies G and writes ForceSoft-shaped records.
+//  * no tensor cores: this is not a contraction.
+#include "pb_device.h"
+
+namespace pb {
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int NR>
+__device__ __forceinline__ float2 rsqrt2(float2 x) {
+    float2 y = make_float2(rsqrt_approx(x.x), rsqrt_approx(x.y));
+    if (NR >= 1) {
+        // y <- y * (1.5 - 0.5 x y^2)
+        float2 h  = __fmul2_rn(x, make_float2(-0.5f, -0.5f));
+        float2 y2 = __fmul2_rn(y, y);
+        float2 c  = __ffma2_rn(h, y2, make_float2(1.5f, 1.5f));
+        y = __fmul2_rn(y, c);
+    }
+    return y;
+}
+
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
+
+// compensated running sum (Kahan-Babuska / Neumaier): sum + comp carries the exact-ish total
+struct KSum {
+    float s, c;
+    __device__ __forceinline__ void init() { s = 0.f; c = 0.f; }
+    __device__ __forceinline__ void add(float v) {
+        float t = s + v;
+        float bp = t - s;
+        c += (s - (t - bp)) + (v - bp);   // two-sum error term
+        s = t;
+    }
+    __device__ __forceinline__ double value() const { return (double)s + (double)c; }
+};
+
+// ------------------------------------------------------------------------------------------
+// shared-memory tiles
+// ------------------------------------------------------------------------------------------
+struct EpTile {                       // 128 pairs, 40 B per pair
+    float4 a[kTilePairs];             // {x0, x1, y0, y1}
+    float4 b[kTilePairs];             // {z0, z1, m0, m1}
+    float2 c[kTilePairs];             // {r_search0^2, r_search1^2}
+};
+struct SpTile {                       // 128 pairs, 96 B per pair
+    float4 q0[kTilePairs];            // {x0, x1, y0, y1}
+    float4 q1[kTilePairs];            // {z0, z1, m0, m1}
+    float4 q2[kTilePairs];            // {qxx0, qxx1, qyy0, qyy1}
+    float4 q3[kTilePairs];            // {qzz0, qzz1, qxy0, qxy1}
+    float4 q4[kTilePairs];            // {qxz0, qxz1, qyz0, qyz1}
+    float4 q5[kTilePairs];            // {tr0, tr1, 0.5tr0, 0.5tr1}
+};
+union __align__(16) Smem {
+    EpTile ep[2];
+    SpTile sp[2];
+    double red[kWarpsPerCta][4][32];  // cross-warp combine when jsplit > 1
+};
+
+constexpr float kPadPos = 1.0e10f;    // padded j: far away, zero mass, never a neighbour
+
+// ------------------------------------------------------------------------------------------
+// EP-EP: clamped ("linear cutoff") Plummer force + neighbour count
+//   dx = xj - xi ; r2 = eps2 + dx.dx ; n += (r2 < max(rs_i, rs_j)^2)
+//   r2c = max(r2, rcut2) ; rinv = rsqrt(r2c) ; acc += m rinv^3 dx ; pot -= m rinv
+// (reference src/force_gpu_cuda.cu:58-74; G is applied once at the end, as soft_force.hpp:73-77)
+// ------------------------------------------------------------------------------------------
+struct EpRegs { float4 a, b; };       // one gathered j: {xh,yh,zh,m}, {xl,yl,zl,rs}
+
+__device__ __forceinline__ int ep_load_id(const int* __restrict__ ids, int j, int j_count) {
+    return (j < j_count) ? __ldg(ids + j) : -1;
+}
+__device__ __forceinline__ EpRegs ep_load_j(const float4* __restrict__ epj, int id) {
+    EpRegs r;
+    if (id >= 0) {
+        r.a = __ldg(epj + 2 * (size_t)id);
+        r.b = __ldg(epj + 2 * (size_t)id + 1);
+    } else {
+        r.a = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.b = make_float4(0.f, 0.f, 0.f, -1.f);
+    }
+    return r;
+}
+// writes j into the pair-interleaved tile; returns whether this j can be a neighbour of ANY
+// i-particle of the walk (distance from the i bounding box below max(rs_j, max rs_i), with a
+// safety margin far above fp32 rounding) — tiles segments without such a j skip the count.
+__device__ __forceinline__ bool ep_store(EpTile& t, int tid, int id, const EpRegs& r, const Walk& w) {
+    float x, y, z, m, rs2;
+    bool near = false;
+    if (id >= 0) {
+        x = (r.a.x - w.ohx) + (r.b.x - w.olx);
+        y = (r.a.y - w.ohy) + (r.b.y - w.oly);
+        z = (r.a.z - w.ohz) + (r.b.z - w.olz);
+        m = r.a.w;
+        rs2 = r.b.w * r.b.w;
+        const float ex = fmaxf(fabsf(x) - w.hx, 0.f);
+        const float ey = fmaxf(fabsf(y) - w.hy, 0.f);
+        const float ez = fmaxf(fabsf(z) - w.hz, 0.f);
+        const float d2 = ex * ex + ey * ey + ez * ez;      // hx = +inf (culling off): d2 = 0, always near
+        near = !(d2 * 0.999f >= fmaxf(rs2, w.rsi2max));
+    } else {
+        x = y = z = kPadPos; m = 0.f; rs2 = -1.f;
+    }
+    const int p = tid >> 1, s = tid & 1;
+    float* a = reinterpret_cast<float*>(&t.a[p]);
+    float* b = reinterpret_cast<float*>(&t.b[p]);
+    float* c = reinterpret_cast<float*>(&t.c[p]);
+    a[s] = x; a[2 + s] = y;
+    b[s] = z; b[2 + s] = m;
+    c[s] = rs2;
+    return near;
+}
+
+template <int NR, bool COUNT>
+__device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
+                                         float xi, float yi, float zi, float rsi2,
+                                         float eps2, float rcut2,
+                                         float2& ax, float2& ay, float2& az, float2& pt, float2& cf) {
+    const float2 nxi = bc(-xi), nyi = bc(-yi), nzi = bc(-zi), e2 = bc(eps2);
+#pragma unroll kPairUnroll
+    for (int p = p0; p < p1; ++p) {
+        const float4 A = t.a[p];
+        const float4 B = t.b[p];
+        const float2 dx = __fadd2_rn(make_float2(A.x, A.y), nxi);
+        const float2 dy = __fadd2_rn(make_float2(A.z, A.w), nyi);
+        const float2 dz = __fadd2_rn(make_float2(B.x, B.y), nzi);
+        float2 r2 = __ffma2_rn(dx, dx, e2);
+        r2 = __ffma2_rn(dy, dy, r2);
+        r2 = __ffma2_rn(dz, dz, r2);
+        if (COUNT) {
+            // neighbour flags as 0.0f/1.0f, summed packed; exact (counts per tile are tiny)
+            const float2 C = t.c[p];
+            const float2 f = make_float2((r2.x < fmaxf(C.x, rsi2)) ? 1.f : 0.f,
+                                         (r2.y < fmaxf(C.y, rsi2)) ? 1.f : 0.f);
+            cf = __fadd2_rn(cf, f);
+        }
+        const float2 r2c  = make_float2(fmaxf(r2.x, rcut2), fmaxf(r2.y, rcut2));
+        const float2 ri   = rsqrt2<NR>(r2c);
+        const float2 pij  = __fmul2_rn(make_float2(B.z, B.w), ri);
+        const float2 ri2  = __fmul2_rn(ri, ri);
+        const float2 mri3 = __fmul2_rn(pij, ri2);
+        ax = __ffma2_rn(mri3, dx, ax);
+        ay = __ffma2_rn(mri3, dy, ay);
+        az = __ffma2_rn(mri3, dz, az);
+        pt = __fadd2_rn(pt, pij);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// EP-SP: monopole + quadrupole of a superparticle; Q is the raw second-moment tensor
+//   dx = xi - xj ; r2 = eps2 + dx.dx ; qr = Q dx ; qrr = dx.qr
+//   A = m r^-3 - 1.5 tr r^-5 + 7.5 qrr r^-7 ; B = -3 r^-5
+//   acc -= A dx + B qr ; pot -= m r^-1 - 0.5 tr r^-3 + 1.5 qrr r^-5
+// (reference src/force_gpu_cuda.cu:283-308, same operation order)
+// ------------------------------------------------------------------------------------------
+struct SpRegs { float4 a, b, c, d; };  // {xh,yh,zh,m}, {xl,yl,zl,qxx}, {qyy,qzz,qxy,qxz}, {qyz,tr,-,-}
+
+__device__ __forceinline__ SpRegs sp_load_j(const float4* __restrict__ spj, int id) {
+    SpRegs r;
+    if (id >= 0) {
+        const float4* p = spj + 4 * (size_t)id;
+        r.a = __ldg(p); r.b = __ldg(p + 1); r.c = __ldg(p + 2); r.d = __ldg(p + 3);
+    } else {
+        r.a = r.b = r.c = r.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return r;
+}
+__device__ __forceinline__ void sp_store(SpTile& t, int tid, int id, const SpRegs& r, const Walk& w) {
+    float v[12];
+    if (id >= 0) {
+        v[0] = (r.a.x - w.ohx) + (r.b.x - w.olx);
+        v[1] = (r.a.y - w.ohy) + (r.b.y - w.oly);
+        v[2] = (r.a.z - w.ohz) + (r.b.z - w.olz);
+        v[3] = r.a.w;                                  // m
+        v[4] = r.b.w; v[5] = r.c.x; v[6] = r.c.y;      // qxx qyy qzz
+        v[7] = r.c.z; v[8] = r.c.w; v[9] = r.d.x;      // qxy qxz qyz
+        v[10] = r.d.y;                                 // tr = qxx+qyy+qzz (formed in fp64 on the host)
+        v[11] = 0.5f * r.d.y;
+    } else {
+        v[0] = v[1] = v[2] = kPadPos;
+#pragma unroll
+        for (int k = 3; k < 12; ++k) v[k] = 0.f;
+    }
+    const int p = tid >> 1, s = tid & 1;
+    float* q0 = reinterpret_cast<float*>(&t.q0[p]);
+    float* q1 = reinterpret_cast<float*>(&t.q1[p]);
+    float* q2 = reinterpret_cast<float*>(&t.q2[p]);
+    float* q3 = reinterpret_cast<float*>(&t.q3[p]);
+    float* q4 = reinterpret_cast<float*>(&t.q4[p]);
+    float* q5 = reinterpret_cast<float*>(&t.q5[p]);
+    q0[s] = v[0]; q0[2 + s] = v[1];
+    q1[s] = v[2]; q1[2 + s] = v[3];
+    q2[s] = v[4]; q2[2 + s] = v[5];
+    q3[s] = v[6]; q3[2 + s] = v[7];
+    q4[s] = v[8]; q4[2 + s] = v[9];
+    q5[s] = v[10]; q5[2 + s] = v[11];
+}
+
+template <int NR>
+__device__ __forceinline__ void sp_pairs(const SpTile& t, int p0, int p1,
+                                         float xi, float yi, float zi, float eps2,
+                                         float2& ax, float2& ay, float2& az, float2& pt) {
+    const float2 vxi = bc(xi), vyi = bc(yi), vzi = bc(zi), e2 = bc(eps2);
+#pragma unroll 2
+    for (int p = p0; p < p1; ++p) {
+        const float4 Q0 = t.q0[p], Q1 = t.q1[p], Q2 = t.q2[p], Q3 = t.q3[p], Q4 = t.q4[p], Q5 = t.q5[p];
+        const float2 xj = make_float2(Q0.x, Q0.y), yj = make_float2(Q0.z, Q0.w), zj = make_float2(Q1.x, Q1.y);
+        const float2 mj = make_float2(Q1.z, Q1.w);
+        const float2 qxx = make_float2(Q2.x, Q2.y), qyy = make_float2(Q2.z, Q2.w);
+        const float2 qzz = make_float2(Q3.x, Q3.y), qxy = make_float2(Q3.z, Q3.w);
+        const float2 qxz = make_float2(Q4.x, Q4.y), qyz = make_float2(Q4.z, Q4.w);
+        const float2 tr  = make_float2(Q5.x, Q5.y), htr = make_float2(Q5.z, Q5.w);
+        const float2 dx = __fadd2_rn(vxi, make_float2(-xj.x, -xj.y));
+        const float2 dy = __fadd2_rn(vyi, make_float2(-yj.x, -yj.y));
+        const float2 dz = __fadd2_rn(vzi, make_float2(-zj.x, -zj.y));
+        float2 r2 = __ffma2_rn(dx, dx, e2);
+        r2 = __ffma2_rn(dy, dy, r2);
+        r2 = __ffma2_rn(dz, dz, r2);
+        const float2 rinv = rsqrt2<NR>(r2);
+        float2 qrx = __fmul2_rn(qxx, dx); qrx = __ffma2_rn(qxy, dy, qrx); qrx = __ffma2_rn(qxz, dz, qrx);
+        float2 qry = __fmul2_rn(qxy, dx); qry = __ffma2_rn(qyy, dy, qry); qry = __ffma2_rn(qyz, dz, qry);
+        float2 qrz = __fmul2_rn(qxz, dx); qrz = __ffma2_rn(qyz, dy, qrz); qrz = __ffma2_rn(qzz, dz, qrz);
+        float2 qrr = __fmul2_rn(qrx, dx); qrr = __ffma2_rn(qry, dy, qrr); qrr = __ffma2_rn(qrz, dz, qrr);
+        const float2 rinv2  = __fmul2_rn(rinv, rinv);
+        const float2 rinv3  = __fmul2_rn(rinv2, rinv);
+        const float2 rinv5  = __fmul2_rn(__fmul2_rn(rinv2, rinv3), bc(1.5f));
+        const float2 qrr_r5 = __fmul2_rn(rinv5, qrr);
+        const float2 qrr_r7 = __fmul2_rn(rinv2, qrr_r5);
+        float2 A = __fmul2_rn(mj, rinv3);
+        A = __ffma2_rn(make_float2(-tr.x, -tr.y), rinv5, A);
+        A = __ffma2_rn(bc(5.0f), qrr_r7, A);
+        const float2 nB = __fmul2_rn(bc(2.0f), rinv5);                 // -B
+        // acc -= A dx + B qr   ==   acc += (-A) dx + (-B) qr
+        const float2 nA = make_float2(-A.x, -A.y);
+        ax = __ffma2_rn(nA, dx, ax); ax = __ffma2_rn(nB, qrx, ax);
+        ay = __ffma2_rn(nA, dy, ay); ay = __ffma2_rn(nB, qry, ay);
+        az = __ffma2_rn(nA, dz, az); az = __ffma2_rn(nB, qrz, az);
+        // pot accumulates +(m r^-1 - 0.5 tr r^-3 + 1.5 qrr r^-5); negated at the end
+        float2 ph = __fmul2_rn(mj, rinv);
+        ph = __ffma2_rn(make_float2(-htr.x, -htr.y), rinv3, ph);
+        ph = __fadd2_rn(ph, qrr_r5);
+        pt = __fadd2_rn(pt, ph);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the force kernel
+// ------------------------------------------------------------------------------------------
+template <int NR>
+__global__ void __launch_bounds__(kThreads, 2)
+force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
+             const float4* __restrict__ epi,
+             const int* __restrict__ id_epj, const int* __restrict__ id_spj,
+             const float4* __restrict__ epj, const float4* __restrict__ spj,
+             double4* __restrict__ part4, int* __restrict__ partn, Params prm)
+{
+    __shared__ Smem sm;
+    __shared__ int near_flag[2][kWarpsPerCta];   // per tile buffer, per staging warp (= 16-pair segment)
+
+    const Task task = tasks[blockIdx.x];
+    const Walk w    = walks[task.walk];
+    const int tid   = threadIdx.x;
+    const int warp  = tid >> 5, lane = tid & 31;
+
+    // warp role: i-block `ib` of the group, j-split slot `js`
+    const bool busy = warp < task.nib * task.jsplit;
+    const int  ib   = busy ? warp % task.nib : 0;
+    const int  js   = busy ? warp / task.nib : 0;
+    const int  ppw  = kTilePairs / task.jsplit;             // pairs of each tile this warp consumes
+
+    // i-particle (registers): relative to the walk origin already (host formed x_i - origin in fp64)
+    const int  i_loc  = task.i_first + ib * 32 + lane;
+    const bool ivalid = busy && (i_loc < w.ni);
+    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ivalid) pi = __ldg(epi + w.i_off + i_loc);
+    const float rsi2 = ivalid ? pi.w * pi.w : -1.f;
+
+    KSum kx, ky, kz, kp;
+    kx.init(); ky.init(); kz.init(); kp.init();
+    int cnt = 0;
+
+    const int n_tiles = (task.j_count + kTileJ - 1) / kTileJ;
+
+    if (task.kind == 0) {
+        const int* ids = id_epj + w.ej_off + task.j_begin;
+        // software pipeline: ids run two tiles ahead, gathered j one tile ahead
+        int id_cur = ep_load_id(ids, tid, task.j_count);
+        EpRegs jr  = ep_load_j(epj, id_cur);
+        int id_nxt = ep_load_id(ids, kTileJ + tid, task.j_count);
+        {
+            const bool nr_ = ep_store(sm.ep[0], tid, id_cur, jr, w);
+            const unsigned bal = __ballot_sync(0xffffffffu, nr_);
+            if (lane == 0) near_flag[0][warp] = (bal != 0u);
+        }
+        __syncthreads();
+        for (int k = 0; k < n_tiles; ++k) {
+            const bool more = (k + 1 < n_tiles);
+            if (more) jr = ep_load_j(epj, id_nxt);
+            const int id_nn = ep_load_id(ids, (k + 2) * kTileJ + tid, task.j_count);
+            if (busy) {
+                const int nv  = min(kTileJ, task.j_count - k * kTileJ);
+                const int npu = (((nv + 1) >> 1) + kPairUnroll - 1) & ~(kPairUnroll - 1);
+                const int p0  = js * ppw, p1 = min(p0 + ppw, npu);
+                float2 ax = bc(0.f), ay = bc(0.f), az = bc(0.f), pt = bc(0.f), cf = bc(0.f);
+                // 16-pair segments = the 32 j one staging warp wrote; count only where flagged
+                for (int seg = p0; seg < p1; seg += 16) {
+                    const int e = min(seg + 16, p1);
+                    if (near_flag[k & 1][seg >> 4])
+                        ep_pairs<NR, true>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                    else
+                        ep_pairs<NR, false>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                }
+                kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
+                cnt += (int)(cf.x + cf.y);
+            }
+            if (more) {
+                const bool nr_ = ep_store(sm.ep[(k + 1) & 1], tid, id_nxt, jr, w);
+                const unsigned bal = __ballot_sync(0xffffffffu, nr_);
+                if (lane == 0) near_flag[(k + 1) & 1][warp] = (bal != 0u);
+            }
+            id_nxt = id_nn;
+            __syncthreads();
+        }
+    } else {
+        const int* ids = id_spj + w.sj_off + task.j_begin;
+        int id_cur = ep_load_id(ids, tid, task.j_count);
+        SpRegs jr  = sp_load_j(spj, id_cur);
+        int id_nxt = ep_load_id(ids, kTileJ + tid, task.j_count);
+        sp_store(sm.sp[0], tid, id_cur, jr, w);
+        __syncthreads();
+        for (int k = 0; k < n_tiles; ++k) {
+            const bool more = (k + 1 < n_tiles);
+            if (more) jr = sp_load_j(spj, id_nxt);
+            const int id_nn = ep_load_id(ids, (k + 2) * kTileJ + tid, task.j_count);
+            if (busy) {
+                const int nv  = min(kTileJ, task.j_count - k * kTileJ);
+                const int npu = (((nv + 1) >> 1) + 1) & ~1;
+                const int p0  = js * ppw, p1 = min(p0 + ppw, npu);
+                float2 ax = bc(0.f), ay = bc(0.f), az = bc(0.f), pt = bc(0.f);
+                sp_pairs<NR>(sm.sp[k & 1], p0, p1, pi.x, pi.y, pi.z, prm.eps2, ax, ay, az, pt);
+                kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
+            }
+            if (more) sp_store(sm.sp[(k + 1) & 1], tid, id_nxt, jr, w);
+            id_nxt = id_nn;
+            __syncthreads();
+        }
+    }
+
+    // per-warp totals as exact doubles (hi + lo)
+    double dax = kx.value(), day = ky.value(), daz = kz.value(), dpt = kp.value();
+
+    if (task.jsplit > 1) {
+        // combine the jsplit warps that share an i-block, in fixed order js = 0,1,...
+        // (the loop above ended with __syncthreads, so the tile buffers may be reused)
+        if (busy) {
+            sm.red[warp][0][lane] = dax; sm.red[warp][1][lane] = day;
+            sm.red[warp][2][lane] = daz; sm.red[warp][3][lane] = dpt;
+        }
+        // neighbour counts ride in a second pass to keep the scratch small
+        __syncthreads();
+        if (busy && js == 0) {
+            for (int s = 1; s < task.jsplit; ++s) {
+                const int ww = s * task.nib + ib;
+                dax += sm.red[ww][0][lane]; day += sm.red[ww][1][lane];
+                daz += sm.red[ww][2][lane]; dpt += sm.red[ww][3][lane];
+            }
+        }
+        __syncthreads();
+        int* redn = reinterpret_cast<int*>(&sm.red[0][0][0]);
+        if (busy) redn[warp * 32 + lane] = cnt;
+        __syncthreads();
+        if (busy && js == 0)
+            for (int s = 1; s < task.jsplit; ++s) cnt += redn[(s * task.nib + ib) * 32 + lane];
+    }
+
+    if (busy && js == 0) {
+        const int slot = task.part_base + ib * 32 + lane;
+        part4[slot] = make_double4(dax, day, daz, dpt);
+        partn[slot] = cnt;
+    }
+}
+
+cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps,
+                         const Walk* walks, const Task* tasks,
+                         const float4* epi, const int* id_epj, const int* id_spj,
+                         const float4* epj, const float4* spj,
+                         double4* part4, int* partn, Params p)
+{
+    if (n_tasks <= 0) return cudaSuccess;
+    if (nr_steps >= 1)
+        force_kernel<1><<<n_tasks, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
+    else
+        force_kernel<0><<<n_tasks, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// reduction: one warp per 32-wide i-block adds that block's task partials in fp64, chunk order
+// fixed, applies G and writes ForceSoft-shaped records.
+//   acc = G * sum ; pot = -G * sum(pot terms)   (signs: see the pair loops above)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+reduce_kernel(int n_iblocks, const IBlock* __restrict__ iblocks,
+              const double4* __restrict__ part4, const int* __restrict__ partn,
+              ForceOut* __restrict__ out, double G)
+{
+    const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= n_iblocks) return;
+    const IBlock ibk = iblocks[b];
+    if (lane >= ibk.n_valid) return;
+    double ax = 0.0, ay = 0.0, az = 0.0, pt = 0.0;
+    long long n = 0;
+    for (int c = 0; c < ibk.n_chunks; ++c) {
+        const int slot = ibk.part_base + c * ibk.stride + lane;
+        const double4 v = part4[slot];
+        ax += v.x; ay += v.y; az += v.z; pt += v.w;
+        n += partn[slot];
+    }
+    ForceOut o;
+    o.ax = G * ax; o.ay = G * ay; o.az = G * az; o.pot = -(G * pt); o.n_ngb = n;
+    out[ibk.out_off + lane] = o;
+}
+
+cudaError_t launch_reduce(cudaStream_t s, int n_iblocks, const IBlock* iblocks,
+                          const double4* part4, const int* partn, ForceOut* out, double G)
+{
+    if (n_iblocks <= 0) return cudaSuccess;
+    const int wpb = 8;
+    reduce_kernel<<<(n_iblocks + wpb - 1) / wpb, wpb * 32, 0, s>>>(n_iblocks, iblocks, part4, partn, out, G);
+    return cudaGetLastError();
+}
+
+} // namespace pb

@@ -1,0 +1,231 @@
+"""Python face of the native soft-force engine.
+
+Two layers, both thin:
+
+* :data:`lib` — the raw C ABI of ``libpetar_b200.so`` (``include/petar_b200.h``) via ctypes.
+* :class:`CalcForceWithLinearCutoffCUDAMultiWalk` / :func:`RetrieveForceCUDA` — the reference's
+  dispatch / retrieve functors (``src/force_gpu_cuda.hpp:103-133, 165-168``) with the same names,
+  argument order and meaning, routed through the C++ shim ``force_gpu_b200.cpp`` (the object that
+  replaces ``build/force_gpu_cuda.o``) so that tests drive the very symbols PeTar would link.
+* :func:`calc_force_all_and_write_back` — the loop FDPS ``calcForceAllAndWriteBackMultiWalkIndex``
+  runs around those functors (call site ``src/petar.hpp:894-899``) over a prebuilt
+  :class:`~petar_b200.walks.WalkBatch`.
+
+There is no CPU fallback anywhere in this module: if the native libraries are missing it raises,
+and without a CUDA device every call fails with ``PB_ERR_NO_DEVICE``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .types import EPISoft, EPJSoft, SPJQuad, ForceSoft
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.join(_HERE, "lib")
+
+_vp = C.c_void_p
+
+
+class PbError(RuntimeError):
+    def __init__(self, code, where, msg):
+        super().__init__(f"{where} failed ({code}): {msg}")
+        self.code = code
+
+
+class LayoutEpi(C.Structure):
+    _fields_ = [("stride", C.c_size_t), ("off_pos", C.c_size_t), ("off_rsearch", C.c_size_t)]
+
+
+class LayoutEpj(C.Structure):
+    _fields_ = [("stride", C.c_size_t), ("off_pos", C.c_size_t), ("off_mass", C.c_size_t), ("off_rsearch", C.c_size_t)]
+
+
+class LayoutSpj(C.Structure):
+    _fields_ = [("stride", C.c_size_t), ("off_pos", C.c_size_t), ("off_mass", C.c_size_t), ("off_quad", C.c_size_t), ("has_quad", C.c_int)]
+
+
+class LayoutForce(C.Structure):
+    _fields_ = [("stride", C.c_size_t), ("off_acc", C.c_size_t), ("off_pot", C.c_size_t), ("off_nngb", C.c_size_t)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("t_copy", C.c_double), ("t_send", C.c_double), ("t_recv", C.c_double), ("t_calc", C.c_double),
+                ("n_walk", C.c_longlong), ("n_epi", C.c_longlong), ("n_epj", C.c_longlong), ("n_spj", C.c_longlong),
+                ("n_call", C.c_longlong), ("n_interaction_ep", C.c_longlong), ("n_interaction_sp", C.c_longlong),
+                ("n_kernel_launch", C.c_longlong), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _off(dt, name):
+    return dt.fields[name][1]
+
+
+LAYOUT_EPI = LayoutEpi(EPISoft.itemsize, _off(EPISoft, "pos"), _off(EPISoft, "r_search"))
+LAYOUT_EPJ = LayoutEpj(EPJSoft.itemsize, _off(EPJSoft, "pos"), _off(EPJSoft, "mass"), _off(EPJSoft, "r_search"))
+LAYOUT_SPJ = LayoutSpj(SPJQuad.itemsize, _off(SPJQuad, "pos"), _off(SPJQuad, "mass"), _off(SPJQuad, "quad"), 1)
+LAYOUT_FORCE = LayoutForce(ForceSoft.itemsize, _off(ForceSoft, "acc"), _off(ForceSoft, "pot"), _off(ForceSoft, "n_ngb"))
+
+# every symbol include/petar_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "pb_init", "pb_finalize", "pb_abi_version", "pb_last_error", "pb_set_params", "pb_set_option",
+    "pb_upload_j", "pb_dispatch_index", "pb_dispatch_direct", "pb_retrieve", "pb_get_profile",
+    "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
+    "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_spj_host",
+]
+
+_lib = None
+_shim = None
+_shim_direct = None
+
+
+def _need(path):
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"native library {path} is missing: build it with `python -m petar_b200.build` "
+            "(petar_b200 has no CPU fallback)")
+    return path
+
+
+def load():
+    """Load libpetar_b200.so and declare the C ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = C.CDLL(_need(os.path.join(LIBDIR, "libpetar_b200.so")), mode=C.RTLD_GLOBAL)
+    L.pb_init.argtypes = [C.c_int, C.c_int]
+    L.pb_finalize.restype = None
+    L.pb_last_error.restype = C.c_char_p
+    L.pb_set_params.argtypes = [C.c_double, C.c_double, C.c_double]
+    L.pb_set_option.argtypes = [C.c_char_p, C.c_longlong]
+    L.pb_upload_j.argtypes = [_vp, C.c_int, C.POINTER(LayoutEpj), _vp, C.c_int, C.POINTER(LayoutSpj)]
+    L.pb_dispatch_index.argtypes = [C.c_int, _vp, _vp, C.POINTER(LayoutEpi), _vp, _vp, _vp, _vp]
+    L.pb_dispatch_direct.argtypes = [C.c_int, _vp, _vp, C.POINTER(LayoutEpi), _vp, _vp, C.POINTER(LayoutEpj), _vp, _vp, C.POINTER(LayoutSpj)]
+    L.pb_retrieve.argtypes = [C.c_int, _vp, _vp, C.POINTER(LayoutForce)]
+    L.pb_get_profile.argtypes = [C.POINTER(Profile), C.c_int]
+    L.pb_replay.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.pb_reserve_j.argtypes = [C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]
+    L.pb_upload_j_range.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(LayoutEpj), _vp, C.c_int, C.c_int, C.POINTER(LayoutSpj)]
+    L.pb_publish_j.argtypes = [_vp]
+    L.pb_pack_epj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutEpj), _vp]
+    L.pb_pack_spj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutSpj), _vp]
+    _lib = L
+    return L
+
+
+def load_shim(direct=False):
+    """Load the C++ shim that defines PeTar's functor symbols (index or non-index build)."""
+    global _shim, _shim_direct
+    load()
+    if direct:
+        if _shim_direct is None:
+            S = C.CDLL(_need(os.path.join(LIBDIR, "libpetar_b200_shim_direct.so")))
+            S.pb_shim_dispatch_direct.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                                  _vp, _vp, _vp, _vp, _vp, _vp]
+            S.pb_shim_retrieve.argtypes = [C.c_int, C.c_int, _vp, _vp]
+            _shim_direct = S
+        return _shim_direct
+    if _shim is None:
+        S = C.CDLL(_need(os.path.join(LIBDIR, "libpetar_b200_shim.so")))
+        S.pb_shim_dispatch.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int]
+        S.pb_shim_retrieve.argtypes = [C.c_int, C.c_int, _vp, _vp]
+        S.pb_shim_profile.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
+        S.pb_shim_profile.restype = None
+        _shim = S
+    return _shim
+
+
+def check(rc, where):
+    if rc != 0:
+        raise PbError(rc, where, load().pb_last_error().decode())
+
+
+def set_option(key, value):
+    check(load().pb_set_option(key.encode(), int(value)), f"pb_set_option({key})")
+
+
+def get_profile(reset=False):
+    p = Profile()
+    load().pb_get_profile(C.byref(p), int(reset))
+    return p.as_dict()
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None and len(a) else None
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's functor interface (src/force_gpu_cuda.hpp), same names and argument order
+# ---------------------------------------------------------------------------------------------
+class CalcForceWithLinearCutoffCUDAMultiWalk:
+    """Dispatch functor, index mode.  State is only (my_rank, eps2, rcut2, G), as in the reference;
+    PeTar constructs a temporary of it every tree step (src/petar.hpp:894)."""
+
+    def __init__(self, my_rank=0, eps2=0.0, rcut2=0.0, G=1.0):
+        self.initialize(my_rank, eps2, rcut2, G)
+
+    def initialize(self, my_rank, eps2, rcut2, G):
+        self.my_rank, self.eps2, self.rcut2, self.G = int(my_rank), float(eps2), float(rcut2), float(G)
+
+    def __call__(self, tag, n_walk, epi, n_epi, id_epj, n_epj, id_spj, n_spj, epj, n_epj_tot, spj, n_spj_tot, send_flag):
+        """epi / id_epj / id_spj: uint64 arrays of per-walk pointers; n_*: int32 arrays;
+        epj / spj: the shared sorted arrays (EPJSoft / SPJQuad)."""
+        S = load_shim()
+        assert epj.dtype == EPJSoft and spj.dtype == SPJQuad
+        return S.pb_shim_dispatch(self.my_rank, self.eps2, self.rcut2, self.G, int(tag), int(n_walk),
+                                  _ptr(epi), _ptr(n_epi), _ptr(id_epj), _ptr(n_epj), _ptr(id_spj), _ptr(n_spj),
+                                  _ptr(epj), int(n_epj_tot), _ptr(spj), int(n_spj_tot), int(bool(send_flag)))
+
+
+class CalcForceWithLinearCutoffCUDA:
+    """Dispatch functor, non-index mode: per-walk j arrays (src/force_gpu_cuda.hpp:137-162)."""
+
+    def __init__(self, my_rank=0, eps2=0.0, rcut2=0.0, G=1.0):
+        self.my_rank, self.eps2, self.rcut2, self.G = int(my_rank), float(eps2), float(rcut2), float(G)
+
+    def __call__(self, tag, n_walk, epi, n_epi, epj, n_epj, spj, n_spj):
+        S = load_shim(direct=True)
+        return S.pb_shim_dispatch_direct(self.my_rank, self.eps2, self.rcut2, self.G, int(tag), int(n_walk),
+                                         _ptr(epi), _ptr(n_epi), _ptr(epj), _ptr(n_epj), _ptr(spj), _ptr(n_spj))
+
+
+def RetrieveForceCUDA(tag, n_walk, ni, force, direct=False):
+    """Retrieve functor (src/force_gpu_cuda.hpp:165-168): ASSIGNS force[iw][i].{acc,pot,n_ngb}."""
+    return load_shim(direct).pb_shim_retrieve(int(tag), int(n_walk), _ptr(ni), _ptr(force))
+
+
+# ---------------------------------------------------------------------------------------------
+# what FDPS does around the functors
+# ---------------------------------------------------------------------------------------------
+N_WALK_LIMIT = 200   # reference src/petar.hpp:888
+
+
+def calc_force_all_and_write_back(batch, eps, r_out, G, n_walk_limit=N_WALK_LIMIT, my_rank=0, force=None, send=True):
+    """Emulates ``tree_soft.calcForceAllAndWriteBackMultiWalkIndex(dispatch, retrieve, 1, ..., n_walk_limit)``
+    (src/petar.hpp:888-899) over a prebuilt WalkBatch: one dispatch with send_flag=true publishing all
+    j, then per walk group dispatch(send_flag=false) and — after the next group's lists would have
+    been built — retrieve of the previous group.  Returns ForceSoft[n_epi_total]."""
+    f = np.zeros(batch.n_epi_total, dtype=ForceSoft) if force is None else force
+    disp = CalcForceWithLinearCutoffCUDAMultiWalk(my_rank, eps * eps, r_out * r_out, G)
+    none_u64 = np.zeros(0, dtype=np.uint64)
+    none_i32 = np.zeros(0, dtype=np.int32)
+    if send:
+        rc = disp(0, 0, none_u64, none_i32, none_u64, none_i32, none_u64, none_i32,
+                  batch.epj, len(batch.epj), batch.spj, len(batch.spj), True)
+        assert rc == 0
+    prev = None
+    for w0 in range(0, batch.n_walk, n_walk_limit):
+        t = batch.pointer_tables(f, slice(w0, min(w0 + n_walk_limit, batch.n_walk)))
+        if prev is not None:
+            RetrieveForceCUDA(0, prev.n_walk, prev.n_epi, prev.force_ptrs)
+        disp = CalcForceWithLinearCutoffCUDAMultiWalk(my_rank, eps * eps, r_out * r_out, G)
+        rc = disp(0, t.n_walk, t.epi_ptrs, t.n_epi, t.id_epj_ptrs, t.n_epj, t.id_spj_ptrs, t.n_spj,
+                  batch.epj, len(batch.epj), batch.spj, len(batch.spj), False)
+        assert rc == 0
+        prev = t
+    if prev is not None:
+        RetrieveForceCUDA(0, prev.n_walk, prev.n_epi, prev.force_ptrs)
+    return f

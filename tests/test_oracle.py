@@ -1,0 +1,216 @@
+"""CPU tests of the checker itself: the fp64 oracle against the reference's own kernels (golden
+fixtures generated from oracle/_ref, and oracle/_ref live where it exists) and against analytic
+known answers."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from petar_b200.types import EPISoft, EPJSoft, SPJQuad, ForceSoft
+from conftest import GOLDEN
+
+P = ob.SIMDTEST_PARAMS
+
+
+def _rel_acc(a, b):
+    return np.abs(a["acc"] - b["acc"]).max(axis=1) / np.linalg.norm(b["acc"], axis=1)
+
+
+def _mk_epi(pos, rs):
+    e = np.zeros(len(pos), dtype=EPISoft)
+    e["pos"] = pos
+    e["r_search"] = rs
+    e["type"] = 1
+    e["id"] = np.arange(len(pos)) + 1
+    return e
+
+
+def _mk_epj(pos, mass, rs):
+    e = np.zeros(len(pos), dtype=EPJSoft)
+    e["pos"] = pos
+    e["mass"] = mass
+    e["r_search"] = rs
+    e["id"] = np.arange(len(pos)) + 1
+    return e
+
+
+# ---- golden vectors -------------------------------------------------------------------------
+def test_mt19937_known_answer():
+    """10000th output of mt19937 seeded with 5489 is 4123659995 (C++11 [rand.predef])."""
+    import ctypes as C
+    L = ob.oracle_lib()
+    st = (C.c_uint32 * 625)()
+    L.orc_mt_init(st, 5489)
+    v = 0
+    for _ in range(10000):
+        v = L.orc_mt_int32(st)
+    assert v == 4123659995
+
+
+def test_simdtest_inputs_reproduce_golden():
+    g = np.load(os.path.join(GOLDEN, "simdtest.npz"))
+    epi, epj, spj = ob.simdtest_inputs()
+    assert np.array_equal(epi["pos"][:4], g["epi_pos_head"])
+    assert np.array_equal(spj[:2], g["spj_head"])
+    # recipe facts of src/simd_test.cxx: N=2000 equal masses, r_search = r_out = 0.01 for everyone
+    assert np.all(epj["mass"] == 1.0 / 2000) and np.all(epi["r_search"] == 0.01)
+    assert 1.0 <= spj["pos"].min() and spj["pos"].max() <= 11.0
+
+
+def test_oracle_matches_golden_bitwise():
+    g = np.load(os.path.join(GOLDEN, "simdtest.npz"))
+    epi, epj, spj = ob.simdtest_inputs()
+    ep = ob.force_epep(epi, epj, P["eps"], P["r_out"], P["G"])
+    sp = ob.force_epsp_quad(epi, spj, P["eps"], P["G"])
+    for k in ("acc", "pot", "n_ngb"):
+        assert np.array_equal(ep[k], g["oracle_ep"][k])
+        assert np.array_equal(sp[k], g["oracle_sp"][k])
+
+
+@pytest.mark.parametrize("isa", ["avx2", "avx512"])
+def test_oracle_vs_reference_simd_golden(isa):
+    """The fp64 restatement agrees with the reference's own fp32 SIMD kernels to the SIMD kernels'
+    precision: EP-EP (rsqrt + one Newton step) ~1e-6, EP-SP (raw rsqrt, no Newton step) within the
+    reference test's own 7e-3 print threshold (src/simd_test.cxx:68); neighbour counts identical."""
+    g = np.load(os.path.join(GOLDEN, "simdtest.npz"))
+    ep, sp = g["oracle_ep"], g["oracle_sp"]
+    rep, rsp = g[f"ref_{isa}_ep"], g[f"ref_{isa}_sp"]
+    assert _rel_acc(rep, ep).max() < 2e-5 and np.median(_rel_acc(rep, ep)) < 2e-6
+    assert np.abs((rep["pot"] - ep["pot"]) / ep["pot"]).max() < 1e-5
+    assert _rel_acc(rsp, sp).max() < 7e-3
+    assert np.abs((rsp["pot"] - sp["pot"]) / sp["pot"]).max() < 1e-2
+    assert np.array_equal(rep["n_ngb"], ep["n_ngb"])
+    assert np.array_equal(g[f"ref_{isa}_nb"]["n_ngb"], g["oracle_nb"]["n_ngb"])
+
+
+@pytest.mark.skipif(not ob.ref_available("avx2"), reason="oracle/_ref not built (no /root/reference here)")
+def test_reference_simd_live_equals_golden():
+    g = np.load(os.path.join(GOLDEN, "simdtest.npz"))
+    epi, epj, spj = ob.simdtest_inputs()
+    rep = ob.ref_force_epep(epi, epj, P["eps"], P["r_out"], P["G"], isa="avx2")
+    assert np.allclose(rep["acc"], g["ref_avx2_ep"]["acc"], rtol=0, atol=0)
+    assert np.array_equal(rep["n_ngb"], g["ref_avx2_ep"]["n_ngb"])
+
+
+def test_plummer1k_walks_golden():
+    from petar_b200 import harness as hz
+    g = np.load(os.path.join(GOLDEN, "plummer1k_walks.npz"))
+    batch, _, prm, _ = hz.plummer_case(1000)
+    assert batch.n_walk == int(g["n_walk"]) and np.array_equal(batch.ej_off, g["ej_off"])
+    f = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"])
+    assert np.array_equal(f["n_ngb"], g["oracle"]["n_ngb"])
+    assert np.allclose(f["acc"], g["oracle"]["acc"], rtol=1e-13, atol=0)
+    # reference SIMD path on the same lists (all masses > 0, all types 1: no filtering differences)
+    for isa in ("avx2", "avx512"):
+        r = g[f"ref_{isa}"]
+        assert np.array_equal(r["n_ngb"], f["n_ngb"])
+        assert np.median(_rel_acc(r, f)) < 1e-4      # dominated by the no-Newton-step SP kernel
+
+
+# ---- analytic known answers -----------------------------------------------------------------
+def test_two_body_outside_cutoff():
+    epi = _mk_epi([[0.0, 0, 0]], 0.1)
+    epj = _mk_epj([[3.0, 4.0, 0.0]], [2.0], 0.1)
+    f = ob.force_epep(epi, epj, 0.0, 0.5, 1.5)
+    assert np.allclose(f["acc"][0], 1.5 * 2.0 / 125.0 * np.array([3.0, 4.0, 0.0]), rtol=1e-15)
+    assert np.isclose(f["pot"][0], -1.5 * 2.0 / 5.0, rtol=1e-15)
+    assert f["n_ngb"][0] == 0
+
+
+def test_self_only_list():
+    """i in its own list: zero force, pot = -G m / r_out (clamp), counted as neighbour (SURVEY §7 hard part 2)."""
+    epi = _mk_epi([[0.3, -0.2, 0.9]], 0.02)
+    epj = _mk_epj([[0.3, -0.2, 0.9]], [1e-3], 0.02)
+    f = ob.force_epep(epi, epj, 0.0, 0.01, 1.0)
+    assert np.all(f["acc"][0] == 0.0)
+    assert np.isclose(f["pot"][0], -1e-3 / 0.01, rtol=1e-15)
+    assert f["n_ngb"][0] == 1
+
+
+def test_inside_cutoff_is_linear():
+    """inside r_out the force is G m dx / r_out^3 (hence 'linear cutoff')."""
+    epi = _mk_epi([[0.0, 0, 0]], 0.0)
+    for d in (1e-4, 3e-3, 9.9e-3):
+        epj = _mk_epj([[d, 0.0, 0.0]], [1.0], 0.0)
+        f = ob.force_epep(epi, epj, 0.0, 0.01, 1.0)
+        assert np.isclose(f["acc"][0, 0], d / 0.01 ** 3, rtol=1e-13)
+        assert np.isclose(f["pot"][0], -1.0 / 0.01, rtol=1e-13)
+
+
+def test_neighbour_tie_is_strict():
+    """r2 < rs^2 is strict: a j exactly at max(rs_i, rs_j) is not a neighbour; eps is not in the test."""
+    epi = _mk_epi([[0.0, 0, 0]], 0.25)
+    epj = _mk_epj([[0.5, 0.0, 0.0], [0.4999999, 0, 0]], [1.0, 1.0], [0.5, 0.5])
+    f = ob.force_epep(epi, epj, 10.0, 0.01, 1.0)
+    assert f["n_ngb"][0] == 1
+
+
+def test_zero_mass_j_counts_but_no_force():
+    epi = _mk_epi([[0.0, 0, 0]], 0.1)
+    epj = _mk_epj([[0.05, 0.0, 0.0]], [0.0], 0.1)
+    f = ob.force_epep(epi, epj, 0.0, 0.01, 1.0)
+    assert np.all(f["acc"] == 0) and f["pot"][0] == 0 and f["n_ngb"][0] == 1
+
+
+def test_eps_larger_than_rout_makes_clamp_inert():
+    rng = np.random.default_rng(1)
+    epi = _mk_epi(rng.normal(size=(8, 3)), 0.0)
+    epj = _mk_epj(rng.normal(size=(50, 3)), rng.random(50), 0.0)
+    a = ob.force_epep(epi, epj, 0.3, 0.2, 1.0)
+    b = ob.force_epep(epi, epj, 0.3, 0.0, 1.0)
+    assert np.array_equal(a["acc"], b["acc"]) and np.array_equal(a["pot"], b["pot"])
+
+
+def test_quad_with_zero_quadrupole_equals_monopole():
+    rng = np.random.default_rng(2)
+    epi = _mk_epi(rng.normal(size=(16, 3)), 0.0)
+    spj = np.zeros(40, dtype=SPJQuad)
+    spj["mass"] = rng.random(40)
+    spj["pos"] = rng.normal(size=(40, 3)) + 5.0
+    q = ob.force_epsp_quad(epi, spj, 0.01, 1.0)
+    m = ob.force_epsp_mono(epi, spj, 0.01, 1.0)
+    assert np.allclose(q["acc"], m["acc"], rtol=1e-14) and np.allclose(q["pot"], m["pot"], rtol=1e-14)
+
+
+def test_pure_trace_quadrupole_is_radial_only():
+    """Q = s*I: traceless part vanishes, so (with eps = 0) the quadrupole terms cancel exactly:
+    A = m r^-3 - 1.5*3s r^-5 + 7.5 s r^2 r^-7 and B qr = -3 s r^-5 dx  =>  force = monopole."""
+    epi = _mk_epi([[0.0, 0, 0]], 0.0)
+    spj = np.zeros(1, dtype=SPJQuad)
+    spj["mass"] = 2.0
+    spj["pos"] = [[1.0, 2.0, 2.0]]
+    spj["quad"] = [[0.7, 0.7, 0.7, 0, 0, 0]]
+    q = ob.force_epsp_quad(epi, spj, 0.0, 1.0)
+    m = ob.force_epsp_mono(epi, spj, 0.0, 1.0)
+    assert np.allclose(q["acc"], m["acc"], rtol=1e-13) and np.allclose(q["pot"], m["pot"], rtol=1e-13)
+
+
+def test_quadrupole_of_two_points_converges_to_direct_sum():
+    """A superparticle built from two point masses reproduces their direct sum to O((d/r)^3)."""
+    x1, x2, m1, m2 = np.array([0.01, 0.0, 0.0]), np.array([-0.01, 0.005, 0.0]), 1.0, 1.0
+    cm = (m1 * x1 + m2 * x2) / (m1 + m2)
+    qq = np.zeros((3, 3))
+    for x, m in ((x1, m1), (x2, m2)):
+        d = x - cm
+        qq += m * np.outer(d, d)
+    spj = np.zeros(1, dtype=SPJQuad)
+    spj["mass"] = m1 + m2
+    spj["pos"] = [cm]
+    spj["quad"] = [[qq[0, 0], qq[1, 1], qq[2, 2], qq[0, 1], qq[0, 2], qq[1, 2]]]
+    epi = _mk_epi([[1.0, 0.5, -0.3]], 0.0)
+    epj = _mk_epj([x1, x2], [m1, m2], 0.0)
+    direct = ob.force_pp(epi, epj, 1.0)
+    quad = ob.force_epsp_quad(epi, spj, 0.0, 1.0)
+    mono = ob.force_epsp_mono(epi, spj, 0.0, 1.0)
+    eq = np.abs(quad["acc"] - direct["acc"]).max()
+    em = np.abs(mono["acc"] - direct["acc"]).max()
+    assert eq < 1e-5 and eq < 0.05 * em
+
+
+def test_empty_lists():
+    epi = _mk_epi([[0.0, 0, 0]], 0.1)
+    f = ob.force_epep(epi, _mk_epj(np.zeros((0, 3)), [], []), 0.0, 0.01, 1.0)
+    assert np.all(f["acc"] == 0) and f["pot"][0] == 0 and f["n_ngb"][0] == 0
+    f = ob.force_epsp_quad(epi, np.zeros(0, dtype=SPJQuad), 0.0, 1.0)
+    assert np.all(f["acc"] == 0)
