@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — soft-force hot path benchmark.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 1000000] [--impl reference]
+
+One "step" = one pass of the hot path over one tree step's worth of walks of the workload
+(N-particle Plummer model, theta 0.3, n_group_limit 512, 200 walks per dispatch — the shape FDPS
+hands to the dispatch functor at reference src/petar.hpp:894-899):
+
+* value  — interactions/s with all packed inputs resident in HBM (pb_replay: every recorded
+           dispatch's force + reduce kernels, CUDA-event timed on the launching stream);
+* e2e    — the same step through the PeTar functor boundary (C++ shim -> C ABI) from HOST buffers:
+           j upload, per-dispatch packing, H2D, kernels, D2H, scatter into ForceSoft arrays;
+* roofline — force-kernel time vs the non-tensor FP32 peak with the north-star flop convention
+           (38 flop per EP-EP, 65 per EP-SP interaction);
+* cpu_baseline — the reference's own AVX-512/AVX2 kernels (oracle/_ref) on this box's host cores.
+
+Multi-GPU (torchrun, one rank per GPU): the particles are split into N spatial domains, each rank
+owns one, the local-essential-tree j (EP near, SP far) travel rank-to-rank in the device j format
+through one NCCL all-to-all per step straight into the receivers' j stores; forces need no
+reduction.  Total work is fixed as N grows ("strong" scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_EP, FLOP_SP = 38.0, 65.0          # north-star convention (BASELINE.json)
+N_SM, FP32_LANES = 148, 128
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                continue
+        # under load = samples in the upper half of the observed clock range
+        load = [s for s in sm if s >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(n, rank, world, args):
+    """Particles, parameters and this rank's walk batch (+ LET plan for world > 1)."""
+    from petar_b200 import harness as hz
+    t0 = time.time()
+    mass, pos, vel = hz.make_plummer(n)
+    prm = hz.petar_auto_params(mass, vel)
+    r_in, r_out, rs = hz.particle_rout_rsearch(mass, vel, prm)
+    wl = {"prm": prm, "n": n}
+    if world == 1:
+        batch, _ = hz.build_walk_batch(pos, mass, rs, vel=vel, r_in=r_in, r_out=r_out)
+        wl["batch"] = batch
+        wl["let"] = None
+    else:
+        from petar_b200 import multigpu
+        wl.update(multigpu.build_domain_workload(pos, mass, vel, rs, r_in, r_out, rank, world))
+    wl["t_build"] = time.time() - t0
+    return wl
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU SIMD kernels (oracle/_ref) over the same walk lists,
+    all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import binding as ob
+    wl = build_workload(args.n, 0, 1, args)
+    batch, prm = wl["batch"], wl["prm"]
+    isa = "avx512" if ob._cpu_has_avx512() else "avx2"
+    kind = "reference" if ob.ref_available(isa) else "port"
+    cores = os.cpu_count()
+    # bounded sample: as many leading walks as keep one step near `--cpu-seconds`
+    I_ep, I_sp = batch.interactions()
+    nw = batch.n_walk
+    force = ob.new_force(batch.n_epi_total)
+
+    def one(nwalks):
+        sl = slice(0, nwalks)
+        if kind == "reference":
+            _, sec = ob.ref_walks_index(batch, prm["eps"], prm["r_out"], prm["G"], isa=isa, n_threads=0, walk_slice=sl, force=force)
+        else:
+            t0 = time.perf_counter()
+            ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"], walk_slice=sl)
+            sec = time.perf_counter() - t0
+        return sec
+
+    probe_w = max(1, min(nw, 64))
+    sec = one(probe_w)
+    ie, isp = batch.interactions(slice(0, probe_w))
+    rate = (ie + isp) / sec
+    target = args.cpu_seconds * rate
+    cum = np.cumsum(batch.n_epi.astype(np.int64) * (batch.n_epj.astype(np.int64) + batch.n_spj))
+    nwalks = int(min(nw, max(1, np.searchsorted(cum, target) + 1)))
+    ie, isp = batch.interactions(slice(0, nwalks))
+    for _ in range(args.warmup):
+        one(min(nwalks, probe_w))
+    times = [one(nwalks) for _ in range(args.steps)]
+    sec = float(np.mean(times))
+    gint = (ie + isp) / sec * 1e-9
+    sample = f"first {nwalks} of {nw} walks of one tree step ({ie + isp:.3e} interactions per step), {isa}, OpenMP dynamic over walks"
+    line = {
+        "impl": "reference", "metric": "soft-force Ginteractions/s", "value": gint, "unit": "Ginteractions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (I_ep + I_sp) / (ie + isp),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, wl, 1),
+        "cpu_baseline": {"value": gint, "unit": "Ginteractions/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": gint, "unit": "Ginteractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sec_per_nbody_time_unit": sec * (I_ep + I_sp) / (ie + isp) / prm["dt_soft"],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, wl, world):
+    prm = wl["prm"]
+    return {"workload": f"plummer_equal_mass_N{args.n}", "n_particles": args.n, "theta": 0.3, "n_leaf_limit": 20,
+            "n_group_limit": 512, "n_walk_limit": 200, "r_out": prm["r_out"], "dt_soft": prm["dt_soft"], "eps": prm["eps"],
+            "multipole": "quadrupole", "parallelism": f"domain_decomposition_x{world}",
+            "l2_policy": "inputs larger than L2: every step re-reads all dispatches' index lists, i-particles and the j store"}
+
+
+def cpu_baseline_leg(args, wl):
+    from oracle import binding as ob
+    batch, prm = wl["batch"], wl["prm"]
+    isa = "avx512" if ob._cpu_has_avx512() else "avx2"
+    if not ob.ref_available(isa):
+        kind = "port"
+    else:
+        kind = "reference"
+    nw = batch.n_walk
+    force = ob.new_force(batch.n_epi_total)
+    probe_w = max(1, min(nw, 32))
+    if kind == "reference":
+        _, sec = ob.ref_walks_index(batch, prm["eps"], prm["r_out"], prm["G"], isa=isa, walk_slice=slice(0, probe_w), force=force)
+    else:
+        t0 = time.perf_counter(); ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"], walk_slice=slice(0, probe_w)); sec = time.perf_counter() - t0
+    ie, isp = batch.interactions(slice(0, probe_w))
+    rate = (ie + isp) / sec
+    cum = np.cumsum(batch.n_epi.astype(np.int64) * (batch.n_epj.astype(np.int64) + batch.n_spj))
+    nwalks = int(min(nw, max(1, np.searchsorted(cum, args.cpu_seconds * rate) + 1)))
+    if kind == "reference":
+        _, sec = ob.ref_walks_index(batch, prm["eps"], prm["r_out"], prm["G"], isa=isa, walk_slice=slice(0, nwalks), force=force)
+    else:
+        t0 = time.perf_counter(); ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"], walk_slice=slice(0, nwalks)); sec = time.perf_counter() - t0
+    ie, isp = batch.interactions(slice(0, nwalks))
+    return {"value": (ie + isp) / sec * 1e-9, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"first {nwalks} of {nw} walks of one tree step ({ie + isp:.3e} interactions, {sec:.2f} s), {isa}, OpenMP over walks"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=1000000, help="number of particles (BASELINE metric: 1e6)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per step of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--nr", type=int, default=0)
+    ap.add_argument("--cull", type=int, default=1)
+    ap.add_argument("--jchunk", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from petar_b200 import engine
+    L = engine.load()
+    engine.check(L.pb_init(rank, local_rank), "pb_init")
+    for k, v in (("streams", args.streams), ("nr", args.nr), ("cull", args.cull), ("jchunk", args.jchunk)):
+        engine.set_option(k, v)
+
+    wl = build_workload(args.n, rank, world, args)
+    batch, prm = wl["batch"], wl["prm"]
+    I_ep, I_sp = batch.interactions()
+    eps, r_out, G = prm["eps"], prm["r_out"], prm["G"]
+    force = np.zeros(batch.n_epi_total, dtype=engine.ForceSoft)
+
+    if world > 1:
+        from petar_b200 import multigpu
+        stepper = multigpu.DomainStepper(wl, rank, world, dist)
+    else:
+        stepper = None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def e2e_step():
+        if stepper is None:
+            engine.calc_force_all_and_write_back(batch, eps, r_out, G, force=force, my_rank=rank)
+        else:
+            stepper.step(force)
+
+    # ---- record one step so its packed inputs stay resident in HBM ----
+    engine.check(L.pb_record_begin(), "pb_record_begin")
+    e2e_step()
+    engine.check(L.pb_record_end(), "pb_record_end")
+    launches_per_step = L.pb_replay_launches()
+
+    # ---- warm-up ----
+    ms_t, ms_f = C.c_float(0), C.c_float(0)
+    for _ in range(args.warmup):
+        engine.check(L.pb_replay(1, C.byref(ms_t), C.byref(ms_f)), "pb_replay")
+        e2e_step()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- timed: K steps, device resident ----
+    barrier()
+    engine.check(L.pb_replay(args.steps, C.byref(ms_t), C.byref(ms_f)), "pb_replay")
+    barrier()
+    ms_step, ms_force = float(ms_t.value), float(ms_f.value)
+
+    # ---- timed: K steps end to end from host buffers ----
+    engine.get_profile(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    sec_e2e = (time.perf_counter() - t0) / args.steps
+    prof = engine.get_profile()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- max over ranks, totals over ranks ----
+    vals = torch.tensor([ms_step, ms_force, sec_e2e], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([I_ep, I_sp, prof["h2d_bytes"] / args.steps, prof["d2h_bytes"] / args.steps,
+                        stepper.nccl_bytes_per_step if stepper else 0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step, ms_force, sec_e2e = (float(x) for x in vals.tolist())
+    I_ep_t, I_sp_t, h2d, d2h, nccl_b = (float(x) for x in tot.tolist())
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        f_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        peak_tf = N_SM * FP32_LANES * 2 * f_mhz * 1e6 / 1e12 * world
+        flops = FLOP_EP * I_ep_t + FLOP_SP * I_sp_t
+        ach_tf = flops / (ms_force * 1e-3) / 1e12
+        inter = I_ep_t + I_sp_t
+        line = {
+            "metric": "soft-force Ginteractions/s", "value": inter / (ms_step * 1e-3) * 1e-9, "unit": "Ginteractions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, wl, world),
+            "interactions_per_step": {"ep_ep": I_ep_t, "ep_sp": I_sp_t},
+            "sec_per_nbody_time_unit": {"kernels_only": ms_step * 1e-3 / prm["dt_soft"], "e2e_hot_path": sec_e2e / prm["dt_soft"],
+                                        "note": "hot path only; FDPS tree build/walk, hard integrator etc. are outside this path"},
+            "e2e": {"value": inter / sec_e2e * 1e-9, "unit": "Ginteractions/s", "ms_per_step": sec_e2e * 1e3,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "nccl_bytes_per_step": nccl_b,
+                    "api": "CalcForceWithLinearCutoffCUDAMultiWalk / RetrieveForceCUDA (C++ shim -> C ABI), host buffers"},
+            # value leg (K x all kernels) + its force-only timing pass (K x force kernels) + e2e leg (counted by the library)
+            "gpu_launches": int(launches_per_step * args.steps + (launches_per_step // 2) * args.steps + prof["n_kernel_launch"]),
+            "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                         "traffic": None, "kernel": "pb::force_kernel", "ms_per_step_kernel": ms_force,
+                         "flop_convention": "38 per EP-EP, 65 per EP-SP interaction (north star)",
+                         "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz={f_mhz:.0f} from {peak_src} (non-tensor FP32; "
+                                        "MEASURED_PEAKS has no FP32-pipe figure)",
+                         "note": "bound is the non-tensor FP32/issue pipe, not HBM or tensor: ~300-500 flop per HBM byte"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline_leg(args, wl)
+            except Exception as ex:  # the checker must never take the bench down
+                line["cpu_baseline"] = {"value": None, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    L.pb_finalize()
+
+
+if __name__ == "__main__":
+    main()
