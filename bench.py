@@ -29,7 +29,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the host-side packing is OpenMP code, so give
+# each rank its share of the host cores (must happen before any OpenMP runtime is loaded)
+_world = int(os.environ.get("WORLD_SIZE", "1"))
+if _world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _world))
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -323,6 +329,9 @@ def main():
                                         "note": "hot path only; FDPS tree build/walk, hard integrator etc. are outside this path"},
             "e2e": {"value": inter / sec_e2e * 1e-9, "unit": "Ginteractions/s", "ms_per_step": sec_e2e * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "nccl_bytes_per_step": nccl_b,
+                    "rank0_ms_per_step": {"host_pack_unpack": prof["t_copy"] * 1e3 / args.steps, "h2d": prof["t_send"] * 1e3 / args.steps,
+                                          "kernels": prof["t_calc"] * 1e3 / args.steps, "d2h": prof["t_recv"] * 1e3 / args.steps,
+                                          "note": "device intervals of concurrent streams overlap; they do not add up to ms_per_step"},
                     "api": "CalcForceWithLinearCutoffCUDAMultiWalk / RetrieveForceCUDA (C++ shim -> C ABI), host buffers"},
             # value leg (K x all kernels) + its force-only timing pass (K x force kernels) + e2e leg (counted by the library)
             "gpu_launches": int(launches_per_step * args.steps + (launches_per_step // 2) * args.steps + prof["n_kernel_launch"]),

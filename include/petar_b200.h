@@ -161,9 +161,10 @@ int  pb_replay_launches(void);
  *
  * Device j formats (little-endian fp32):
  *   EPJ: 32 B = float4{x_hi,y_hi,z_hi,mass}, float4{x_lo,y_lo,z_lo,r_search}
- *   SPJ: 64 B = float4{x_hi,y_hi,z_hi,mass}, float4{x_lo,y_lo,z_lo,qxx},
- *               float4{qyy,qzz,qxy,qxz},     float4{qyz,trace,0,0}
- * with x = x_hi + x_lo (x_hi = float(x), x_lo = float(x - x_hi)). */
+ *   SPJ: 64 B = float4{x_hi,y_hi,z_hi,mass}, float4{x_lo,y_lo,z_lo,q'xx},
+ *               float4{q'yy,q'zz,q'xy,q'xz},  float4{q'yz,trace,0,0}
+ * with x = x_hi + x_lo (x_hi = float(x), x_lo = float(x - x_hi)) and q' = 3 q - trace * I the
+ * traceless form of the raw second-moment tensor q (formed in fp64 before the cast). */
 #define PB_EPJ_DEV_BYTES 32
 #define PB_SPJ_DEV_BYTES 64
 

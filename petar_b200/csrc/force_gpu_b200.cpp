@@ -73,17 +73,22 @@ void first_call(PS::S32 my_rank) {
 #ifdef GPU_PROFILE
 // fold the library's timers/counters into PeTar's globals (reference :610-617, 672-697, 852-861)
 void harvest_profile() {
+    // the library's profile is cumulative; add what accrued since the last harvest (PeTar clears
+    // gpu_profile / gpu_counter itself, reference src/petar.hpp:2081-2084)
+    static pb_profile last = {};
     pb_profile p;
-    pb_get_profile(&p, 1);
-    gpu_profile.copy.time += p.t_copy;
-    gpu_profile.send.time += p.t_send;
-    gpu_profile.recv.time += p.t_recv;
-    gpu_profile.calc.time += p.t_calc;
-    gpu_counter.n_walk += p.n_walk;
-    gpu_counter.n_epi  += p.n_epi;
-    gpu_counter.n_epj  += p.n_epj;
-    gpu_counter.n_spj  += p.n_spj;
-    gpu_counter.n_call += p.n_call;
+    pb_get_profile(&p, 0);
+    if (p.n_call < last.n_call) last = pb_profile{};      // somebody reset the library's profile
+    gpu_profile.copy.time += p.t_copy - last.t_copy;
+    gpu_profile.send.time += p.t_send - last.t_send;
+    gpu_profile.recv.time += p.t_recv - last.t_recv;
+    gpu_profile.calc.time += p.t_calc - last.t_calc;
+    gpu_counter.n_walk += p.n_walk - last.n_walk;
+    gpu_counter.n_epi  += p.n_epi - last.n_epi;
+    gpu_counter.n_epj  += p.n_epj - last.n_epj;
+    gpu_counter.n_spj  += p.n_spj - last.n_spj;
+    gpu_counter.n_call += p.n_call - last.n_call;
+    last = p;
 }
 #endif
 

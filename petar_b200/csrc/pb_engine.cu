@@ -85,6 +85,7 @@ struct Recorded {
     char* d_arena = nullptr;
     Plan  plan;
     bool  direct = false;
+    int   slot = 0;              // the stream slot the dispatch ran on
 };
 
 struct Engine {
@@ -108,8 +109,6 @@ struct Engine {
 
     bool recording = false;
     std::vector<Recorded> recs;
-    double4* rec_part4 = nullptr; int* rec_partn = nullptr; size_t rec_cap_part = 0;
-    ForceOut* rec_out = nullptr; size_t rec_cap_out = 0;
 
     pb_profile prof;
 };
@@ -237,9 +236,11 @@ void pack_spj(const void* spj, int n, const pb_layout_spj& L, float4* out) {
         double q[6] = {0, 0, 0, 0, 0, 0};
         if (L.has_quad)
             for (int k = 0; k < 6; k++) q[k] = ld(p, L.off_quad, k);      // xx yy zz xy xz yz
-        b.w = (float)q[0];
-        c = make_float4((float)q[1], (float)q[2], (float)q[3], (float)q[4]);
-        d = make_float4((float)q[5], (float)(q[0] + q[1] + q[2]), 0.f, 0.f);
+        // traceless form q' = 3 q - tr I, in fp64 (what the kernel's quadrupole formula consumes)
+        const double tr = q[0] + q[1] + q[2];
+        b.w = (float)(3.0 * q[0] - tr);
+        c = make_float4((float)(3.0 * q[1] - tr), (float)(3.0 * q[2] - tr), (float)(3.0 * q[3]), (float)(3.0 * q[4]));
+        d = make_float4((float)(3.0 * q[5]), (float)tr, 0.f, 0.f);
         float4* o = out + 4 * (size_t)i;
         o[0] = a; o[1] = b; o[2] = c; o[3] = d;
     }
@@ -385,30 +386,34 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
     for (int w = 0; w < p.n_walk; w++) {
         Walk& W = hp.walks[w];
         const char* base = (const char*)win[w].epi;
-        double o[3] = {0.0, 0.0, 0.0};
+        // Walk origin = mean position of the i-particles (robust against outliers, unlike the box
+        // centre), as a hi/lo fp32 pair.  i and j positions are shifted to it by the SAME fp32
+        // operation sequence — (x_hi - o_hi) + (x_lo - o_lo) — here for i, in the kernel for j, so
+        // that a particle meeting itself (or an exact copy) gives dx == 0 exactly, as in the
+        // reference kernel; absolute mode is the same code with a zero origin (then x_rel == x_hi).
+        float oh[3] = {0.f, 0.f, 0.f}, ol[3] = {0.f, 0.f, 0.f};
         if (rel && W.ni > 0) {
-            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            double sum[3] = {0.0, 0.0, 0.0};
             for (int i = 0; i < W.ni; i++) {
                 const char* q = base + (size_t)i * Li.stride;
-                for (int k = 0; k < 3; k++) {
-                    const double x = ld(q, Li.off_pos, k);
-                    lo[k] = std::min(lo[k], x); hi[k] = std::max(hi[k], x);
-                }
+                for (int k = 0; k < 3; k++) sum[k] += ld(q, Li.off_pos, k);
             }
-            float oh[3], ol[3];
-            for (int k = 0; k < 3; k++) {
-                split(0.5 * (lo[k] + hi[k]), oh[k], ol[k]);
-                o[k] = (double)oh[k] + (double)ol[k];       // the origin the device will subtract from j
-            }
-            W.ohx = oh[0]; W.ohy = oh[1]; W.ohz = oh[2];
-            W.olx = ol[0]; W.oly = ol[1]; W.olz = ol[2];
+            for (int k = 0; k < 3; k++) split(sum[k] / W.ni, oh[k], ol[k]);
         }
+        W.ohx = oh[0]; W.ohy = oh[1]; W.ohz = oh[2];
+        W.olx = ol[0]; W.oly = ol[1]; W.olz = ol[2];
         float4* e = epi + W.i_off;
         float hmax[3] = {0.f, 0.f, 0.f}, rsmax = 0.f;
         for (int i = 0; i < W.ni; i++) {
             const char* q = base + (size_t)i * Li.stride;
-            const float4 v = make_float4((float)(ld(q, Li.off_pos, 0) - o[0]), (float)(ld(q, Li.off_pos, 1) - o[1]),
-                                         (float)(ld(q, Li.off_pos, 2) - o[2]), (float)ld(q, Li.off_rsearch));
+            float r[3];
+            for (int k = 0; k < 3; k++) {
+                float xh, xl;
+                split(ld(q, Li.off_pos, k), xh, xl);
+                const float d1 = xh - oh[k], d2 = xl - ol[k];
+                r[k] = d1 + d2;
+            }
+            const float4 v = make_float4(r[0], r[1], r[2], (float)ld(q, Li.off_rsearch));
             e[i] = v;
             hmax[0] = std::max(hmax[0], std::fabs(v.x)); hmax[1] = std::max(hmax[1], std::fabs(v.y));
             hmax[2] = std::max(hmax[2], std::fabs(v.z)); rsmax = std::max(rsmax, v.w);
@@ -512,7 +517,7 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
 
         if (E.recording) {
             Recorded r;
-            r.plan = S.plan; r.direct = direct;
+            r.plan = S.plan; r.direct = direct; r.slot = s;
             CU(cudaMalloc(&r.d_arena, S.plan.bytes));
             CU(cudaMemcpyAsync(r.d_arena, S.d_arena, S.plan.bytes, cudaMemcpyDeviceToDevice, S.stream));
             E.recs.push_back(r);
@@ -576,8 +581,6 @@ void pb_finalize(void) {
     cudaDeviceSynchronize();
     for (auto& r : E.recs) cudaFree(r.d_arena);
     E.recs.clear();
-    cudaFree(E.rec_part4); cudaFree(E.rec_partn); cudaFree(E.rec_out);
-    E.rec_part4 = nullptr; E.rec_partn = nullptr; E.rec_out = nullptr; E.rec_cap_part = E.rec_cap_out = 0;
     for (int s = 0; s < kMaxStreams; s++) {
         Slot& S = E.slots[s];
         cudaFreeHost(S.h_arena); cudaFree(S.d_arena);
@@ -801,32 +804,38 @@ int pb_replay(int n_iter, float* ms_total, float* ms_force) {
     if (E.outstanding) return fail(PB_ERR_PROTOCOL, "pb_replay while a dispatch is outstanding");
     if (E.recs.empty()) return fail(PB_ERR_PROTOCOL, "pb_replay: nothing recorded");
     if (n_iter < 1) return fail(PB_ERR_ARG, "pb_replay: n_iter < 1");
-    size_t mp = 0, mo = 0;
-    for (auto& r : E.recs) { mp = std::max(mp, r.plan.n_part); mo = std::max(mo, r.plan.n_i); }
+    // every recorded sub-batch is re-launched on the stream it originally ran on, with that
+    // stream's own partial/output buffers, so kernels of different streams overlap as they do
+    // in a real dispatch
     CU(cudaDeviceSynchronize());
-    if (mp > E.rec_cap_part) {
-        if (E.rec_part4) CU(cudaFree(E.rec_part4));
-        if (E.rec_partn) CU(cudaFree(E.rec_partn));
-        CU(cudaMalloc(&E.rec_part4, mp * sizeof(double4)));
-        CU(cudaMalloc(&E.rec_partn, mp * sizeof(int)));
-        E.rec_cap_part = mp;
+    bool used[kMaxStreams] = {false};
+    for (auto& r : E.recs) {
+        int rc;
+        if ((rc = grow_part(E.slots[r.slot], r.plan.n_part)) != PB_OK) return rc;
+        if ((rc = grow_out(E.slots[r.slot], r.plan.n_i)) != PB_OK) return rc;
+        used[r.slot] = true;
     }
-    if (mo > E.rec_cap_out) {
-        if (E.rec_out) CU(cudaFree(E.rec_out));
-        CU(cudaMalloc(&E.rec_out, mo * sizeof(ForceOut)));
-        E.rec_cap_out = mo;
-    }
-    cudaStream_t st = E.slots[0].stream;
+    cudaStream_t st0 = E.slots[0].stream;
     cudaEvent_t a = E.slots[0].ev[0], b = E.slots[0].ev[1];
     for (int pass = 0; pass < 2; pass++) {
         const bool force_only = (pass == 1);
         float* dst = force_only ? ms_force : ms_total;
         if (!dst) continue;
-        CU(cudaEventRecord(a, st));
+        CU(cudaDeviceSynchronize());
+        CU(cudaEventRecord(a, st0));
+        for (int s = 1; s < kMaxStreams; s++)
+            if (used[s]) CU(cudaStreamWaitEvent(E.slots[s].stream, a, 0));
         for (int it = 0; it < n_iter; it++)
-            for (auto& r : E.recs)
-                CU(launch_plan(st, r.plan, r.d_arena, r.direct, E.rec_part4, E.rec_partn, E.rec_out, force_only));
-        CU(cudaEventRecord(b, st));
+            for (auto& r : E.recs) {
+                Slot& S = E.slots[r.slot];
+                CU(launch_plan(S.stream, r.plan, r.d_arena, r.direct, S.d_part4, S.d_partn, S.d_out, force_only));
+            }
+        for (int s = 1; s < kMaxStreams; s++)
+            if (used[s]) {
+                CU(cudaEventRecord(E.slots[s].ev[3], E.slots[s].stream));
+                CU(cudaStreamWaitEvent(st0, E.slots[s].ev[3], 0));
+            }
+        CU(cudaEventRecord(b, st0));
         CU(cudaEventSynchronize(b));
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, a, b));

@@ -73,10 +73,10 @@ struct EpTile {                       // 128 pairs, 40 B per pair
 struct SpTile {                       // 128 pairs, 96 B per pair
     float4 q0[kTilePairs];            // {x0, x1, y0, y1}
     float4 q1[kTilePairs];            // {z0, z1, m0, m1}
-    float4 q2[kTilePairs];            // {qxx0, qxx1, qyy0, qyy1}
+    float4 q2[kTilePairs];            // {q'xx0, q'xx1, q'yy0, q'yy1}   (q' = 3q - tr I, traceless)
     float4 q3[kTilePairs];            // {qzz0, qzz1, qxy0, qxy1}
     float4 q4[kTilePairs];            // {qxz0, qxz1, qyz0, qyz1}
-    float4 q5[kTilePairs];            // {tr0, tr1, 0.5tr0, 0.5tr1}
+    float2 q5[kTilePairs];            // {-eps2 tr0, -eps2 tr1}
 };
 union __align__(16) Smem {
     EpTile ep[2];
@@ -174,13 +174,20 @@ __device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
 }
 
 // ------------------------------------------------------------------------------------------
-// EP-SP: monopole + quadrupole of a superparticle; Q is the raw second-moment tensor
+// EP-SP: monopole + quadrupole of a superparticle.
+// The reference evaluates, with Q the RAW second-moment tensor and tr its trace
+// (src/force_gpu_cuda.cu:283-308, src/soft_force.hpp:175-194),
 //   dx = xi - xj ; r2 = eps2 + dx.dx ; qr = Q dx ; qrr = dx.qr
 //   A = m r^-3 - 1.5 tr r^-5 + 7.5 qrr r^-7 ; B = -3 r^-5
-//   acc -= A dx + B qr ; pot -= m r^-1 - 0.5 tr r^-3 + 1.5 qrr r^-5
-// (reference src/force_gpu_cuda.cu:283-308, same operation order)
+//   acc -= A dx + B qr ; pot -= m r^-1 - 0.5 tr r^-3 + 1.5 qrr r^-5 .
+// With the traceless tensor Q' = 3Q - tr I (formed in fp64 on the host) and
+// S = dx.Q'dx - eps2 tr  this is, term for term and for any eps2, the same as
+//   acc -= (m r^-3 + 2.5 S r^-7) dx - r^-5 Q'dx ; pot -= m r^-1 + 0.5 S r^-5
+// (3 qrr - tr r2 = S because r2 = dx.dx + eps2) — 34 instead of 38 packed FP operations per
+// pair of interactions.  The reference's own SIMD path uses the same traceless form
+// (src/phantomquad_for_p3t_x86.hpp:144-163).
 // ------------------------------------------------------------------------------------------
-struct SpRegs { float4 a, b, c, d; };  // {xh,yh,zh,m}, {xl,yl,zl,qxx}, {qyy,qzz,qxy,qxz}, {qyz,tr,-,-}
+struct SpRegs { float4 a, b, c, d; };  // {xh,yh,zh,m}, {xl,yl,zl,q'xx}, {q'yy,q'zz,q'xy,q'xz}, {q'yz,tr,-,-}
 
 __device__ __forceinline__ SpRegs sp_load_j(const float4* __restrict__ spj, int id) {
     SpRegs r;
@@ -192,17 +199,17 @@ __device__ __forceinline__ SpRegs sp_load_j(const float4* __restrict__ spj, int 
     }
     return r;
 }
-__device__ __forceinline__ void sp_store(SpTile& t, int tid, int id, const SpRegs& r, const Walk& w) {
+__device__ __forceinline__ void sp_store(SpTile& t, int tid, int id, const SpRegs& r, const Walk& w, float eps2) {
     float v[12];
     if (id >= 0) {
         v[0] = (r.a.x - w.ohx) + (r.b.x - w.olx);
         v[1] = (r.a.y - w.ohy) + (r.b.y - w.oly);
         v[2] = (r.a.z - w.ohz) + (r.b.z - w.olz);
         v[3] = r.a.w;                                  // m
-        v[4] = r.b.w; v[5] = r.c.x; v[6] = r.c.y;      // qxx qyy qzz
-        v[7] = r.c.z; v[8] = r.c.w; v[9] = r.d.x;      // qxy qxz qyz
-        v[10] = r.d.y;                                 // tr = qxx+qyy+qzz (formed in fp64 on the host)
-        v[11] = 0.5f * r.d.y;
+        v[4] = r.b.w; v[5] = r.c.x; v[6] = r.c.y;      // q'xx q'yy q'zz
+        v[7] = r.c.z; v[8] = r.c.w; v[9] = r.d.x;      // q'xy q'xz q'yz
+        v[10] = -(eps2 * r.d.y);                       // -eps2 tr
+        v[11] = 0.f;
     } else {
         v[0] = v[1] = v[2] = kPadPos;
 #pragma unroll
@@ -220,7 +227,7 @@ __device__ __forceinline__ void sp_store(SpTile& t, int tid, int id, const SpReg
     q2[s] = v[4]; q2[2 + s] = v[5];
     q3[s] = v[6]; q3[2 + s] = v[7];
     q4[s] = v[8]; q4[2 + s] = v[9];
-    q5[s] = v[10]; q5[2 + s] = v[11];
+    q5[s] = v[10];
 }
 
 template <int NR>
@@ -230,13 +237,13 @@ __device__ __forceinline__ void sp_pairs(const SpTile& t, int p0, int p1,
     const float2 vxi = bc(xi), vyi = bc(yi), vzi = bc(zi), e2 = bc(eps2);
 #pragma unroll 2
     for (int p = p0; p < p1; ++p) {
-        const float4 Q0 = t.q0[p], Q1 = t.q1[p], Q2 = t.q2[p], Q3 = t.q3[p], Q4 = t.q4[p], Q5 = t.q5[p];
+        const float4 Q0 = t.q0[p], Q1 = t.q1[p], Q2 = t.q2[p], Q3 = t.q3[p], Q4 = t.q4[p];
+        const float2 mtr = t.q5[p];
         const float2 xj = make_float2(Q0.x, Q0.y), yj = make_float2(Q0.z, Q0.w), zj = make_float2(Q1.x, Q1.y);
         const float2 mj = make_float2(Q1.z, Q1.w);
         const float2 qxx = make_float2(Q2.x, Q2.y), qyy = make_float2(Q2.z, Q2.w);
         const float2 qzz = make_float2(Q3.x, Q3.y), qxy = make_float2(Q3.z, Q3.w);
         const float2 qxz = make_float2(Q4.x, Q4.y), qyz = make_float2(Q4.z, Q4.w);
-        const float2 tr  = make_float2(Q5.x, Q5.y), htr = make_float2(Q5.z, Q5.w);
         const float2 dx = __fadd2_rn(vxi, make_float2(-xj.x, -xj.y));
         const float2 dy = __fadd2_rn(vyi, make_float2(-yj.x, -yj.y));
         const float2 dz = __fadd2_rn(vzi, make_float2(-zj.x, -zj.y));
@@ -247,26 +254,23 @@ __device__ __forceinline__ void sp_pairs(const SpTile& t, int p0, int p1,
         float2 qrx = __fmul2_rn(qxx, dx); qrx = __ffma2_rn(qxy, dy, qrx); qrx = __ffma2_rn(qxz, dz, qrx);
         float2 qry = __fmul2_rn(qxy, dx); qry = __ffma2_rn(qyy, dy, qry); qry = __ffma2_rn(qyz, dz, qry);
         float2 qrz = __fmul2_rn(qxz, dx); qrz = __ffma2_rn(qyz, dy, qrz); qrz = __ffma2_rn(qzz, dz, qrz);
-        float2 qrr = __fmul2_rn(qrx, dx); qrr = __ffma2_rn(qry, dy, qrr); qrr = __ffma2_rn(qrz, dz, qrr);
-        const float2 rinv2  = __fmul2_rn(rinv, rinv);
-        const float2 rinv3  = __fmul2_rn(rinv2, rinv);
-        const float2 rinv5  = __fmul2_rn(__fmul2_rn(rinv2, rinv3), bc(1.5f));
-        const float2 qrr_r5 = __fmul2_rn(rinv5, qrr);
-        const float2 qrr_r7 = __fmul2_rn(rinv2, qrr_r5);
-        float2 A = __fmul2_rn(mj, rinv3);
-        A = __ffma2_rn(make_float2(-tr.x, -tr.y), rinv5, A);
-        A = __ffma2_rn(bc(5.0f), qrr_r7, A);
-        const float2 nB = __fmul2_rn(bc(2.0f), rinv5);                 // -B
-        // acc -= A dx + B qr   ==   acc += (-A) dx + (-B) qr
-        const float2 nA = make_float2(-A.x, -A.y);
-        ax = __ffma2_rn(nA, dx, ax); ax = __ffma2_rn(nB, qrx, ax);
-        ay = __ffma2_rn(nA, dy, ay); ay = __ffma2_rn(nB, qry, ay);
-        az = __ffma2_rn(nA, dz, az); az = __ffma2_rn(nB, qrz, az);
-        // pot accumulates +(m r^-1 - 0.5 tr r^-3 + 1.5 qrr r^-5); negated at the end
-        float2 ph = __fmul2_rn(mj, rinv);
-        ph = __ffma2_rn(make_float2(-htr.x, -htr.y), rinv3, ph);
-        ph = __fadd2_rn(ph, qrr_r5);
-        pt = __fadd2_rn(pt, ph);
+        float2 S = __ffma2_rn(qrx, dx, mtr); S = __ffma2_rn(qry, dy, S); S = __ffma2_rn(qrz, dz, S);
+        const float2 rinv2 = __fmul2_rn(rinv, rinv);
+        const float2 mr1   = __fmul2_rn(mj, rinv);
+        const float2 mr3   = __fmul2_rn(mr1, rinv2);
+        const float2 rinv4 = __fmul2_rn(rinv2, rinv2);
+        const float2 rinv5 = __fmul2_rn(rinv4, rinv);
+        const float2 S5    = __fmul2_rn(rinv5, S);
+        const float2 S7    = __fmul2_rn(S5, rinv2);
+        const float2 A     = __ffma2_rn(bc(2.5f), S7, mr3);
+        const float2 nA    = make_float2(-A.x, -A.y);
+        // acc -= A dx - r^-5 Q'dx
+        ax = __ffma2_rn(nA, dx, ax); ax = __ffma2_rn(rinv5, qrx, ax);
+        ay = __ffma2_rn(nA, dy, ay); ay = __ffma2_rn(rinv5, qry, ay);
+        az = __ffma2_rn(nA, dz, az); az = __ffma2_rn(rinv5, qrz, az);
+        // pot accumulates +(m r^-1 + 0.5 S r^-5); negated at the end
+        pt = __ffma2_rn(bc(0.5f), S5, pt);
+        pt = __fadd2_rn(pt, mr1);
     }
 }
 
@@ -353,7 +357,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
         int id_cur = ep_load_id(ids, tid, task.j_count);
         SpRegs jr  = sp_load_j(spj, id_cur);
         int id_nxt = ep_load_id(ids, kTileJ + tid, task.j_count);
-        sp_store(sm.sp[0], tid, id_cur, jr, w);
+        sp_store(sm.sp[0], tid, id_cur, jr, w, prm.eps2);
         __syncthreads();
         for (int k = 0; k < n_tiles; ++k) {
             const bool more = (k + 1 < n_tiles);
@@ -367,7 +371,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 sp_pairs<NR>(sm.sp[k & 1], p0, p1, pi.x, pi.y, pi.z, prm.eps2, ax, ay, az, pt);
                 kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
             }
-            if (more) sp_store(sm.sp[(k + 1) & 1], tid, id_nxt, jr, w);
+            if (more) sp_store(sm.sp[(k + 1) & 1], tid, id_nxt, jr, w, prm.eps2);
             id_nxt = id_nn;
             __syncthreads();
         }

@@ -32,6 +32,7 @@ def lib():
         L.hz_build.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_int, C.c_int]
         L.hz_sizes.argtypes = [_vp, _vp]
         L.hz_export.argtypes = [_vp] * 9
+        L.hz_export_let_sp_src.argtypes = [_vp, _vp]
         L.hz_local_boxes.argtypes = [_vp, _vp]
         L.hz_make_let.argtypes = [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp]
         L.hz_free.argtypes = [_vp]
@@ -154,6 +155,13 @@ class TreeHandle:
         lib().hz_export(self.h, epj_src.ctypes.data, epi_src.ctypes.data, spj.ctypes.data, i_off.ctypes.data,
                         ej_off.ctypes.data, sj_off.ctypes.data, id_epj.ctypes.data, id_spj.ctypes.data)
         return epj_src, epi_src, spj, i_off, ej_off, sj_off, id_epj, id_spj
+
+    def let_sp_src(self):
+        """for spj[n_nodes + k]: index of that entry in the `let["spj"]` array given at build time"""
+        out = np.zeros(self.n_let_sp, dtype=np.int32)
+        if self.n_let_sp:
+            lib().hz_export_let_sp_src(self.h, out.ctypes.data)
+        return out
 
     def local_boxes(self):
         out = np.zeros(12)

@@ -371,6 +371,15 @@ void hz_export(void* h, int* epj_src, int* epi_src, pb_SPJQuad* spj,
     if (!R->id_spj.empty()) memcpy(id_spj, R->id_spj.data(), sizeof(int) * R->id_spj.size());
 }
 
+// For the LET part of spj (entries n_nodes .. n_nodes+n_let_sp-1, Morton order): the index each
+// entry had in the caller's let_sp array.
+void hz_export_let_sp_src(void* h, int* out) {
+    Result* R = (Result*)h;
+    const Tree& G = R->gt();
+    for (size_t i = 0; i < G.el.size(); i++)
+        if (G.sp_index[i] >= 0) out[G.sp_index[i]] = ~G.el[i].src;
+}
+
 // Local boxes of this domain: out[0..5] = particle box lo/hi, out[6..11] = search box lo/hi
 void hz_local_boxes(void* h, double* out) {
     Result* R = (Result*)h;

@@ -1,0 +1,217 @@
+"""Multi-GPU form of the hot path: one rank per GPU, spatial domain decomposition, and the
+local-essential-tree (LET) exchange carried by one NCCL all-to-all per tree step.
+
+In PeTar the decomposition and the LET live in FDPS (``dinfo.decomposeDomainAll``, reference
+``src/petar.hpp:1739-1741``; LET inside ``calcForceAllAndWriteBack*``, profiled as ``Make_LET`` /
+``Ex_LET``, ``src/profile.hpp:286-289``) and travel over MPI as fp64 ``EPJSoft`` (120 B) /
+``SPJQuadrupoleInAndOut`` (80 B).  Here every rank
+
+1. packs the LET entries it owes each peer in the library's DEVICE j format (32 B EP / 64 B SP),
+2. sends them with ``all_to_all_single`` (NCCL over NVLink) straight into the receivers' device
+   j stores, behind the locally uploaded part — no host round trip, no repack on the receiver,
+3. publishes the store to the dispatch streams and runs its walks.  Forces need no reduction.
+
+Which entries go where (the LET *selection*) and the walk lists over local + LET j are FDPS's job;
+the harness (``harness/tree_walk.cpp``) stands in for it, once, outside the timed region.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import engine, harness as hz
+from .types import EPISoft, EPJSoft, SPJQuad, ForceSoft
+from .walks import WalkBatch
+
+
+def domain_split(pos, world):
+    """Recursive coordinate bisection into `world` boxes of equal particle count (x, y, z cycling):
+    the multisection layout FDPS uses for 2/4/8 ranks.  Returns the owner rank of every particle."""
+    owner = np.zeros(len(pos), dtype=np.int32)
+
+    def rec(idx, r0, nparts, axis):
+        if nparts == 1:
+            owner[idx] = r0
+            return
+        nl = nparts // 2
+        order = idx[np.argsort(pos[idx, axis], kind="stable")]
+        cut = len(order) * nl // nparts
+        rec(order[:cut], r0, nl, (axis + 1) % 3)
+        rec(order[cut:], r0 + nl, nparts - nl, (axis + 1) % 3)
+
+    rec(np.arange(len(pos)), 0, world, 0)
+    return owner
+
+
+def _torch_dev(dist):
+    import torch
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def exchange_rows(dist, rows_per_dest, width, dtype):
+    """all-to-all-v of row blocks: rows_per_dest[q] is an (n_q, width) array for rank q.
+    Returns (list of received (m_q, width) arrays by source rank, recv counts)."""
+    import torch
+    world = dist.get_world_size()
+    dev = _torch_dev(dist)
+    cnt_in = torch.tensor([len(r) for r in rows_per_dest], dtype=torch.int64, device=dev)
+    cnt_out = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(cnt_out, cnt_in)
+    cnt_out_l = [int(x) for x in cnt_out.tolist()]
+    send = np.concatenate([np.asarray(r, dtype=dtype).reshape(-1, width) for r in rows_per_dest]) if world else np.zeros((0, width), dtype)
+    tsend = torch.from_numpy(np.ascontiguousarray(send)).to(dev)
+    trecv = torch.empty((sum(cnt_out_l), width), dtype=tsend.dtype, device=dev)
+    dist.all_to_all_single(trecv, tsend, cnt_out_l, [len(r) for r in rows_per_dest])
+    out = trecv.cpu().numpy()
+    offs = np.concatenate([[0], np.cumsum(cnt_out_l)])
+    return [out[offs[q]:offs[q + 1]] for q in range(world)], cnt_out_l
+
+
+def build_domain_workload(pos, mass, vel, rs, r_in, r_out, rank, world, dist=None, theta=hz.THETA,
+                          n_leaf_limit=hz.N_LEAF_LIMIT, n_group_limit=hz.N_GROUP_LIMIT):
+    """This rank's domain, its LET send plan, and its walk batch over local + received LET j.
+
+    j-store order on every rank: EP = [local particles in local Morton order | LET EP by source
+    rank], SP = [cells of the global tree | LET SP by source rank] — exactly where the per-step
+    all-to-all lands them, so the index lists refer to store slots directly."""
+    if dist is None:
+        import torch.distributed as dist
+    owner = domain_split(pos, world)
+    my = np.nonzero(owner == rank)[0]
+    # local Morton order first, so the local part of the store keeps tree locality
+    t0 = hz.TreeHandle(pos[my], mass[my], rs[my], None, theta, n_leaf_limit, n_group_limit)
+    my = my[t0.export()[0]]
+    t0.close()
+    lpos, lmass, lrs, lvel = pos[my], mass[my], rs[my], vel[my]
+    tloc = hz.TreeHandle(lpos, lmass, lrs, None, theta, n_leaf_limit, n_group_limit)
+
+    import torch
+    dev = _torch_dev(dist)
+    boxes = torch.empty(world * 12, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(boxes, torch.from_numpy(tloc.local_boxes()).to(dev))
+    boxes = boxes.cpu().numpy().reshape(world, 12)
+
+    send_ep_idx, send_sp = [], []
+    for q in range(world):
+        if q == rank:
+            send_ep_idx.append(np.zeros(0, dtype=np.int32)); send_sp.append(np.zeros(0, dtype=SPJQuad))
+        else:
+            e, s = tloc.make_let(boxes[q])
+            send_ep_idx.append(e); send_sp.append(s)
+
+    # fp64 LET exchange for the (untimed) global-tree build: what FDPS's MPI exchange carries
+    ep_rows = [np.column_stack([lpos[e], lmass[e], lrs[e]]) if len(e) else np.zeros((0, 5)) for e in send_ep_idx]
+    sp_rows = [s.view(np.float64).reshape(-1, 10) for s in send_sp]
+    recv_ep, recv_ep_cnt = exchange_rows(dist, ep_rows, 5, np.float64)
+    recv_sp, recv_sp_cnt = exchange_rows(dist, sp_rows, 10, np.float64)
+    let_ep = np.concatenate(recv_ep) if recv_ep else np.zeros((0, 5))
+    let_sp = np.ascontiguousarray(np.concatenate(recv_sp)).view(SPJQuad).reshape(-1)
+    let = dict(pos=let_ep[:, 0:3], mass=let_ep[:, 3], rsearch=let_ep[:, 4], spj=let_sp)
+
+    t = hz.TreeHandle(lpos, lmass, lrs, let, theta, n_leaf_limit, n_group_limit)
+    epj_src, epi_src, spj_sorted, i_off, ej_off, sj_off, id_epj, id_spj = t.export()
+    n_loc, n_let_ep, n_nodes, n_let_sp = len(my), len(let_ep), t.n_nodes, t.n_let_sp
+    assert n_let_sp == len(let_sp) and t.n_epj == n_loc + n_let_ep
+
+    epj = np.zeros(n_loc + n_let_ep, dtype=EPJSoft)           # store (= source) order
+    epj["id"][:n_loc] = my + 1
+    epj["mass"] = np.concatenate([lmass, let["mass"]])
+    epj["pos"] = np.concatenate([lpos, let["pos"]])
+    epj["r_search"] = np.concatenate([lrs, let["rsearch"]])
+    epj["vel"][:n_loc] = lvel
+    epj["r_in"][:n_loc] = r_in[my]; epj["r_out"][:n_loc] = r_out[my]
+    epj["r_scale_next"] = 1.0
+    epj["rank_org"] = rank
+    id_epj_store = epj_src[id_epj].astype(np.int32)
+
+    spj = np.concatenate([spj_sorted[:n_nodes], let_sp])
+    sp_src = t.let_sp_src()
+    id_spj_store = np.where(id_spj < n_nodes, id_spj, n_nodes + sp_src[np.maximum(id_spj - n_nodes, 0)]).astype(np.int32) if n_let_sp else id_spj
+
+    epi = np.zeros(t.n_epi, dtype=EPISoft)
+    epi["id"] = my[epi_src] + 1
+    epi["pos"] = lpos[epi_src]
+    epi["r_search"] = lrs[epi_src]
+    epi["rank_org"] = rank
+    epi["type"] = 1
+    batch = WalkBatch(epj, spj, epi, i_off, id_epj_store, ej_off, id_spj_store, sj_off)
+    batch.tree = t
+    return dict(batch=batch, my=my, epi_src=epi_src, n_loc=n_loc, n_nodes=n_nodes, n_let_ep=n_let_ep, n_let_sp=n_let_sp,
+                send_ep_idx=send_ep_idx, send_sp=send_sp, recv_ep_cnt=recv_ep_cnt, recv_sp_cnt=recv_sp_cnt, let=let, local_tree=tloc)
+
+
+class DomainStepper:
+    """One tree step of the hot path on one rank of a multi-GPU run (see module docstring)."""
+
+    def __init__(self, wl, rank, world, dist, device=True):
+        import torch
+        self.torch, self.dist, self.wl, self.rank, self.world, self.device = torch, dist, wl, rank, world, device
+        self.batch, self.prm = wl["batch"], wl["prm"]
+        b = self.batch
+        self.n_loc, self.n_nodes = wl["n_loc"], wl["n_nodes"]
+        self.send_idx = np.concatenate(wl["send_ep_idx"]).astype(np.int64)
+        self.send_sp = np.concatenate(wl["send_sp"])
+        self.in_ep = [len(x) for x in wl["send_ep_idx"]]
+        self.in_sp = [len(x) for x in wl["send_sp"]]
+        self.out_ep, self.out_sp = wl["recv_ep_cnt"], wl["recv_sp_cnt"]
+        self.nccl_bytes_per_step = 32 * len(self.send_idx) + 64 * len(self.send_sp)
+        self.L = engine.load()
+        pin = device
+        self.h_send_ep = torch.empty((len(self.send_idx), 8), dtype=torch.float32, pin_memory=pin)
+        self.h_send_sp = torch.empty((len(self.send_sp), 16), dtype=torch.float32, pin_memory=pin)
+        if device:
+            self.d_send_ep = torch.empty_like(self.h_send_ep, device="cuda")
+            self.d_send_sp = torch.empty_like(self.h_send_sp, device="cuda")
+            self._bind_store()
+        else:
+            self.store_ep = torch.zeros((len(b.epj), 8), dtype=torch.float32)
+            self.store_sp = torch.zeros((len(b.spj), 16), dtype=torch.float32)
+
+    # the library owns the j store; torch only sees it through __cuda_array_interface__
+    def _bind_store(self):
+        b, torch = self.batch, self.torch
+        pe, ps = C.c_void_p(0), C.c_void_p(0)
+        engine.check(self.L.pb_reserve_j(len(b.epj), len(b.spj), C.byref(pe), C.byref(ps)), "pb_reserve_j")
+        self._ptrs = (pe.value, ps.value)
+
+        class _Raw:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+        self.store_ep = torch.as_tensor(_Raw(pe.value, (len(b.epj), 8)), device="cuda")
+        self.store_sp = torch.as_tensor(_Raw(ps.value, (max(len(b.spj), 1), 16)), device="cuda")[:len(b.spj)]
+
+    def pack_sends(self):
+        b = self.batch
+        send_epj = np.ascontiguousarray(b.epj[self.send_idx])          # gather from the local particles
+        if len(send_epj):
+            engine.check(self.L.pb_pack_epj_host(send_epj.ctypes.data, len(send_epj), C.byref(engine.LAYOUT_EPJ),
+                                                 self.h_send_ep.data_ptr()), "pb_pack_epj_host")
+        if len(self.send_sp):
+            engine.check(self.L.pb_pack_spj_host(self.send_sp.ctypes.data, len(self.send_sp), C.byref(engine.LAYOUT_SPJ),
+                                                 self.h_send_sp.data_ptr()), "pb_pack_spj_host")
+
+    def exchange(self):
+        """LET all-to-all in the device j format; lands behind the local part of the store."""
+        torch, dist = self.torch, self.dist
+        if self.device:
+            self.d_send_ep.copy_(self.h_send_ep, non_blocking=True)
+            self.d_send_sp.copy_(self.h_send_sp, non_blocking=True)
+            se, ss = self.d_send_ep, self.d_send_sp
+        else:
+            se, ss = self.h_send_ep, self.h_send_sp
+        dist.all_to_all_single(self.store_ep[self.n_loc:], se, self.out_ep, self.in_ep)
+        dist.all_to_all_single(self.store_sp[self.n_nodes:], ss, self.out_sp, self.in_sp)
+
+    def step(self, force):
+        b, L = self.batch, self.L
+        pe, ps = C.c_void_p(0), C.c_void_p(0)
+        engine.check(L.pb_reserve_j(len(b.epj), len(b.spj), C.byref(pe), C.byref(ps)), "pb_reserve_j")
+        assert (pe.value, ps.value) == self._ptrs, "j store moved"
+        engine.check(L.pb_set_params(self.prm["eps"] ** 2, self.prm["r_out"] ** 2, self.prm["G"]), "pb_set_params")
+        engine.check(L.pb_upload_j_range(b.epj.ctypes.data, 0, self.n_loc, C.byref(engine.LAYOUT_EPJ),
+                                         b.spj.ctypes.data, 0, self.n_nodes, C.byref(engine.LAYOUT_SPJ)), "pb_upload_j_range")
+        self.pack_sends()
+        self.exchange()
+        engine.check(L.pb_publish_j(C.c_void_p(self.torch.cuda.current_stream().cuda_stream)), "pb_publish_j")
+        return engine.calc_force_all_and_write_back(b, self.prm["eps"], self.prm["r_out"], self.prm["G"],
+                                                    force=force, my_rank=self.rank, send=False)

@@ -96,10 +96,14 @@ def test_host_packers_hi_lo_split_is_exact():
     o2 = np.zeros((n, 16), dtype=np.float32)
     assert L.pb_pack_spj_host(spj.ctypes.data, n, C.byref(engine.LAYOUT_SPJ), o2.ctypes.data) == 0
     q = spj["quad"]
-    assert np.array_equal(o2[:, 7], q[:, 0].astype(np.float32))                       # qxx
-    assert np.array_equal(o2[:, 8:12], q[:, 1:5].astype(np.float32))                  # qyy qzz qxy qxz
-    assert np.array_equal(o2[:, 12], q[:, 5].astype(np.float32))                      # qyz
-    assert np.array_equal(o2[:, 13], (q[:, 0] + q[:, 1] + q[:, 2]).astype(np.float32))  # trace in fp64
+    tr = q[:, 0] + q[:, 1] + q[:, 2]                                                   # all in fp64, then cast
+    assert np.array_equal(o2[:, 7], (3 * q[:, 0] - tr).astype(np.float32))             # q'xx = 3 qxx - tr
+    assert np.array_equal(o2[:, 8], (3 * q[:, 1] - tr).astype(np.float32))             # q'yy
+    assert np.array_equal(o2[:, 9], (3 * q[:, 2] - tr).astype(np.float32))             # q'zz
+    assert np.array_equal(o2[:, 10:12], (3 * q[:, 3:5]).astype(np.float32))            # q'xy q'xz
+    assert np.array_equal(o2[:, 12], (3 * q[:, 5]).astype(np.float32))                 # q'yz
+    assert np.array_equal(o2[:, 13], tr.astype(np.float32))
+    assert np.abs(o2[:, 7] + o2[:, 8] + o2[:, 9]).max() < 1e-5                         # traceless
 
 
 def test_layouts_match_petar_structs():
