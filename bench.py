@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--nr", type=int, default=0)
     ap.add_argument("--cull", type=int, default=1)
     ap.add_argument("--jchunk", type=int, default=0)
+    ap.add_argument("--occupancy", type=int, default=2)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -242,7 +243,7 @@ def main():
     from petar_b200 import engine
     L = engine.load()
     engine.check(L.pb_init(rank, local_rank), "pb_init")
-    for k, v in (("streams", args.streams), ("nr", args.nr), ("cull", args.cull), ("jchunk", args.jchunk)):
+    for k, v in (("streams", args.streams), ("nr", args.nr), ("cull", args.cull), ("jchunk", args.jchunk), ("occupancy", args.occupancy)):
         engine.set_option(k, v)
 
     wl = build_workload(args.n, rank, world, args)

@@ -114,6 +114,8 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "nr"         Newton-Raphson steps after MUFU.RSQ (0 default, or 1).
  *   "cull"       1 (default): skip the neighbour test for j-tile segments that cannot reach any
  *                i-particle of the walk (results identical); 0: test every pair.
+ *   "occupancy"  resident CTAs per SM the force kernel is compiled for: 2 (default, 119 registers)
+ *                or 3 (80 registers).
  * Returns PB_ERR_ARG for an unknown key or value. */
 int  pb_set_option(const char* key, long long value);
 

@@ -63,7 +63,7 @@ struct Params {
 };
 
 // launchers (pb_kernels.cu)
-cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps,
+cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_blocks,
                          const Walk* walks, const Task* tasks,
                          const float4* epi, const int* id_epj, const int* id_spj,
                          const float4* epj, const float4* spj,

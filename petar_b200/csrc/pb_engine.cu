@@ -92,7 +92,7 @@ struct Engine {
     bool inited = false;
     int  rank = 0, device = 0;
     double eps2 = 0.0, rcut2 = 0.0, G = 1.0;
-    int opt_coords = 0, opt_streams = 2, opt_jchunk = 0, opt_nr = 0, opt_cull = 1;
+    int opt_coords = 0, opt_streams = 2, opt_jchunk = 0, opt_nr = 0, opt_cull = 1, opt_occ = 2;
 
     // j store
     float4* d_epj = nullptr; size_t cap_epj = 0; int n_epj = 0;
@@ -451,7 +451,7 @@ cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, boo
     prm.rcut2 = (float)E.rcut2;
     const float4* epj = direct ? (const float4*)(d_arena + p.off_lepj) : E.d_epj;
     const float4* spj = direct ? (const float4*)(d_arena + p.off_lspj) : E.d_spj;
-    cudaError_t e = launch_force(st, p.n_tasks, E.opt_nr,
+    cudaError_t e = launch_force(st, p.n_tasks, E.opt_nr, E.opt_occ,
                                  (const Walk*)(d_arena + p.off_walks), (const Task*)(d_arena + p.off_tasks),
                                  (const float4*)(d_arena + p.off_epi),
                                  (const int*)(d_arena + p.off_ide), (const int*)(d_arena + p.off_ids),
@@ -593,10 +593,10 @@ void pb_finalize(void) {
     cudaFree(E.d_epj); cudaFree(E.d_spj); cudaFreeHost(E.h_jstage);
     cudaEventDestroy(E.ev_j_ready); cudaEventDestroy(E.ev_send0); cudaEventDestroy(E.ev_send1);
     cudaStreamDestroy(E.s_upload);
-    const int coords = E.opt_coords, streams = E.opt_streams, jchunk = E.opt_jchunk, nr = E.opt_nr, cull = E.opt_cull;
+    const int coords = E.opt_coords, streams = E.opt_streams, jchunk = E.opt_jchunk, nr = E.opt_nr, cull = E.opt_cull, occ = E.opt_occ;
     const double eps2 = E.eps2, rcut2 = E.rcut2, G = E.G;
     E = Engine();
-    E.opt_coords = coords; E.opt_streams = streams; E.opt_jchunk = jchunk; E.opt_nr = nr; E.opt_cull = cull;
+    E.opt_coords = coords; E.opt_streams = streams; E.opt_jchunk = jchunk; E.opt_nr = nr; E.opt_cull = cull; E.opt_occ = occ;
     E.eps2 = eps2; E.rcut2 = rcut2; E.G = G;
 }
 
@@ -612,6 +612,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "streams must be 1..%d", kMaxStreams); E.opt_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "jchunk"))  { if (v < 0 || v > (1 << 20)) return fail(PB_ERR_ARG, "jchunk out of range"); E.opt_jchunk = (int)v; return PB_OK; }
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
+    if (!strcmp(key, "occupancy")) { if (v < 2 || v > 3) return fail(PB_ERR_ARG, "occupancy must be 2 or 3"); E.opt_occ = (int)v; return PB_OK; }
     if (!strcmp(key, "nr"))      { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nr must be 0 or 1"); E.opt_nr = (int)v; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_set_option: unknown key '%s'", key);
 }

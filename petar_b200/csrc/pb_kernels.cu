@@ -277,8 +277,8 @@ __device__ __forceinline__ void sp_pairs(const SpTile& t, int p0, int p1,
 // ------------------------------------------------------------------------------------------
 // the force kernel
 // ------------------------------------------------------------------------------------------
-template <int NR>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int NR, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
              const float4* __restrict__ epi,
              const int* __restrict__ id_epj, const int* __restrict__ id_spj,
@@ -411,17 +411,17 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
     }
 }
 
-cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps,
+cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_blocks,
                          const Walk* walks, const Task* tasks,
                          const float4* epi, const int* id_epj, const int* id_spj,
                          const float4* epj, const float4* spj,
                          double4* part4, int* partn, Params p)
 {
     if (n_tasks <= 0) return cudaSuccess;
-    if (nr_steps >= 1)
-        force_kernel<1><<<n_tasks, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
-    else
-        force_kernel<0><<<n_tasks, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
+#define PB_LAUNCH(NR_, MB_) force_kernel<NR_, MB_><<<n_tasks, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p)
+    if (nr_steps >= 1) { if (min_blocks >= 3) PB_LAUNCH(1, 3); else PB_LAUNCH(1, 2); }
+    else               { if (min_blocks >= 3) PB_LAUNCH(0, 3); else PB_LAUNCH(0, 2); }
+#undef PB_LAUNCH
     return cudaGetLastError();
 }
 
