@@ -89,6 +89,9 @@ typedef struct pb_profile {
     long long n_interaction_sp;     /* sum n_epi*n_spj  (PeTar Ep-Sp_sum) */
     long long n_kernel_launch;      /* kernels launched by this library */
     long long h2d_bytes, d2h_bytes;
+    /* host sub-phases of t_copy (seconds): task planning, packing into pinned staging, result
+     * scatter; and the time spent enqueueing copies/kernels (not part of t_copy) */
+    double t_plan, t_pack, t_unpack, t_enqueue;
 } pb_profile;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */

@@ -382,7 +382,7 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
     float4* lepj = (float4*)(arena + p.off_lepj);
     float4* lspj = (float4*)(arena + p.off_lspj);
     const bool rel = (E.opt_coords == 0);
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 1)
     for (int w = 0; w < p.n_walk; w++) {
         Walk& W = hp.walks[w];
         const char* base = (const char*)win[w].epi;
@@ -488,19 +488,32 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
     }
 
     static HostPlan hp[kMaxStreams];
+    // plan all sub-batches at once (independent of each other), then pack + enqueue them in turn
+    // so that the GPU starts on sub-batch 0 while the host packs sub-batch 1
+    const double tp0 = now_s();
     for (int s = 0; s < n_slots; s++) {
         Slot& S = E.slots[s];
         S.w_begin = cut[s]; S.w_end = cut[s + 1];
         S.active = S.w_end > S.w_begin;
+    }
+#pragma omp parallel for schedule(static, 1) num_threads(n_slots)
+    for (int s = 0; s < n_slots; s++) {
+        const Slot& S = E.slots[s];
+        if (S.active) plan_batch(win + S.w_begin, S.w_end - S.w_begin, direct, n_slots, hp[s]);
+    }
+    E.prof.t_plan += now_s() - tp0;
+    for (int s = 0; s < n_slots; s++) {
+        Slot& S = E.slots[s];
         if (!S.active) continue;
-        plan_batch(win + S.w_begin, S.w_end - S.w_begin, direct, n_slots, hp[s]);
         int rc;
         if ((rc = grow_arena(S, hp[s].p.bytes)) != PB_OK) return rc;
         if ((rc = grow_out(S, hp[s].p.n_i)) != PB_OK) return rc;
         if ((rc = grow_part(S, hp[s].p.n_part)) != PB_OK) return rc;
+        const double tp2 = now_s();
         pack_batch(win + S.w_begin, direct, Li, Lj, Ls, hp[s], S.h_arena);
         S.plan = hp[s].p;
         const double t1 = now_s();
+        E.prof.t_pack += t1 - tp2;
         // enqueue: the sub-batch's whole input travels in one copy
         if (!direct) CU(cudaStreamWaitEvent(S.stream, E.ev_j_ready, 0));
         CU(cudaEventRecord(S.ev[0], S.stream));
@@ -513,7 +526,11 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         E.prof.h2d_bytes += (long long)S.plan.bytes;
         E.prof.d2h_bytes += (long long)(sizeof(ForceOut) * S.plan.n_i);
         E.prof.n_kernel_launch += (S.plan.n_tasks > 0) + (S.plan.n_iblocks > 0);
-        E.prof.t_copy -= now_s() - t1;        // enqueue time is not packing time
+        {
+            const double te = now_s() - t1;   // enqueue time is not packing time
+            E.prof.t_copy -= te;
+            E.prof.t_enqueue += te;
+        }
 
         if (E.recording) {
             Recorded r;
@@ -745,8 +762,13 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
         CU(cudaEventElapsedTime(&ms, S.ev[1], S.ev[2])); E.prof.t_calc += 1e-3 * ms;
         CU(cudaEventElapsedTime(&ms, S.ev[2], S.ev[3])); E.prof.t_recv += 1e-3 * ms;
         const double t0 = now_s();
-        const ForceOut* src = S.h_out;
-        for (int w = S.w_begin; w < S.w_end; w++) {
+        const int nw = S.w_end - S.w_begin;
+        std::vector<size_t> first(nw + 1, 0);
+        for (int k = 0; k < nw; k++) first[k + 1] = first[k] + (size_t)ni[S.w_begin + k];
+#pragma omp parallel for schedule(static)
+        for (int k = 0; k < nw; k++) {
+            const int w = S.w_begin + k;
+            const ForceOut* src = S.h_out + first[k];
             char* dst = (char*)force[w];
             if (plain) {
                 memcpy(dst, src, sizeof(ForceOut) * (size_t)ni[w]);
@@ -758,9 +780,9 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
                     memcpy(q + L->off_nngb, &src[i].n_ngb, 8);
                 }
             }
-            src += ni[w];
         }
         E.prof.t_copy += now_s() - t0;
+        E.prof.t_unpack += now_s() - t0;
         S.active = false;
     }
     if (E.send_timed) {

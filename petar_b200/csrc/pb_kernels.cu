@@ -442,7 +442,8 @@ reduce_kernel(int n_iblocks, const IBlock* __restrict__ iblocks,
     if (lane >= ibk.n_valid) return;
     double ax = 0.0, ay = 0.0, az = 0.0, pt = 0.0;
     long long n = 0;
-    for (int c = 0; c < ibk.n_chunks; ++c) {
+#pragma unroll 8
+    for (int c = 0; c < ibk.n_chunks; ++c) {          // independent loads: unrolled for memory-level parallelism
         const int slot = ibk.part_base + c * ibk.stride + lane;
         const double4 v = part4[slot];
         ax += v.x; ay += v.y; az += v.z; pt += v.w;

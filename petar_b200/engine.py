@@ -53,7 +53,8 @@ class Profile(C.Structure):
     _fields_ = [("t_copy", C.c_double), ("t_send", C.c_double), ("t_recv", C.c_double), ("t_calc", C.c_double),
                 ("n_walk", C.c_longlong), ("n_epi", C.c_longlong), ("n_epj", C.c_longlong), ("n_spj", C.c_longlong),
                 ("n_call", C.c_longlong), ("n_interaction_ep", C.c_longlong), ("n_interaction_sp", C.c_longlong),
-                ("n_kernel_launch", C.c_longlong), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
+                ("n_kernel_launch", C.c_longlong), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
+                ("t_plan", C.c_double), ("t_pack", C.c_double), ("t_unpack", C.c_double), ("t_enqueue", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -203,11 +204,19 @@ def RetrieveForceCUDA(tag, n_walk, ni, force, direct=False):
 N_WALK_LIMIT = 200   # reference src/petar.hpp:888
 
 
-def calc_force_all_and_write_back(batch, eps, r_out, G, n_walk_limit=N_WALK_LIMIT, my_rank=0, force=None, send=True):
+def make_dispatch_tables(batch, force, n_walk_limit=N_WALK_LIMIT):
+    """The per-walk-group pointer tables FDPS holds ready when it calls dispatch (built once for a
+    prebuilt WalkBatch so that the emulated FDPS loop does not pay numpy bookkeeping per group)."""
+    return [batch.pointer_tables(force, slice(w0, min(w0 + n_walk_limit, batch.n_walk)))
+            for w0 in range(0, batch.n_walk, n_walk_limit)]
+
+
+def calc_force_all_and_write_back(batch, eps, r_out, G, n_walk_limit=N_WALK_LIMIT, my_rank=0, force=None, send=True, tables=None):
     """Emulates ``tree_soft.calcForceAllAndWriteBackMultiWalkIndex(dispatch, retrieve, 1, ..., n_walk_limit)``
     (src/petar.hpp:888-899) over a prebuilt WalkBatch: one dispatch with send_flag=true publishing all
     j, then per walk group dispatch(send_flag=false) and — after the next group's lists would have
-    been built — retrieve of the previous group.  Returns ForceSoft[n_epi_total]."""
+    been built — retrieve of the previous group.  Returns ForceSoft[n_epi_total].
+    `tables` (optional): make_dispatch_tables(batch, force, n_walk_limit), reused across steps."""
     f = np.zeros(batch.n_epi_total, dtype=ForceSoft) if force is None else force
     disp = CalcForceWithLinearCutoffCUDAMultiWalk(my_rank, eps * eps, r_out * r_out, G)
     none_u64 = np.zeros(0, dtype=np.uint64)
@@ -217,8 +226,9 @@ def calc_force_all_and_write_back(batch, eps, r_out, G, n_walk_limit=N_WALK_LIMI
                   batch.epj, len(batch.epj), batch.spj, len(batch.spj), True)
         assert rc == 0
     prev = None
-    for w0 in range(0, batch.n_walk, n_walk_limit):
-        t = batch.pointer_tables(f, slice(w0, min(w0 + n_walk_limit, batch.n_walk)))
+    if tables is None:
+        tables = make_dispatch_tables(batch, f, n_walk_limit)
+    for t in tables:
         if prev is not None:
             RetrieveForceCUDA(0, prev.n_walk, prev.n_epi, prev.force_ptrs)
         disp = CalcForceWithLinearCutoffCUDAMultiWalk(my_rank, eps * eps, r_out * r_out, G)

@@ -213,5 +213,7 @@ class DomainStepper:
         self.pack_sends()
         self.exchange()
         engine.check(L.pb_publish_j(C.c_void_p(self.torch.cuda.current_stream().cuda_stream)), "pb_publish_j")
+        if getattr(self, "_tables_for", None) is not force:
+            self._tables, self._tables_for = engine.make_dispatch_tables(b, force), force
         return engine.calc_force_all_and_write_back(b, self.prm["eps"], self.prm["r_out"], self.prm["G"],
-                                                    force=force, my_rank=self.rank, send=False)
+                                                    force=force, my_rank=self.rank, send=False, tables=self._tables)

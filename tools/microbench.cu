@@ -26,6 +26,11 @@ __global__ void probe(float* out, float seed, long long* cycles) {
             if (KIND == 4) { a[k].x = fmaxf(a[k].x, c.x) ; a[k].y = fminf(a[k].y, b.y); }         // 2x FMNMX (alu)
             if (KIND == 5) { a[k] = __ffma2_rn(a[k], b, c); a[k].x = fmaxf(a[k].x, c.y); }         // FFMA2 + FMNMX mix
             if (KIND == 6) { a[k].x = fmaf(a[k].x, b.x, c.x); a[k].y = fmaf(a[k].y, b.y, c.y); }  // 2x FFMA
+            if (KIND == 8) { a[k] = __ffma2_rn(a[k], a[k], c); }                                  // FFMA2, 2 distinct operands
+            if (KIND == 9) { a[k] = __ffma2_rn(a[k], make_float2(seed, seed), c); }               // FFMA2 with scalar-broadcast operand
+            if (KIND == 10) { a[k] = __fmul2_rn(a[k], b); }                                       // FMUL2
+            if (KIND == 11) { a[k] = __ffma2_rn(b, c, a[k]); }                                    // FFMA2 accumulate form
+            if (KIND == 12) { a[k] = __ffma2_rn(a[k], b, c); a[(k + 1) % CHAINS].x = fmaf(a[(k + 1) % CHAINS].x, b.x, c.x); } // FFMA2 + FFMA
             if (KIND == 7) { a[k] = __ffma2_rn(a[k], b, c); asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a[k].y)); } // FFMA2+MUFU
         }
     }
@@ -52,7 +57,7 @@ void run(const char* name, int inst_per_step, int warps_per_sm) {
 }
 
 int main() {
-    for (int w : {4, 8, 16, 32}) {
+    for (int w : {8, 16, 32}) {
         run<0>("FFMA", 1, w);
         run<6>("2x FFMA (indep halves)", 2, w);
         run<1>("FFMA2", 1, w);
@@ -61,6 +66,11 @@ int main() {
         run<4>("2x FMNMX", 2, w);
         run<5>("FFMA2 + FMNMX", 2, w);
         run<7>("FFMA2 + MUFU.RSQ", 2, w);
+        run<8>("FFMA2 a*a+c", 1, w);
+        run<9>("FFMA2 a*bcast(s)+c", 1, w);
+        run<10>("FMUL2", 1, w);
+        run<11>("FFMA2 b*c+a", 1, w);
+        run<12>("FFMA2 + FFMA", 2, w);
         printf("\n");
     }
     return 0;
