@@ -103,17 +103,25 @@ def build_workload(n, rank, world, args):
     """Particles, parameters and this rank's walk batch (+ LET plan for world > 1)."""
     from petar_b200 import harness as hz
     t0 = time.time()
-    mass, pos, vel = hz.make_plummer(n)
-    prm = hz.petar_auto_params(mass, vel)
-    r_in, r_out, rs = hz.particle_rout_rsearch(mass, vel, prm)
-    wl = {"prm": prm, "n": n}
+    if args.workload == "plummer":
+        mass, pos, vel = hz.make_plummer(n)
+        prm = hz.petar_auto_params(mass, vel)
+        r_in, r_out, rs = hz.particle_rout_rsearch(mass, vel, prm)
+        ptype = None
+        wl = {"prm": prm, "n": n, "n_tree": n, "name": f"plummer_equal_mass_N{n}"}
+    else:
+        # BASELINE.json configs[2]: Kroupa IMF, 10 % of the stars in binaries, artificial particles
+        P = hz.kroupa_binary_particles(n, f_bin=args.f_bin, seed=1)
+        mass, pos, vel, rs, r_in, r_out, ptype, prm = (P[k] for k in ("mass", "pos", "vel", "rs", "r_in", "r_out", "ptype", "prm"))
+        wl = {"prm": prm, "n": n, "n_tree": len(mass), "n_bin": P["n_bin"],
+              "name": f"plummer_kroupa_N{n}_bin{int(round(100 * args.f_bin))}pct_artificial"}
     if world == 1:
-        batch, _ = hz.build_walk_batch(pos, mass, rs, vel=vel, r_in=r_in, r_out=r_out)
+        batch, _ = hz.build_walk_batch(pos, mass, rs, vel=vel, r_in=r_in, r_out=r_out, ptype=ptype)
         wl["batch"] = batch
         wl["let"] = None
     else:
         from petar_b200 import multigpu
-        wl.update(multigpu.build_domain_workload(pos, mass, vel, rs, r_in, r_out, rank, world))
+        wl.update(multigpu.build_domain_workload(pos, mass, vel, rs, r_in, r_out, rank, world, ptype=ptype))
     wl["t_build"] = time.time() - t0
     return wl
 
@@ -172,7 +180,7 @@ def run_reference(args, rank, world):
 
 def workload_config(args, wl, world):
     prm = wl["prm"]
-    return {"workload": f"plummer_equal_mass_N{args.n}", "n_particles": args.n, "theta": 0.3, "n_leaf_limit": 20,
+    return {"workload": wl["name"], "n_particles": args.n, "n_tree_particles": wl["n_tree"], "theta": 0.3, "n_leaf_limit": 20,
             "n_group_limit": 512, "n_walk_limit": 200, "r_out": prm["r_out"], "dt_soft": prm["dt_soft"], "eps": prm["eps"],
             "multipole": "quadrupole", "parallelism": f"domain_decomposition_x{world}",
             "l2_policy": "inputs larger than L2: every step re-reads all dispatches' index lists, i-particles and the j store"}
@@ -220,6 +228,9 @@ def main():
     ap.add_argument("--cull", type=int, default=1)
     ap.add_argument("--jchunk", type=int, default=0)
     ap.add_argument("--occupancy", type=int, default=2)
+    ap.add_argument("--workload", default="kroupa_binaries", choices=["kroupa_binaries", "plummer"],
+                    help="kroupa_binaries = BASELINE.json configs[2] stand-in (default); plummer = equal-mass Plummer (configs[1] shape)")
+    ap.add_argument("--f-bin", type=float, default=0.1, help="fraction of stars in binaries (kroupa_binaries)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -496,7 +496,7 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         S.w_begin = cut[s]; S.w_end = cut[s + 1];
         S.active = S.w_end > S.w_begin;
     }
-#pragma omp parallel for schedule(static, 1) num_threads(n_slots)
+#pragma omp parallel for schedule(static, 1)      // same team size as the packing loops: no team re-creation
     for (int s = 0; s < n_slots; s++) {
         const Slot& S = E.slots[s];
         if (S.active) plan_batch(win + S.w_begin, S.w_end - S.w_begin, direct, n_slots, hp[s]);

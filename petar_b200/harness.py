@@ -240,3 +240,65 @@ def plummer_case(n, rank_seed=0, theta=THETA, n_group_limit=N_GROUP_LIMIT, n_lea
     batch, epi_src = build_walk_batch(pos, mass, rs, vel=vel, r_in=r_in, r_out=r_out, theta=theta,
                                       n_group_limit=n_group_limit, n_leaf_limit=n_leaf_limit)
     return batch, epi_src, prm, (mass, pos, vel)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 3 stand-in: Kroupa masses, primordial binaries, artificial particles
+# ---------------------------------------------------------------------------------------------
+def kroupa_binary_particles(n_star, f_bin=0.1, seed=1):
+    """The particle set PeTar's SOFT tree sees for an N-star Plummer cluster with a Kroupa IMF and a
+    fraction f_bin of the stars in primordial binaries, every binary carrying its artificial
+    particles (worst case of SURVEY §2 #16): per binary 2 members with their soft mass zeroed,
+    8 zero-mass tidal-tensor probes, 1 zero-mass centre-of-mass particle and 3 orbit-sample
+    pseudo-particles that carry the binary mass and are `type 0` i-particles
+    (reference src/artificial_particles.hpp:427-429, src/tidal_tensor.hpp:435-441,
+    src/pseudoparticle_multipole.hpp:58-60, src/soft_ptcl.hpp:282-284).  The geometry of the
+    artificial particles is schematic (probes on a cube of half-size 2a, samples on the relative
+    orbit): what matters for the hot path is their number, masses, types and clustering.
+
+    Returns dict(pos, mass, vel, rs, r_in, r_out, ptype, prm, n_star, n_bin)."""
+    rng = np.random.default_rng(seed)
+    _, pos, vel = make_plummer(n_star)                   # centre-of-mass phase space, MT19937 seed 0
+    m_star = kroupa_masses(n_star, rng)
+    n_bin = int(round(0.5 * f_bin * n_star))
+    prm = petar_auto_params(m_star, vel)                 # PeTar measures these on the stars
+    prm["mean_mass"] = 1.0 / n_star
+
+    # binaries = star pairs (2k, 2k+1), k < n_bin, placed around the position of star 2k
+    a = np.exp(rng.uniform(np.log(1e-6), np.log(0.8 * prm["r_in"]), n_bin))       # inside r_bin = 0.8 r_in
+    d = rng.normal(size=(n_bin, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    m1, m2 = m_star[0:2 * n_bin:2], m_star[1:2 * n_bin:2]
+    mb = m1 + m2
+    cm_pos, cm_vel = pos[0:2 * n_bin:2].copy(), vel[0:2 * n_bin:2].copy()
+    p1 = cm_pos + d * (a * m2 / mb)[:, None]
+    p2 = cm_pos - d * (a * m1 / mb)[:, None]
+    # an orthonormal frame of the orbital plane for the orbit samples
+    e2 = np.cross(d, rng.normal(size=(n_bin, 3)))
+    e2 /= np.linalg.norm(e2, axis=1)[:, None]
+    ph = rng.uniform(0, 2 * np.pi, n_bin)
+    samples = [cm_pos + 0.5 * a[:, None] * (np.cos(ph + k * 2 * np.pi / 3)[:, None] * d + np.sin(ph + k * 2 * np.pi / 3)[:, None] * e2)
+               for k in range(3)]
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64)
+    probes = (cm_pos[:, None, :] + 2.0 * a[:, None, None] * corners[None, :, :]).reshape(-1, 3)
+
+    singles = np.arange(2 * n_bin, n_star)
+    pos_all = np.concatenate([p1, p2, probes, cm_pos] + samples + [pos[singles]])
+    zeros = np.zeros(n_bin)
+    mass_all = np.concatenate([zeros, zeros, np.zeros(8 * n_bin), zeros, mb / 3, mb / 3, mb / 3, m_star[singles]])
+    vel_all = np.concatenate([cm_vel, cm_vel, np.repeat(cm_vel, 8, axis=0), cm_vel, cm_vel, cm_vel, cm_vel, vel[singles]])
+    # changeover radius / r_search follow the mass the particle stands for (member: its own, artificial: the binary's)
+    m_for_r = np.concatenate([m1, m2, np.repeat(mb, 8), mb, mb, mb, mb, m_star[singles]])
+    r_in, r_out, rs = particle_rout_rsearch(m_for_r, vel_all, prm)
+    ptype = np.ones(len(mass_all), dtype=np.int32)
+    ptype[11 * n_bin:14 * n_bin] = 0                     # orbit samples: artificial, not c.m., mass > 0
+    return dict(pos=pos_all, mass=mass_all, vel=vel_all, rs=rs, r_in=r_in, r_out=r_out, ptype=ptype, prm=prm,
+                n_star=n_star, n_bin=n_bin)
+
+
+def kroupa_binary_case(n_star, f_bin=0.1, seed=1, theta=THETA, n_group_limit=N_GROUP_LIMIT, n_leaf_limit=N_LEAF_LIMIT):
+    """Walk lists for :func:`kroupa_binary_particles` (single domain)."""
+    P = kroupa_binary_particles(n_star, f_bin, seed)
+    batch, epi_src = build_walk_batch(P["pos"], P["mass"], P["rs"], vel=P["vel"], r_in=P["r_in"], r_out=P["r_out"], ptype=P["ptype"],
+                                      theta=theta, n_group_limit=n_group_limit, n_leaf_limit=n_leaf_limit)
+    return batch, epi_src, P["prm"], P

@@ -67,7 +67,7 @@ def exchange_rows(dist, rows_per_dest, width, dtype):
 
 
 def build_domain_workload(pos, mass, vel, rs, r_in, r_out, rank, world, dist=None, theta=hz.THETA,
-                          n_leaf_limit=hz.N_LEAF_LIMIT, n_group_limit=hz.N_GROUP_LIMIT):
+                          n_leaf_limit=hz.N_LEAF_LIMIT, n_group_limit=hz.N_GROUP_LIMIT, ptype=None):
     """This rank's domain, its LET send plan, and its walk batch over local + received LET j.
 
     j-store order on every rank: EP = [local particles in local Morton order | LET EP by source
@@ -132,7 +132,7 @@ def build_domain_workload(pos, mass, vel, rs, r_in, r_out, rank, world, dist=Non
     epi["pos"] = lpos[epi_src]
     epi["r_search"] = lrs[epi_src]
     epi["rank_org"] = rank
-    epi["type"] = 1
+    epi["type"] = 1 if ptype is None else np.asarray(ptype)[my[epi_src]]
     batch = WalkBatch(epj, spj, epi, i_off, id_epj_store, ej_off, id_spj_store, sj_off)
     batch.tree = t
     return dict(batch=batch, my=my, epi_src=epi_src, n_loc=n_loc, n_nodes=n_nodes, n_let_ep=n_let_ep, n_let_sp=n_let_sp,

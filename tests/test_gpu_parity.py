@@ -325,3 +325,17 @@ def test_replay_is_deterministic_and_counts_launches(plummer100k):
     assert L.pb_replay_launches() == 2 * 2 * ((batch.n_walk + 199) // 200)    # 2 kernels x 2 streams x dispatches
     I_ep, I_sp = batch.interactions()
     print(f"[replay N=1e5] {ms_t.value:.3f} ms per step, force kernels {ms_f.value:.3f} ms -> {(I_ep + I_sp) / ms_f.value * 1e-6:.1f} Gint/s")
+
+
+def test_kroupa_binaries_with_artificial_particles():
+    """BASELINE config 3 stand-in at N = 2e4 stars: Kroupa masses (per-particle r_out / r_search),
+    10 % binaries each with 11 zero-mass and 3 massive type-0 artificial particles in a tight clump.
+    GPU semantics = NoSimd oracle semantics: zero-mass j are counted, type-0 i get a force."""
+    batch, _, prm, P = hz.kroupa_binary_case(20000)
+    assert (P["mass"] == 0).sum() == 11 * P["n_bin"] and (P["ptype"] == 0).sum() == 3 * P["n_bin"]
+    ref = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"])
+    f = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"])
+    check_tol(f, ref, "Kroupa + binaries + artificial particles, N=2e4 stars")
+    nbad = count_mismatch_report(batch, f, ref, "Kroupa + binaries")
+    assert nbad <= 1e-4 * len(f)
+    assert f["n_ngb"].max() >= 14          # members + artificial particles of a binary see each other
