@@ -60,7 +60,22 @@ struct ForceOut {
 struct Params {
     float eps2;
     float rcut2;
+    int   abs_mode;       // 1: absolute-coordinate mode (no lo parts: dx = float(xj) - float(xi))
 };
+
+// Two-float position relative to the walk origin: hi + lo = (xh + xl) - (oh + ol) to ~2^-46,
+// hi = fl((xh - oh) + (xl - ol)).  The SAME code runs on the host for i-particles and in the
+// kernel for j-particles, so a particle meeting itself gets bit-identical (hi, lo) and dx == 0.
+__host__ __device__ inline void rel_hilo(float xh, float xl, float oh, float ol, float& hi, float& lo) {
+    const float s  = xh - oh;
+    const float bb = s - xh;
+    const float e1 = (xh - (s - bb)) - (oh + bb);      // exact rounding error of s
+    const float t  = xl - ol;
+    hi = s + t;
+    const float b2 = hi - s;
+    const float e2 = (s - (hi - b2)) + (t - b2);        // exact rounding error of hi
+    lo = e1 + e2;
+}
 
 // launchers (pb_kernels.cu)
 cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_blocks,

@@ -364,7 +364,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     p.off_walks = o;   o = align_up(o + sizeof(Walk) * n_walk, 256);
     p.off_tasks = o;   o = align_up(o + sizeof(Task) * p.n_tasks, 256);
     p.off_iblocks = o; o = align_up(o + sizeof(IBlock) * p.n_iblocks, 256);
-    p.off_epi = o;     o = align_up(o + sizeof(float4) * p.n_i, 256);
+    p.off_epi = o;     o = align_up(o + 2 * sizeof(float4) * p.n_i, 256);
     p.off_ide = o;     o = align_up(o + sizeof(int) * p.n_ide, 256);
     p.off_ids = o;     o = align_up(o + sizeof(int) * p.n_ids, 256);
     p.off_lepj = o;    o = align_up(o + (size_t)PB_EPJ_DEV_BYTES * p.n_lepj, 256);
@@ -402,19 +402,20 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
         }
         W.ohx = oh[0]; W.ohy = oh[1]; W.ohz = oh[2];
         W.olx = ol[0]; W.oly = ol[1]; W.olz = ol[2];
-        float4* e = epi + W.i_off;
+        float4* e = epi + 2 * (size_t)W.i_off;           // two float4 per i: {x,y,z,rs}, {xl,yl,zl,0}
         float hmax[3] = {0.f, 0.f, 0.f}, rsmax = 0.f;
         for (int i = 0; i < W.ni; i++) {
             const char* q = base + (size_t)i * Li.stride;
-            float r[3];
+            float r[3], rl[3];
             for (int k = 0; k < 3; k++) {
                 float xh, xl;
                 split(ld(q, Li.off_pos, k), xh, xl);
-                const float d1 = xh - oh[k], d2 = xl - ol[k];
-                r[k] = d1 + d2;
+                rel_hilo(xh, xl, oh[k], ol[k], r[k], rl[k]);
+                if (!rel) rl[k] = 0.f;
             }
             const float4 v = make_float4(r[0], r[1], r[2], (float)ld(q, Li.off_rsearch));
-            e[i] = v;
+            e[2 * i] = v;
+            e[2 * i + 1] = make_float4(rl[0], rl[1], rl[2], 0.f);
             hmax[0] = std::max(hmax[0], std::fabs(v.x)); hmax[1] = std::max(hmax[1], std::fabs(v.y));
             hmax[2] = std::max(hmax[2], std::fabs(v.z)); rsmax = std::max(rsmax, v.w);
         }
@@ -422,7 +423,13 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
         // neighbour test for j segments that are provably out of reach of every i of the walk
         if (rel && E.opt_cull) { W.hx = hmax[0]; W.hy = hmax[1]; W.hz = hmax[2]; }
         else                   { W.hx = W.hy = W.hz = INFINITY; }
-        W.rsi2max = rsmax * rsmax;
+        // "near" radius: max r_search of the i-particles, and at least kPrecFactor ulps of the box
+        // half-size — inside it a single-float relative coordinate is not accurate enough against
+        // the pair separation, so those segments take the exact-dx loop
+        const float hbox = std::max(hmax[0], std::max(hmax[1], hmax[2]));
+        const float rprec = rel ? 4.0e4f * (std::nextafter(hbox, INFINITY) - hbox) : 0.f;
+        const float rnear = std::max(rsmax, rprec);
+        W.rsi2max = rnear * rnear;
         if (!direct) {
             if (W.nej) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
             if (W.nsj) memcpy(ids + W.sj_off, win[w].ids, sizeof(int) * (size_t)W.nsj);
@@ -449,6 +456,7 @@ cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, boo
     Params prm;
     prm.eps2 = (float)E.eps2;
     prm.rcut2 = (float)E.rcut2;
+    prm.abs_mode = E.opt_coords == 1 ? 1 : 0;
     const float4* epj = direct ? (const float4*)(d_arena + p.off_lepj) : E.d_epj;
     const float4* spj = direct ? (const float4*)(d_arena + p.off_lspj) : E.d_spj;
     cudaError_t e = launch_force(st, p.n_tasks, E.opt_nr, E.opt_occ,

@@ -65,10 +65,12 @@ struct KSum {
 // ------------------------------------------------------------------------------------------
 // shared-memory tiles
 // ------------------------------------------------------------------------------------------
-struct EpTile {                       // 128 pairs, 40 B per pair
-    float4 a[kTilePairs];             // {x0, x1, y0, y1}
+struct EpTile {                       // 128 pairs, 64 B per pair
+    float4 a[kTilePairs];             // {x0, x1, y0, y1}   origin-relative position, hi part
     float4 b[kTilePairs];             // {z0, z1, m0, m1}
     float2 c[kTilePairs];             // {r_search0^2, r_search1^2}
+    float4 al[kTilePairs];            // {xl0, xl1, yl0, yl1} lo part (only read in "near" segments)
+    float2 bl[kTilePairs];            // {zl0, zl1}
 };
 struct SpTile {                       // 128 pairs, 96 B per pair
     float4 q0[kTilePairs];            // {x0, x1, y0, y1}
@@ -108,16 +110,21 @@ __device__ __forceinline__ EpRegs ep_load_j(const float4* __restrict__ epj, int 
     }
     return r;
 }
-// writes j into the pair-interleaved tile; returns whether this j can be a neighbour of ANY
-// i-particle of the walk (distance from the i bounding box below max(rs_j, max rs_i), with a
-// safety margin far above fp32 rounding) — tiles segments without such a j skip the count.
-__device__ __forceinline__ bool ep_store(EpTile& t, int tid, int id, const EpRegs& r, const Walk& w) {
-    float x, y, z, m, rs2;
+// writes j into the pair-interleaved tile; returns whether this j is "near" the walk: within
+// sqrt(max(rs_j^2, w.rsi2max)) of the bounding box of the walk's i-particles (0.1 % margin, far
+// above fp32 rounding).  w.rsi2max covers max rs_i^2 AND the radius inside which the fp32
+// rounding of an origin-relative coordinate (ulp of the box half-size) is not negligible against
+// the pair separation.  Segments without a near j run the fast loop: no neighbour test (none is
+// possible), single-float dx.  Near segments run the exact loop: neighbour test and
+// dx = (xj_hi - xi_hi) + (xj_lo - xi_lo), the difference of the two-float relative positions.
+__device__ __forceinline__ bool ep_store(EpTile& t, int tid, int id, const EpRegs& r, const Walk& w, int abs_mode) {
+    float x, y, z, xl = 0.f, yl = 0.f, zl = 0.f, m, rs2;
     bool near = false;
     if (id >= 0) {
-        x = (r.a.x - w.ohx) + (r.b.x - w.olx);
-        y = (r.a.y - w.ohy) + (r.b.y - w.oly);
-        z = (r.a.z - w.ohz) + (r.b.z - w.olz);
+        rel_hilo(r.a.x, r.b.x, w.ohx, w.olx, x, xl);
+        rel_hilo(r.a.y, r.b.y, w.ohy, w.oly, y, yl);
+        rel_hilo(r.a.z, r.b.z, w.ohz, w.olz, z, zl);
+        if (abs_mode) { xl = 0.f; yl = 0.f; zl = 0.f; }   // reference arithmetic: dx = float(xj) - float(xi)
         m = r.a.w;
         rs2 = r.b.w * r.b.w;
         const float ex = fmaxf(fabsf(x) - w.hx, 0.f);
@@ -132,29 +139,42 @@ __device__ __forceinline__ bool ep_store(EpTile& t, int tid, int id, const EpReg
     float* a = reinterpret_cast<float*>(&t.a[p]);
     float* b = reinterpret_cast<float*>(&t.b[p]);
     float* c = reinterpret_cast<float*>(&t.c[p]);
+    float* al = reinterpret_cast<float*>(&t.al[p]);
+    float* bl = reinterpret_cast<float*>(&t.bl[p]);
     a[s] = x; a[2 + s] = y;
     b[s] = z; b[2 + s] = m;
     c[s] = rs2;
+    al[s] = xl; al[2 + s] = yl;
+    bl[s] = zl;
     return near;
 }
 
-template <int NR, bool COUNT>
+// NEAR = false: fast loop (13 packed FP ops per pair).  NEAR = true: exact dx + neighbour count.
+template <int NR, bool NEAR>
 __device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
-                                         float xi, float yi, float zi, float rsi2,
+                                         float xi, float yi, float zi, float xil, float yil, float zil, float rsi2,
                                          float eps2, float rcut2,
                                          float2& ax, float2& ay, float2& az, float2& pt, float2& cf) {
     const float2 nxi = bc(-xi), nyi = bc(-yi), nzi = bc(-zi), e2 = bc(eps2);
+    const float2 nxil = bc(-xil), nyil = bc(-yil), nzil = bc(-zil);
 #pragma unroll kPairUnroll
     for (int p = p0; p < p1; ++p) {
         const float4 A = t.a[p];
         const float4 B = t.b[p];
-        const float2 dx = __fadd2_rn(make_float2(A.x, A.y), nxi);
-        const float2 dy = __fadd2_rn(make_float2(A.z, A.w), nyi);
-        const float2 dz = __fadd2_rn(make_float2(B.x, B.y), nzi);
+        float2 dx = __fadd2_rn(make_float2(A.x, A.y), nxi);
+        float2 dy = __fadd2_rn(make_float2(A.z, A.w), nyi);
+        float2 dz = __fadd2_rn(make_float2(B.x, B.y), nzi);
+        if (NEAR) {
+            const float4 AL = t.al[p];
+            const float2 BL = t.bl[p];
+            dx = __fadd2_rn(dx, __fadd2_rn(make_float2(AL.x, AL.y), nxil));
+            dy = __fadd2_rn(dy, __fadd2_rn(make_float2(AL.z, AL.w), nyil));
+            dz = __fadd2_rn(dz, __fadd2_rn(BL, nzil));
+        }
         float2 r2 = __ffma2_rn(dx, dx, e2);
         r2 = __ffma2_rn(dy, dy, r2);
         r2 = __ffma2_rn(dz, dz, r2);
-        if (COUNT) {
+        if (NEAR) {
             // neighbour flags as 0.0f/1.0f, summed packed; exact (counts per tile are tiny)
             const float2 C = t.c[p];
             const float2 f = make_float2((r2.x < fmaxf(C.x, rsi2)) ? 1.f : 0.f,
@@ -302,8 +322,11 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
     // i-particle (registers): relative to the walk origin already (host formed x_i - origin in fp64)
     const int  i_loc  = task.i_first + ib * 32 + lane;
     const bool ivalid = busy && (i_loc < w.ni);
-    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ivalid) pi = __ldg(epi + w.i_off + i_loc);
+    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), pil = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ivalid) {
+        pi  = __ldg(epi + 2 * (size_t)(w.i_off + i_loc));        // {x, y, z, r_search}: relative position, hi part
+        pil = __ldg(epi + 2 * (size_t)(w.i_off + i_loc) + 1);    // {xl, yl, zl, -}: lo part
+    }
     const float rsi2 = ivalid ? pi.w * pi.w : -1.f;
 
     KSum kx, ky, kz, kp;
@@ -319,7 +342,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
         EpRegs jr  = ep_load_j(epj, id_cur);
         int id_nxt = ep_load_id(ids, kTileJ + tid, task.j_count);
         {
-            const bool nr_ = ep_store(sm.ep[0], tid, id_cur, jr, w);
+            const bool nr_ = ep_store(sm.ep[0], tid, id_cur, jr, w, prm.abs_mode);
             const unsigned bal = __ballot_sync(0xffffffffu, nr_);
             if (lane == 0) near_flag[0][warp] = (bal != 0u);
         }
@@ -337,15 +360,15 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 for (int seg = p0; seg < p1; seg += 16) {
                     const int e = min(seg + 16, p1);
                     if (near_flag[k & 1][seg >> 4])
-                        ep_pairs<NR, true>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                        ep_pairs<NR, true>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
                     else
-                        ep_pairs<NR, false>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                        ep_pairs<NR, false>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
                 }
                 kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
                 cnt += (int)(cf.x + cf.y);
             }
             if (more) {
-                const bool nr_ = ep_store(sm.ep[(k + 1) & 1], tid, id_nxt, jr, w);
+                const bool nr_ = ep_store(sm.ep[(k + 1) & 1], tid, id_nxt, jr, w, prm.abs_mode);
                 const unsigned bal = __ballot_sync(0xffffffffu, nr_);
                 if (lane == 0) near_flag[(k + 1) & 1][warp] = (bal != 0u);
             }
