@@ -52,6 +52,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per force-kernel launch from the committed ncu
+    --set full capture (it cannot be measured inside a timed run); None if no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1_force_kernel_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -223,7 +234,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per step of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--nr", type=int, default=0)
     ap.add_argument("--cull", type=int, default=1)
     ap.add_argument("--jchunk", type=int, default=0)
@@ -353,7 +364,10 @@ def main():
             # value leg (K x all kernels) + its force-only timing pass (K x force kernels) + e2e leg (counted by the library)
             "gpu_launches": int(launches_per_step * args.steps + (launches_per_step // 2) * args.steps + prof["n_kernel_launch"]),
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                         "traffic": None, "kernel": "pb::force_kernel", "ms_per_step_kernel": ms_force,
+                         "traffic": ncu_traffic(), "traffic_unit": "DRAM bytes per launch (ncu capture, profiles/)",
+                         "kernel": "pb::force_kernel", "ms_per_step_kernel": ms_force,
+                         "force_kernel_launches_per_step": launches_per_step // 2,
+                         "algorithmic_flop_per_launch": flops / max(1, (launches_per_step // 2) * world),
                          "flop_convention": "38 per EP-EP, 65 per EP-SP interaction (north star)",
                          "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz={f_mhz:.0f} from {peak_src} (non-tensor FP32; "
                                         "MEASURED_PEAKS has no FP32-pipe figure)",

@@ -112,7 +112,7 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *                1: absolute coordinates cast to fp32 — dx = float(xj) - float(xi), the exact
  *                   arithmetic the reference kernel and the CPU changeover correction replay use
  *                   (src/force_gpu_cuda.cu:58-60, src/hard.hpp:1346-1351).
- *   "streams"    number of CUDA streams one dispatch is split across (default 2, 1..8).
+ *   "streams"    number of CUDA streams one dispatch is split across (default 4, 1..8).
  *   "jchunk"     target EP j-chunk per warp-task (default 0 = automatic).
  *   "nr"         Newton-Raphson steps after MUFU.RSQ (0 default, or 1).
  *   "cull"       1 (default): skip the neighbour test for j-tile segments that cannot reach any

@@ -197,7 +197,11 @@ def test_plummer100k_option_matrix(plummer100k):
     r = ref[:sub.n_epi_total]
     engine.set_option("cull", 0)
     f = engine.calc_force_all_and_write_back(sub, prm["eps"], prm["r_out"], prm["G"])
-    assert np.array_equal(f, base), "neighbour culling changed results"
+    # cull=0 sends every segment through the exact loop (two-float dx + neighbour test): counts must
+    # be identical, forces may differ from the mixed fast/exact default only at fp32 rounding level
+    assert np.array_equal(f["n_ngb"], base["n_ngb"]), "neighbour culling changed the counts"
+    check_tol(f, r, "cull=0 (exact loop everywhere)")
+    assert np.abs(f["acc"] - base["acc"]).max() <= 2e-6 * np.abs(base["acc"]).max()
     engine.set_option("cull", 1)
     for ns in (1, 4):
         engine.set_option("streams", ns)
