@@ -242,6 +242,7 @@ def main():
     ap.add_argument("--workload", default="kroupa_binaries", choices=["kroupa_binaries", "plummer"],
                     help="kroupa_binaries = BASELINE.json configs[2] stand-in (default); plummer = equal-mass Plummer (configs[1] shape)")
     ap.add_argument("--f-bin", type=float, default=0.1, help="fraction of stars in binaries (kroupa_binaries)")
+    ap.add_argument("--opt", action="append", default=[], help="extra library option key=value (pb_set_option), repeatable")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -267,6 +268,9 @@ def main():
     engine.check(L.pb_init(rank, local_rank), "pb_init")
     for k, v in (("streams", args.streams), ("nr", args.nr), ("cull", args.cull), ("jchunk", args.jchunk), ("occupancy", args.occupancy)):
         engine.set_option(k, v)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        engine.set_option(k, int(v))
 
     wl = build_workload(args.n, rank, world, args)
     batch, prm = wl["batch"], wl["prm"]
@@ -374,6 +378,9 @@ def main():
                          "note": "bound is the non-tensor FP32/issue pipe, not HBM or tensor: ~300-500 flop per HBM byte"},
             "clocks": clocks,
         }
+        if stepper is not None and stepper.n_steps:
+            line["e2e"]["rank0_step_phases_ms"] = {k: v * 1e3 / stepper.n_steps for k, v in stepper.host_s.items()}
+            line["e2e"]["omp_threads_per_rank"] = int(os.environ.get("OMP_NUM_THREADS", "0"))
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline_leg(args, wl)

@@ -187,6 +187,9 @@ int  pb_publish_j(void* cuda_stream);
 /* Pack host j to the device format into caller-provided HOST buffers (for building LET send
  * buffers). */
 int  pb_pack_epj_host(const void* epj, int n, const pb_layout_epj* l, void* out32);
+/* Same, gathering: out32[k] = pack(epj[idx[k]]), k < n (LET send lists are index lists into the
+ * local particle array). */
+int  pb_pack_epj_host_indexed(const void* epj, const long long* idx, int n, const pb_layout_epj* l, void* out32);
 int  pb_pack_spj_host(const void* spj, int n, const pb_layout_spj* l, void* out64);
 
 #ifdef __cplusplus

@@ -92,7 +92,7 @@ struct Engine {
     bool inited = false;
     int  rank = 0, device = 0;
     double eps2 = 0.0, rcut2 = 0.0, G = 1.0;
-    int opt_coords = 0, opt_streams = 4, opt_jchunk = 0, opt_nr = 0, opt_cull = 1, opt_occ = 2;
+    int opt_coords = 0, opt_streams = 4, opt_jchunk = 0, opt_nr = 0, opt_cull = 1, opt_occ = 2, opt_lead = 1;
 
     // j store
     float4* d_epj = nullptr; size_t cap_epj = 0; int n_epj = 0;
@@ -481,8 +481,10 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         cum[w + 1] = cum[w] + (double)win[w].ni * ((double)win[w].nej + 2.0 * (double)win[w].nsj) + 1.0;
     std::vector<int> cut(n_slots + 1, 0);
     cut[n_slots] = n_walk;
+    // the first sub-batch is half the size of the others: the GPU is idle until its copy lands
+    const double unit = cum[n_walk] / (n_slots - 0.5);
     for (int s = 1; s < n_slots; s++) {
-        const double target = cum[n_walk] * s / n_slots;
+        const double target = E.opt_lead ? unit * (s - 0.5) : cum[n_walk] * s / n_slots;
         cut[s] = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
         cut[s] = std::max(cut[s], cut[s - 1]);
         cut[s] = std::min(cut[s], n_walk);
@@ -618,10 +620,10 @@ void pb_finalize(void) {
     cudaFree(E.d_epj); cudaFree(E.d_spj); cudaFreeHost(E.h_jstage);
     cudaEventDestroy(E.ev_j_ready); cudaEventDestroy(E.ev_send0); cudaEventDestroy(E.ev_send1);
     cudaStreamDestroy(E.s_upload);
-    const int coords = E.opt_coords, streams = E.opt_streams, jchunk = E.opt_jchunk, nr = E.opt_nr, cull = E.opt_cull, occ = E.opt_occ;
+    const int coords = E.opt_coords, streams = E.opt_streams, jchunk = E.opt_jchunk, nr = E.opt_nr, cull = E.opt_cull, occ = E.opt_occ, lead = E.opt_lead;
     const double eps2 = E.eps2, rcut2 = E.rcut2, G = E.G;
     E = Engine();
-    E.opt_coords = coords; E.opt_streams = streams; E.opt_jchunk = jchunk; E.opt_nr = nr; E.opt_cull = cull; E.opt_occ = occ;
+    E.opt_coords = coords; E.opt_streams = streams; E.opt_jchunk = jchunk; E.opt_nr = nr; E.opt_cull = cull; E.opt_occ = occ; E.opt_lead = lead;
     E.eps2 = eps2; E.rcut2 = rcut2; E.G = G;
 }
 
@@ -637,6 +639,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "streams must be 1..%d", kMaxStreams); E.opt_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "jchunk"))  { if (v < 0 || v > (1 << 20)) return fail(PB_ERR_ARG, "jchunk out of range"); E.opt_jchunk = (int)v; return PB_OK; }
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
+    if (!strcmp(key, "lead"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "lead must be 0 or 1"); E.opt_lead = (int)v; return PB_OK; }
     if (!strcmp(key, "occupancy")) { if (v < 2 || v > 3) return fail(PB_ERR_ARG, "occupancy must be 2 or 3"); E.opt_occ = (int)v; return PB_OK; }
     if (!strcmp(key, "nr"))      { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nr must be 0 or 1"); E.opt_nr = (int)v; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_set_option: unknown key '%s'", key);
@@ -711,6 +714,25 @@ int pb_upload_j(const void* epj, int n_epj, const pb_layout_epj* lepj,
 int pb_pack_epj_host(const void* epj, int n, const pb_layout_epj* l, void* out32) {
     if (n < 0 || (n && (!epj || !l || !out32))) return fail(PB_ERR_ARG, "pb_pack_epj_host: bad argument");
     if (n) pack_epj(epj, n, *l, (float4*)out32);
+    return PB_OK;
+}
+
+int pb_pack_epj_host_indexed(const void* epj, const long long* idx, int n, const pb_layout_epj* l, void* out32) {
+    if (n < 0 || (n && (!epj || !idx || !l || !out32))) return fail(PB_ERR_ARG, "pb_pack_epj_host_indexed: bad argument");
+    const char* base = (const char*)epj;
+    float4* out = (float4*)out32;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        const char* p = base + (size_t)idx[i] * l->stride;
+        float4 a, b;
+        split(ld(p, l->off_pos, 0), a.x, b.x);
+        split(ld(p, l->off_pos, 1), a.y, b.y);
+        split(ld(p, l->off_pos, 2), a.z, b.z);
+        a.w = (float)ld(p, l->off_mass);
+        b.w = (float)ld(p, l->off_rsearch);
+        out[2 * (size_t)i]     = a;
+        out[2 * (size_t)i + 1] = b;
+    }
     return PB_OK;
 }
 

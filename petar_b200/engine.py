@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "pb_init", "pb_finalize", "pb_abi_version", "pb_last_error", "pb_set_params", "pb_set_option",
     "pb_upload_j", "pb_dispatch_index", "pb_dispatch_direct", "pb_retrieve", "pb_get_profile",
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
-    "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_spj_host",
+    "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
 ]
 
 _lib = None
@@ -111,6 +111,7 @@ def load():
     L.pb_upload_j_range.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(LayoutEpj), _vp, C.c_int, C.c_int, C.POINTER(LayoutSpj)]
     L.pb_publish_j.argtypes = [_vp]
     L.pb_pack_epj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutEpj), _vp]
+    L.pb_pack_epj_host_indexed.argtypes = [_vp, _vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_spj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutSpj), _vp]
     _lib = L
     return L

@@ -154,6 +154,7 @@ class DomainStepper:
         self.in_sp = [len(x) for x in wl["send_sp"]]
         self.out_ep, self.out_sp = wl["recv_ep_cnt"], wl["recv_sp_cnt"]
         self.nccl_bytes_per_step = 32 * len(self.send_idx) + 64 * len(self.send_sp)
+        self.host_s, self.n_steps = {}, 0          # wall-clock of the step's host phases (seconds, accumulated)
         self.L = engine.load()
         pin = device
         self.h_send_ep = torch.empty((len(self.send_idx), 8), dtype=torch.float32, pin_memory=pin)
@@ -182,10 +183,9 @@ class DomainStepper:
 
     def pack_sends(self):
         b = self.batch
-        send_epj = np.ascontiguousarray(b.epj[self.send_idx])          # gather from the local particles
-        if len(send_epj):
-            engine.check(self.L.pb_pack_epj_host(send_epj.ctypes.data, len(send_epj), C.byref(engine.LAYOUT_EPJ),
-                                                 self.h_send_ep.data_ptr()), "pb_pack_epj_host")
+        if len(self.send_idx):                                          # gather from the local particles while packing
+            engine.check(self.L.pb_pack_epj_host_indexed(b.epj.ctypes.data, self.send_idx.ctypes.data, len(self.send_idx),
+                                                         C.byref(engine.LAYOUT_EPJ), self.h_send_ep.data_ptr()), "pb_pack_epj_host_indexed")
         if len(self.send_sp):
             engine.check(self.L.pb_pack_spj_host(self.send_sp.ctypes.data, len(self.send_sp), C.byref(engine.LAYOUT_SPJ),
                                                  self.h_send_sp.data_ptr()), "pb_pack_spj_host")
@@ -203,17 +203,27 @@ class DomainStepper:
         dist.all_to_all_single(self.store_sp[self.n_nodes:], ss, self.out_sp, self.in_sp)
 
     def step(self, force):
+        import time
         b, L = self.batch, self.L
+        t0 = time.perf_counter()
         pe, ps = C.c_void_p(0), C.c_void_p(0)
         engine.check(L.pb_reserve_j(len(b.epj), len(b.spj), C.byref(pe), C.byref(ps)), "pb_reserve_j")
         assert (pe.value, ps.value) == self._ptrs, "j store moved"
         engine.check(L.pb_set_params(self.prm["eps"] ** 2, self.prm["r_out"] ** 2, self.prm["G"]), "pb_set_params")
         engine.check(L.pb_upload_j_range(b.epj.ctypes.data, 0, self.n_loc, C.byref(engine.LAYOUT_EPJ),
                                          b.spj.ctypes.data, 0, self.n_nodes, C.byref(engine.LAYOUT_SPJ)), "pb_upload_j_range")
+        t1 = time.perf_counter()
         self.pack_sends()
+        t2 = time.perf_counter()
         self.exchange()
         engine.check(L.pb_publish_j(C.c_void_p(self.torch.cuda.current_stream().cuda_stream)), "pb_publish_j")
+        t3 = time.perf_counter()
         if getattr(self, "_tables_for", None) is not force:
             self._tables, self._tables_for = engine.make_dispatch_tables(b, force), force
-        return engine.calc_force_all_and_write_back(b, self.prm["eps"], self.prm["r_out"], self.prm["G"],
-                                                    force=force, my_rank=self.rank, send=False, tables=self._tables)
+        f = engine.calc_force_all_and_write_back(b, self.prm["eps"], self.prm["r_out"], self.prm["G"],
+                                                 force=force, my_rank=self.rank, send=False, tables=self._tables)
+        t4 = time.perf_counter()
+        for k, v in (("upload_local_j", t1 - t0), ("pack_let", t2 - t1), ("let_all_to_all_enqueue", t3 - t2), ("dispatch_retrieve_loop", t4 - t3)):
+            self.host_s[k] = self.host_s.get(k, 0.0) + v
+        self.n_steps += 1
+        return f
