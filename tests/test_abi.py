@@ -106,6 +106,23 @@ def test_host_packers_hi_lo_split_is_exact():
     assert np.abs(o2[:, 7] + o2[:, 8] + o2[:, 9]).max() < 1e-5                         # traceless
 
 
+def test_indexed_packer_equals_gather_then_pack():
+    L = engine.load()
+    rng = np.random.default_rng(3)
+    n = 5000
+    epj = np.zeros(n, dtype=EPJSoft)
+    epj["pos"] = rng.normal(size=(n, 3))
+    epj["mass"] = rng.random(n)
+    epj["r_search"] = rng.random(n)
+    idx = rng.integers(0, n, 1234).astype(np.int64)
+    a = np.zeros((len(idx), 8), dtype=np.float32)
+    b = np.zeros((len(idx), 8), dtype=np.float32)
+    g = np.ascontiguousarray(epj[idx])
+    assert L.pb_pack_epj_host(g.ctypes.data, len(idx), C.byref(engine.LAYOUT_EPJ), a.ctypes.data) == 0
+    assert L.pb_pack_epj_host_indexed(epj.ctypes.data, idx.ctypes.data, len(idx), C.byref(engine.LAYOUT_EPJ), b.ctypes.data) == 0
+    assert np.array_equal(a, b)
+
+
 def test_layouts_match_petar_structs():
     assert (engine.LAYOUT_EPI.stride, engine.LAYOUT_EPI.off_pos, engine.LAYOUT_EPI.off_rsearch) == (48, 8, 32)
     assert (engine.LAYOUT_EPJ.stride, engine.LAYOUT_EPJ.off_pos, engine.LAYOUT_EPJ.off_mass, engine.LAYOUT_EPJ.off_rsearch) == (120, 16, 8, 80)

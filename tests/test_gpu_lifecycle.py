@@ -1,0 +1,92 @@
+"""GPU tests of the engine's life cycle and of the layout-agnostic C ABI: re-initialisation,
+buffer growth, foreign struct layouts (a KDKDK_4TH-like build of PeTar), the indexed LET packer."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from petar_b200 import engine, harness as hz
+from petar_b200.types import ForceSoft
+from petar_b200.walks import WalkBatch
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(f_acc, f_pot, ref):
+    ea = np.linalg.norm(f_acc - ref["acc"], axis=1) / np.linalg.norm(ref["acc"], axis=1)
+    ep = np.abs((f_pot - ref["pot"]) / ref["pot"])
+    assert np.median(ea) <= 1e-6 and ea.max() <= 1e-4 and np.median(ep) <= 1e-6 and ep.max() <= 1e-4
+
+
+def test_finalize_and_reinit_and_growth():
+    L = engine.load()
+    small, _, prm_s, _ = hz.plummer_case(500)
+    big, _, prm_b, _ = hz.plummer_case(30000)
+    f1 = engine.calc_force_all_and_write_back(small, prm_s["eps"], prm_s["r_out"], prm_s["G"])
+    f2 = engine.calc_force_all_and_write_back(big, prm_b["eps"], prm_b["r_out"], prm_b["G"])      # every buffer grows
+    L.pb_finalize()
+    engine.set_option("streams", 3)
+    f3 = engine.calc_force_all_and_write_back(small, prm_s["eps"], prm_s["r_out"], prm_s["G"])    # lazy re-init
+    assert np.array_equal(f1["n_ngb"], f3["n_ngb"]) and np.allclose(f1["acc"], f3["acc"], rtol=1e-12, atol=0)
+    _tol(f2["acc"], f2["pot"], ob.walks_index(big, prm_b["eps"], prm_b["r_out"], prm_b["G"]))
+    engine.set_option("streams", 4)
+
+
+def test_foreign_struct_layouts():
+    """PeTar built with KDKDK_4TH has EPISoft/EPJSoft with an extra `acc` member and ForceSoft with
+    `acorr` (reference src/soft_ptcl.hpp:8-10, 279-281, 316-318).  The C ABI takes stride + offsets,
+    so such arrays bind without recompiling; members the kernel does not own must stay untouched."""
+    L = engine.load()
+    batch, _, prm, _ = hz.plummer_case(3000)
+    epi4 = np.dtype([("id", "<i8"), ("pos", "<f8", (3,)), ("r_search", "<f8"), ("rank_org", "<i4"), ("type", "<i4"), ("acc", "<f8", (3,))], align=True)
+    epj4 = np.dtype([("id", "<i8"), ("mass", "<f8"), ("pos", "<f8", (3,)), ("vel", "<f8", (3,)), ("acc", "<f8", (3,)), ("r_in", "<f8"),
+                     ("r_out", "<f8"), ("r_search", "<f8"), ("r_scale_next", "<f8"), ("group_data", "<i8", (2,)), ("rank_org", "<i4"), ("adr_org", "<i4")], align=True)
+    frc4 = np.dtype([("acc", "<f8", (3,)), ("pot", "<f8"), ("acorr", "<f8", (3,)), ("n_ngb", "<i8")], align=True)
+    ei = np.zeros(len(batch.epi), dtype=epi4)
+    ej = np.zeros(len(batch.epj), dtype=epj4)
+    for k in ("pos", "r_search"):
+        ei[k] = batch.epi[k]
+        ej[k] = batch.epj[k]
+    ej["mass"] = batch.epj["mass"]
+    ei["acc"] = 7.0
+    fr = np.zeros(batch.n_epi_total, dtype=frc4)
+    fr["acorr"] = 3.25
+    lei = engine.LayoutEpi(epi4.itemsize, epi4.fields["pos"][1], epi4.fields["r_search"][1])
+    lej = engine.LayoutEpj(epj4.itemsize, epj4.fields["pos"][1], epj4.fields["mass"][1], epj4.fields["r_search"][1])
+    lfr = engine.LayoutForce(frc4.itemsize, frc4.fields["acc"][1], frc4.fields["pot"][1], frc4.fields["n_ngb"][1])
+    io = batch.i_off[:-1]
+    epi_ptrs = (ei.ctypes.data + io * epi4.itemsize).astype(np.uint64)
+    frc_ptrs = (fr.ctypes.data + io * frc4.itemsize).astype(np.uint64)
+    ide_ptrs = (batch.id_epj.ctypes.data + batch.ej_off[:-1] * 4).astype(np.uint64)
+    ids_ptrs = (batch.id_spj.ctypes.data + batch.sj_off[:-1] * 4).astype(np.uint64)
+    n_epi, n_epj, n_spj = batch.n_epi, batch.n_epj, batch.n_spj
+    engine.check(L.pb_set_params(prm["eps"] ** 2, prm["r_out"] ** 2, prm["G"]), "set_params")
+    engine.check(L.pb_upload_j(ej.ctypes.data, len(ej), C.byref(lej), batch.spj.ctypes.data, len(batch.spj), C.byref(engine.LAYOUT_SPJ)), "upload_j")
+    engine.check(L.pb_dispatch_index(batch.n_walk, epi_ptrs.ctypes.data, n_epi.ctypes.data, C.byref(lei), ide_ptrs.ctypes.data, n_epj.ctypes.data,
+                                     ids_ptrs.ctypes.data, n_spj.ctypes.data), "dispatch_index")
+    engine.check(L.pb_retrieve(batch.n_walk, n_epi.ctypes.data, frc_ptrs.ctypes.data, C.byref(lfr)), "retrieve")
+    ref = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"])
+    _tol(fr["acc"], fr["pot"], ref)
+    assert np.array_equal(fr["n_ngb"], ref["n_ngb"])
+    assert np.all(fr["acorr"] == 3.25), "retrieve wrote outside acc / pot / n_ngb"
+
+
+def test_monopole_only_superparticles():
+    """pb_layout_spj.has_quad = 0 (PS::SPJMonopoleInAndOut, a build without USE_QUAD)."""
+    L = engine.load()
+    batch, _, prm, _ = hz.plummer_case(2000)
+    mono = np.zeros(len(batch.spj), dtype=np.dtype([("mass", "<f8"), ("pos", "<f8", (3,))], align=True))
+    mono["mass"], mono["pos"] = batch.spj["mass"], batch.spj["pos"]
+    lsp = engine.LayoutSpj(32, 8, 0, 0, 0)
+    f = np.zeros(batch.n_epi_total, dtype=ForceSoft)
+    t = batch.pointer_tables(f)
+    engine.check(L.pb_set_params(prm["eps"] ** 2, prm["r_out"] ** 2, prm["G"]), "set_params")
+    engine.check(L.pb_upload_j(batch.epj.ctypes.data, len(batch.epj), C.byref(engine.LAYOUT_EPJ), mono.ctypes.data, len(mono), C.byref(lsp)), "upload_j")
+    engine.check(L.pb_dispatch_index(t.n_walk, t.epi_ptrs.ctypes.data, t.n_epi.ctypes.data, C.byref(engine.LAYOUT_EPI), t.id_epj_ptrs.ctypes.data,
+                                     t.n_epj.ctypes.data, t.id_spj_ptrs.ctypes.data, t.n_spj.ctypes.data), "dispatch_index")
+    engine.check(L.pb_retrieve(t.n_walk, t.n_epi.ctypes.data, t.force_ptrs.ctypes.data, C.byref(engine.LAYOUT_FORCE)), "retrieve")
+    zq = WalkBatch(batch.epj, batch.spj.copy(), batch.epi, batch.i_off, batch.id_epj, batch.ej_off, batch.id_spj, batch.sj_off)
+    zq.spj["quad"] = 0.0
+    ref = ob.walks_index(zq, prm["eps"], prm["r_out"], prm["G"])
+    _tol(f["acc"], f["pot"], ref)
