@@ -386,6 +386,21 @@ def main():
                 line["cpu_baseline"] = cpu_baseline_leg(args, wl)
             except Exception as ex:  # the checker must never take the bench down
                 line["cpu_baseline"] = {"value": None, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
+            # informational second baseline: the reference's own CUDA kernels and host
+            # protocol (blocking copies, default stream, 1 warp per block) on this same GPU and lists
+            try:
+                from oracle import binding as ob
+                if ob.ref_cuda_available():
+                    L.pb_finalize()                       # release our device buffers first
+                    ob.ref_cuda_step(batch, eps, r_out, G)          # warm-up (allocations)
+                    _, ms_k, ms_w = ob.ref_cuda_step(batch, eps, r_out, G)
+                    line["reference_cuda_kernels"] = {
+                        "kernels_ms_per_step": ms_k, "kernels_ginteractions_per_s": (I_ep + I_sp) / (ms_k * 1e-3) * 1e-9,
+                        "e2e_ms_per_step": ms_w, "e2e_ginteractions_per_s": (I_ep + I_sp) / (ms_w * 1e-3) * 1e-9,
+                        "note": "informational: reference src/force_gpu_cuda.cu device code compiled for sm_100a, host side restated "
+                                "(oracle/ref_cuda_driver.cu); same GPU, same walk lists, 200 walks per dispatch"}
+            except Exception as ex:  # noqa: BLE001
+                line["reference_cuda_kernels"] = {"unavailable": repr(ex)}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -212,3 +212,33 @@ def simdtest_inputs(n_epi=1000, n_epj=2000, n_spj=1000):
 
 
 SIMDTEST_PARAMS = dict(eps=1e-4, r_out=0.01, G=1.0)  # reference src/simd_test.cxx:65-67
+
+
+# ---- informational second baseline: the reference's own CUDA kernels on this GPU ------------
+_ref_cuda = None
+
+
+def ref_cuda_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libpetar_ref_cuda.so"))
+
+
+def ref_cuda_step(batch, eps, r_out, G, n_walk_limit=200):
+    """One tree step through the reference's CUDA kernels (device code extracted at build time from
+    /root/reference/src/force_gpu_cuda.cu, host side restated in oracle/ref_cuda_driver.cu).
+    Returns (ForceSoft[...], ms of the two kernels summed over dispatches, ms wall-clock of the step)."""
+    global _ref_cuda
+    if _ref_cuda is None:
+        L = C.CDLL(os.path.join(_HERE, "_ref", "libpetar_ref_cuda.so"))
+        L.refcuda_step.argtypes = [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp,
+                                   C.c_double, C.c_double, C.c_double, C.c_int, _vp]
+        _ref_cuda = L
+    force = new_force(batch.n_epi_total)
+    t = batch.pointer_tables(force)
+    ms = np.zeros(2, dtype=np.float32)
+    rc = _ref_cuda.refcuda_step(t.n_walk, t.epi_ptrs.ctypes.data, t.n_epi.ctypes.data, t.id_epj_ptrs.ctypes.data, t.n_epj.ctypes.data,
+                                t.id_spj_ptrs.ctypes.data, t.n_spj.ctypes.data, _chk(batch.epj, EPJSoft), len(batch.epj),
+                                _chk(batch.spj, SPJQuad), len(batch.spj), t.force_ptrs.ctypes.data,
+                                eps * eps, r_out * r_out, G, int(n_walk_limit), ms.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("reference CUDA baseline failed")
+    return force, float(ms[0]), float(ms[1])
