@@ -144,6 +144,18 @@ int  pb_dispatch_direct(int n_walk,
  * n_walk / ni must equal those of the dispatch being retrieved. */
 int  pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_force* lforce);
 
+/* ---- direct-sum field query ---------------------------------------------
+ * acc and potential at n_points arbitrary positions from n_ptcl particles, eps = 0, no cutoff, G
+ * included, particles with mass <= 0 skipped: what the AMUSE worker's get_gravity_at_point /
+ * get_potential_at_point compute with CalcForcePPSimd per point on the CPU (reference
+ * amuse-interface/interface.cc:966-1030, src/soft_force.hpp:285-344).  `ptcl` is described by
+ * stride + offsets of pos (3 doubles) and mass (double), e.g. PeTar's FPSoft array.  Outputs are
+ * ASSIGNED; any of ax/ay/az/pot may be NULL.  Replaces the content of the j store (FDPS re-publishes
+ * it at the start of every tree step anyway). */
+int  pb_field_at_points(const double* x, const double* y, const double* z, int n_points,
+                        const void* ptcl, int n_ptcl, size_t stride, size_t off_pos, size_t off_mass,
+                        double G, double* ax, double* ay, double* az, double* pot);
+
 /* ---- profiling ---------------------------------------------------------------------------- */
 int  pb_get_profile(pb_profile* out, int reset);
 

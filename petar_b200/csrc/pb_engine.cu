@@ -289,12 +289,14 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     for (int w = 0; w < n_walk; w++) {
         Walk& W = hp.walks[w];
         W.i_off = (int)i_off; W.ni = win[w].ni;
-        W.ej_off = (int)ide;  W.nej = win[w].nej;
+        // index mode with a null EP list pointer = DENSE walk: its EP list is the whole j store in order
+        const bool dense = !direct && win[w].ide == nullptr && win[w].nej > 0;
+        W.ej_off = dense ? -1 : (int)ide;  W.nej = win[w].nej;
         W.sj_off = (int)ids;  W.nsj = win[w].nsj;
         W.ohx = W.ohy = W.ohz = W.olx = W.oly = W.olz = 0.f;
         W.hx = W.hy = W.hz = INFINITY; W.rsi2max = 0.f;
         i_off += (size_t)win[w].ni;
-        ide += align_up((size_t)win[w].nej, 4);
+        if (!dense) ide += align_up((size_t)win[w].nej, 4);
         ids += align_up((size_t)win[w].nsj, 4);
         if (direct) {
             hp.lepj_off[w] = lepj; hp.lspj_off[w] = lspj;
@@ -431,7 +433,7 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
         const float rnear = std::max(rsmax, rprec);
         W.rsi2max = rnear * rnear;
         if (!direct) {
-            if (W.nej) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
+            if (W.nej && W.ej_off >= 0) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
             if (W.nsj) memcpy(ids + W.sj_off, win[w].ids, sizeof(int) * (size_t)W.nsj);
         } else {
             const size_t e0 = hp.lepj_off[w], s0 = hp.lspj_off[w];
@@ -821,6 +823,63 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
         E.send_timed = false;
     }
     E.outstanding = false;
+    return PB_OK;
+}
+
+// ---- direct-sum field query ---------------------------------------------------
+int pb_field_at_points(const double* x, const double* y, const double* z, int n_points,
+                       const void* ptcl, int n_ptcl, size_t stride, size_t off_pos, size_t off_mass,
+                       double G, double* ax, double* ay, double* az, double* pot) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    if (E.outstanding) return fail(PB_ERR_PROTOCOL, "pb_field_at_points while a dispatch is outstanding");
+    if (n_points < 0 || n_ptcl < 0 || (n_points && (!x || !y || !z)) || (n_ptcl && !ptcl))
+        return fail(PB_ERR_ARG, "pb_field_at_points: bad argument");
+    // j = particles with mass > 0 (as CalcForcePPSimd filters, reference src/soft_force.hpp:293-296)
+    struct PJ { double mass; double pos[3]; double rs; };
+    std::vector<PJ> pj;
+    pj.reserve((size_t)n_ptcl);
+    for (int i = 0; i < n_ptcl; i++) {
+        const char* p = (const char*)ptcl + (size_t)i * stride;
+        const double m = ld(p, off_mass);
+        if (m > 0.0) pj.push_back({m, {ld(p, off_pos, 0), ld(p, off_pos, 1), ld(p, off_pos, 2)}, 0.0});
+    }
+    const pb_layout_epj lj = {sizeof(PJ), offsetof(PJ, pos), offsetof(PJ, mass), offsetof(PJ, rs)};
+    if ((rc = pb_upload_j(pj.data(), (int)pj.size(), &lj, nullptr, 0, nullptr)) != PB_OK) return rc;
+
+    struct PI { double pos[3]; double rs; };
+    std::vector<PI> pi((size_t)n_points);
+    for (int i = 0; i < n_points; i++) pi[i] = {{x[i], y[i], z[i]}, 0.0};
+    const pb_layout_epi li = {sizeof(PI), offsetof(PI, pos), offsetof(PI, rs)};
+    const int chunk = 512;
+    const int n_walk = (n_points + chunk - 1) / chunk;
+    std::vector<WalkIn> win(n_walk);
+    std::vector<int> ni(n_walk);
+    std::vector<ForceOut> out((size_t)n_points);
+    std::vector<void*> fptr(n_walk);
+    for (int w = 0; w < n_walk; w++) {
+        ni[w] = std::min(chunk, n_points - w * chunk);
+        win[w] = {&pi[(size_t)w * chunk], ni[w], nullptr, (int)pj.size(), nullptr, 0, nullptr, nullptr};   // dense EP list
+        fptr[w] = &out[(size_t)w * chunk];
+    }
+    // eps = 0, no cutoff: CalcForcePP semantics (src/soft_force.hpp:209-211, 311-312)
+    const double eps2 = E.eps2, rcut2 = E.rcut2, G0 = E.G;
+    E.eps2 = 0.0; E.rcut2 = 0.0; E.G = G;
+    const pb_layout_force lf = {sizeof(ForceOut), 0, 24, 32};
+    const int batch = 32;                                     // 16k points per dispatch bounds the partial-sum buffer
+    for (int w0 = 0; w0 < n_walk && rc == PB_OK; w0 += batch) {
+        const int nw = std::min(batch, n_walk - w0);
+        rc = dispatch_common(nw, win.data() + w0, false, li, nullptr, nullptr);
+        if (rc == PB_OK) rc = pb_retrieve(nw, ni.data() + w0, fptr.data() + w0, &lf);
+    }
+    E.eps2 = eps2; E.rcut2 = rcut2; E.G = G0;
+    if (rc != PB_OK) return rc;
+    for (int i = 0; i < n_points; i++) {
+        if (ax) ax[i] = out[i].ax;
+        if (ay) ay[i] = out[i].ay;
+        if (az) az[i] = out[i].az;
+        if (pot) pot[i] = out[i].pot;
+    }
     return PB_OK;
 }
 

@@ -96,8 +96,11 @@ constexpr float kPadPos = 1.0e10f;    // padded j: far away, zero mass, never a 
 // ------------------------------------------------------------------------------------------
 struct EpRegs { float4 a, b; };       // one gathered j: {xh,yh,zh,m}, {xl,yl,zl,rs}
 
-__device__ __forceinline__ int ep_load_id(const int* __restrict__ ids, int j, int j_count) {
-    return (j < j_count) ? __ldg(ids + j) : -1;
+// index of list element j of the chunk; ids == nullptr marks a DENSE list (all of the j store in
+// order: the direct-sum field query), where element j is simply store slot dense_base + j
+__device__ __forceinline__ int ep_load_id(const int* __restrict__ ids, int j, int j_count, int dense_base = 0) {
+    if (j >= j_count) return -1;
+    return ids ? __ldg(ids + j) : dense_base + j;
 }
 __device__ __forceinline__ EpRegs ep_load_j(const float4* __restrict__ epj, int id) {
     EpRegs r;
@@ -336,11 +339,12 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
     const int n_tiles = (task.j_count + kTileJ - 1) / kTileJ;
 
     if (task.kind == 0) {
-        const int* ids = id_epj + w.ej_off + task.j_begin;
+        const int* ids = (w.ej_off >= 0) ? id_epj + w.ej_off + task.j_begin : nullptr;   // ej_off < 0: dense list
+        const int dbase = task.j_begin;
         // software pipeline: ids run two tiles ahead, gathered j one tile ahead
-        int id_cur = ep_load_id(ids, tid, task.j_count);
+        int id_cur = ep_load_id(ids, tid, task.j_count, dbase);
         EpRegs jr  = ep_load_j(epj, id_cur);
-        int id_nxt = ep_load_id(ids, kTileJ + tid, task.j_count);
+        int id_nxt = ep_load_id(ids, kTileJ + tid, task.j_count, dbase);
         {
             const bool nr_ = ep_store(sm.ep[0], tid, id_cur, jr, w, prm.abs_mode);
             const unsigned bal = __ballot_sync(0xffffffffu, nr_);
@@ -350,7 +354,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
         for (int k = 0; k < n_tiles; ++k) {
             const bool more = (k + 1 < n_tiles);
             if (more) jr = ep_load_j(epj, id_nxt);
-            const int id_nn = ep_load_id(ids, (k + 2) * kTileJ + tid, task.j_count);
+            const int id_nn = ep_load_id(ids, (k + 2) * kTileJ + tid, task.j_count, dbase);
             if (busy) {
                 const int nv  = min(kTileJ, task.j_count - k * kTileJ);
                 const int npu = (((nv + 1) >> 1) + kPairUnroll - 1) & ~(kPairUnroll - 1);

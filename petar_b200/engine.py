@@ -75,6 +75,7 @@ ABI_SYMBOLS = [
     "pb_upload_j", "pb_dispatch_index", "pb_dispatch_direct", "pb_retrieve", "pb_get_profile",
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
+    "pb_field_at_points",
 ]
 
 _lib = None
@@ -113,6 +114,7 @@ def load():
     L.pb_pack_epj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_epj_host_indexed.argtypes = [_vp, _vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_spj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutSpj), _vp]
+    L.pb_field_at_points.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]
     _lib = L
     return L
 
@@ -197,6 +199,20 @@ class CalcForceWithLinearCutoffCUDA:
 def RetrieveForceCUDA(tag, n_walk, ni, force, direct=False):
     """Retrieve functor (src/force_gpu_cuda.hpp:165-168): ASSIGNS force[iw][i].{acc,pot,n_ngb}."""
     return load_shim(direct).pb_shim_retrieve(int(tag), int(n_walk), _ptr(ni), _ptr(force))
+
+
+def get_gravity_and_potential_at_point(x, y, z, particles, G=1.0):
+    """AMUSE's ``get_gravity_at_point`` + ``get_potential_at_point`` (reference
+    amuse-interface/interface.cc:966-1030) in one call: direct sum over ``particles`` (any structured
+    array with ``pos`` (3 x f8) and ``mass`` (f8) fields), eps = 0, no cutoff.  Returns (ax, ay, az, phi)."""
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+    n = len(x)
+    out = [np.zeros(n) for _ in range(4)]
+    dt = particles.dtype
+    check(load().pb_field_at_points(x.ctypes.data, y.ctypes.data, z.ctypes.data, n, particles.ctypes.data, len(particles),
+                                    dt.itemsize, dt.fields["pos"][1], dt.fields["mass"][1], float(G),
+                                    *(o.ctypes.data for o in out)), "pb_field_at_points")
+    return tuple(out)
 
 
 # ---------------------------------------------------------------------------------------------
