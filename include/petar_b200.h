@@ -140,6 +140,15 @@ int  pb_dispatch_direct(int n_walk,
                         const void* const* epj, const int* n_epj, const pb_layout_epj* lepj,
                         const void* const* spj, const int* n_spj, const pb_layout_spj* lspj);
 
+/* Neighbour search only: for PeTar's second tree, tree_nb, whose functor
+ * SearchNeighborEpEpSimd runs on the CPU every step even in GPU builds (reference
+ * src/petar.hpp:767-788, src/soft_force.hpp:11-34, 239-283).  Counts j with
+ * r^2 < max(rs_i, rs_j)^2 (no eps, as SearchNeighborEpEpNoSimd) over each walk's EP list.
+ * Retrieve with pb_retrieve: only n_ngb is assigned, acc / pot are left untouched. */
+int  pb_dispatch_count_index(int n_walk,
+                             const void* const* epi, const int* n_epi, const pb_layout_epi* lepi,
+                             const int* const* id_epj, const int* n_epj);
+
 /* Wait for the outstanding dispatch and ASSIGN force[iw][i].{acc,pot,n_ngb}, i < ni[iw].
  * n_walk / ni must equal those of the dispatch being retrieved. */
 int  pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_force* lforce);

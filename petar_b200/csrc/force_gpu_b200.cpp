@@ -146,6 +146,32 @@ PS::S32 CalcForceWithLinearCutoffCUDA::operator()(const PS::S32 tag,
 
 #endif
 
+#ifdef PARTICLE_SIMULATOR_GPU_MULIT_WALK_INDEX
+// EXTENSION (not declared by PeTar's force_gpu_cuda.hpp): a multiwalk dispatch
+// functor for the neighbour-search tree.  PeTar would use it by replacing, in treeNeighborSearch
+// (reference src/petar.hpp:774-778),
+//     tree_nb.calcForceAllAndWriteBack(SearchNeighborEpEpSimd(), system_soft, dinfo);
+// with
+//     tree_nb.calcForceAllAndWriteBackMultiWalkIndex(SearchNeighborCUDAMultiWalk(my_rank),
+//                                                    RetrieveForceCUDA, 1, system_soft, dinfo, 200);
+// Same argument list as the force functor; superparticle arguments are ignored.
+struct SearchNeighborCUDAMultiWalk {
+    PS::S32 my_rank;
+    explicit SearchNeighborCUDAMultiWalk(PS::S32 r = 0) : my_rank(r) {}
+    PS::S32 operator()(const PS::S32 tag, const PS::S32 n_walk, const EPISoft** epi, const PS::S32* n_epi,
+                       const PS::S32** id_epj, const PS::S32* n_epj, const PS::S32** id_spj, const PS::S32* n_spj,
+                       const EPJSoft* epj, const PS::S32 n_epj_tot, const SPJSoft* spj, const PS::S32 n_spj_tot,
+                       const bool send_flag) {
+        (void)tag; (void)id_spj; (void)n_spj; (void)spj; (void)n_spj_tot;
+        first_call(my_rank);
+        if (send_flag) check(pb_upload_j(epj, n_epj_tot, &kLayoutEpj, nullptr, 0, nullptr), "pb_upload_j");
+        else check(pb_dispatch_count_index(n_walk, (const void* const*)epi, n_epi, &kLayoutEpi, (const int* const*)id_epj, n_epj),
+                   "pb_dispatch_count_index");
+        return 0;
+    }
+};
+#endif
+
 // replaces reference src/force_gpu_cuda.cu:831-880
 PS::S32 RetrieveForceCUDA(const PS::S32 tag, const PS::S32 n_walk, const PS::S32* ni, ForceSoft** force) {
     (void)tag;
@@ -175,6 +201,15 @@ int pb_shim_dispatch_direct(int my_rank, double eps2, double rcut2, double G, in
                             const void** spj, const int* n_spj) {
     CalcForceWithLinearCutoffCUDA f(my_rank, eps2, rcut2, G);
     return f(tag, n_walk, (const EPISoft**)epi, n_epi, (const EPJSoft**)epj, n_epj, (const SPJSoft**)spj, n_spj);
+}
+#endif
+
+#ifdef PARTICLE_SIMULATOR_GPU_MULIT_WALK_INDEX
+int pb_shim_dispatch_count(int my_rank, int tag, int n_walk, const void** epi, const int* n_epi,
+                           const int** id_epj, const int* n_epj, const void* epj, int n_epj_tot, int send_flag) {
+    SearchNeighborCUDAMultiWalk f(my_rank);
+    return f(tag, n_walk, (const EPISoft**)epi, n_epi, id_epj, n_epj, nullptr, nullptr,
+             (const EPJSoft*)epj, n_epj_tot, nullptr, 0, send_flag != 0);
 }
 #endif
 

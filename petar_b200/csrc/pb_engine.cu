@@ -68,6 +68,7 @@ struct Plan {                // layout of one sub-batch inside an arena
     size_t n_lepj = 0, n_lspj = 0;            // direct mode: dispatch-local j store entries
     size_t off_walks = 0, off_tasks = 0, off_iblocks = 0, off_epi = 0, off_ide = 0, off_ids = 0;
     size_t off_lepj = 0, off_lspj = 0, bytes = 0;
+    int    count_only = 0;                    // neighbour search only: EP lists as kind-2 tasks, no SP, eps2 = 0
 };
 
 struct Slot {
@@ -104,6 +105,7 @@ struct Engine {
 
     Slot slots[kMaxStreams];
     bool outstanding = false;
+    bool count_only = false, out_count_only = false;   // transient: set by pb_dispatch_count_index
     int  out_n_walk = 0, out_n_slots = 0;
     std::vector<int> out_ni;
 
@@ -320,7 +322,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
         const Walk& W = hp.walks[g.walk];
         const int stride = g.nib * 32;
         const int nce = W.nej > 0 ? (int)((W.nej + (size_t)U * g.jsplit - 1) / ((size_t)U * g.jsplit)) : 0;
-        const int ncs = W.nsj > 0 ? (int)((W.nsj + (size_t)Us * g.jsplit - 1) / ((size_t)Us * g.jsplit)) : 0;
+        const int ncs = (W.nsj > 0 && !E.count_only) ? (int)((W.nsj + (size_t)Us * g.jsplit - 1) / ((size_t)Us * g.jsplit)) : 0;
         const int part_base = (int)part;
         int chunk = 0;
         for (int kind = 0; kind < 2; kind++) {
@@ -334,7 +336,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
                 if (jb >= nj) break;
                 Task t;
                 t.walk = g.walk; t.i_first = g.i_first; t.nib = g.nib; t.jsplit = g.jsplit;
-                t.kind = kind; t.j_begin = jb; t.j_count = std::min(len, nj - jb);
+                t.kind = (kind == 0 && E.count_only) ? 2 : kind; t.j_begin = jb; t.j_count = std::min(len, nj - jb);
                 t.part_base = part_base + chunk * stride;
                 hp.tasks.push_back(t);
                 chunk++;
@@ -360,6 +362,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     });
 
     Plan& p = hp.p;
+    p.count_only = E.count_only ? 1 : 0;
     p.n_walk = n_walk; p.n_tasks = (int)hp.tasks.size(); p.n_iblocks = (int)hp.iblocks.size();
     p.n_i = i_off; p.n_ide = ide; p.n_ids = ids; p.n_part = part; p.n_lepj = lepj; p.n_lspj = lspj;
     size_t o = 0;
@@ -456,7 +459,7 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
 cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, bool direct,
                         double4* part4, int* partn, ForceOut* out, bool force_only = false) {
     Params prm;
-    prm.eps2 = (float)E.eps2;
+    prm.eps2 = p.count_only ? 0.f : (float)E.eps2;        // SearchNeighborEpEpNoSimd tests r2 without eps
     prm.rcut2 = (float)E.rcut2;
     prm.abs_mode = E.opt_coords == 1 ? 1 : 0;
     const float4* epj = direct ? (const float4*)(d_arena + p.off_lepj) : E.d_epj;
@@ -555,6 +558,7 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
     for (int s = n_slots; s < kMaxStreams; s++) E.slots[s].active = false;
 
     E.outstanding = true;
+    E.out_count_only = E.count_only;
     E.out_n_walk = n_walk; E.out_n_slots = n_slots;
     E.out_ni.resize(n_walk);
     for (int w = 0; w < n_walk; w++) E.out_ni[w] = win[w].ni;
@@ -761,6 +765,24 @@ int pb_dispatch_index(int n_walk,
     return dispatch_common(n_walk, win.data(), false, *lepi, nullptr, nullptr);
 }
 
+int pb_dispatch_count_index(int n_walk,
+                            const void* const* epi, const int* n_epi, const pb_layout_epi* lepi,
+                            const int* const* id_epj, const int* n_epj) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    if (n_walk < 0) return fail(PB_ERR_ARG, "pb_dispatch_count_index: n_walk < 0");
+    if (n_walk && (!epi || !n_epi || !lepi || !id_epj || !n_epj)) return fail(PB_ERR_ARG, "pb_dispatch_count_index: null argument");
+    std::vector<WalkIn> win(n_walk);
+    for (int w = 0; w < n_walk; w++) {
+        if (n_epi[w] < 0 || n_epj[w] < 0) return fail(PB_ERR_ARG, "pb_dispatch_count_index: negative count in walk %d", w);
+        win[w] = {epi[w], n_epi[w], id_epj[w], n_epj[w], nullptr, 0, nullptr, nullptr};
+    }
+    E.count_only = true;
+    rc = dispatch_common(n_walk, win.data(), false, *lepi, nullptr, nullptr);
+    E.count_only = false;
+    return rc;
+}
+
 int pb_dispatch_direct(int n_walk,
                        const void* const* epi, const int* n_epi, const pb_layout_epi* lepi,
                        const void* const* epj, const int* n_epj, const pb_layout_epj* lepj,
@@ -784,7 +806,7 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
     if (n_walk && (!ni || !force || !L)) return fail(PB_ERR_ARG, "pb_retrieve: null argument");
     for (int w = 0; w < n_walk; w++)
         if (ni[w] != E.out_ni[w]) return fail(PB_ERR_ARG, "pb_retrieve: ni[%d]=%d != dispatched %d", w, ni[w], E.out_ni[w]);
-    const bool plain = L && L->stride == sizeof(ForceOut) && L->off_acc == 0 && L->off_pot == 24 && L->off_nngb == 32;
+    const bool plain = !E.out_count_only && L && L->stride == sizeof(ForceOut) && L->off_acc == 0 && L->off_pot == 24 && L->off_nngb == 32;
     for (int s = 0; s < E.out_n_slots; s++) {
         Slot& S = E.slots[s];
         if (!S.active) continue;
@@ -807,8 +829,10 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
             } else {
                 for (int i = 0; i < ni[w]; i++) {
                     char* q = dst + (size_t)i * L->stride;
-                    memcpy(q + L->off_acc, &src[i].ax, 24);
-                    memcpy(q + L->off_pot, &src[i].pot, 8);
+                    if (!E.out_count_only) {              // the neighbour-search functor assigns n_ngb only
+                        memcpy(q + L->off_acc, &src[i].ax, 24);
+                        memcpy(q + L->off_pot, &src[i].pot, 8);
+                    }
                     memcpy(q + L->off_nngb, &src[i].n_ngb, 8);
                 }
             }

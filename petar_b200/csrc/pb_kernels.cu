@@ -196,6 +196,31 @@ __device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
     }
 }
 
+// Neighbour search only (the kernel behind PeTar's second tree, tree_nb —
+// SearchNeighborEpEpNoSimd, reference src/soft_force.hpp:11-34): n += (r2 < max(rs_i, rs_j)^2),
+// exact two-float dx.  Only called for near segments; far segments cannot hold a neighbour.
+__device__ __forceinline__ void ep_count_pairs(const EpTile& t, int p0, int p1,
+                                               float xi, float yi, float zi, float xil, float yil, float zil, float rsi2,
+                                               float eps2, float2& cf) {
+    const float2 nxi = bc(-xi), nyi = bc(-yi), nzi = bc(-zi), e2 = bc(eps2);
+    const float2 nxil = bc(-xil), nyil = bc(-yil), nzil = bc(-zil);
+#pragma unroll kPairUnroll
+    for (int p = p0; p < p1; ++p) {
+        const float4 A = t.a[p], AL = t.al[p];
+        const float4 B = t.b[p];
+        const float2 BL = t.bl[p], C = t.c[p];
+        const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.y), nxi), __fadd2_rn(make_float2(AL.x, AL.y), nxil));
+        const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.z, A.w), nyi), __fadd2_rn(make_float2(AL.z, AL.w), nyil));
+        const float2 dz = __fadd2_rn(__fadd2_rn(make_float2(B.x, B.y), nzi), __fadd2_rn(BL, nzil));
+        float2 r2 = __ffma2_rn(dx, dx, e2);
+        r2 = __ffma2_rn(dy, dy, r2);
+        r2 = __ffma2_rn(dz, dz, r2);
+        const float2 f = make_float2((r2.x < fmaxf(C.x, rsi2)) ? 1.f : 0.f,
+                                     (r2.y < fmaxf(C.y, rsi2)) ? 1.f : 0.f);
+        cf = __fadd2_rn(cf, f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // EP-SP: monopole + quadrupole of a superparticle.
 // The reference evaluates, with Q the RAW second-moment tensor and tr its trace
@@ -338,7 +363,8 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
 
     const int n_tiles = (task.j_count + kTileJ - 1) / kTileJ;
 
-    if (task.kind == 0) {
+    if (task.kind == 0 || task.kind == 2) {
+        const bool count_only = (task.kind == 2);     // neighbour search only (tree_nb): no force math
         const int* ids = (w.ej_off >= 0) ? id_epj + w.ej_off + task.j_begin : nullptr;   // ej_off < 0: dense list
         const int dbase = task.j_begin;
         // software pipeline: ids run two tiles ahead, gathered j one tile ahead
@@ -363,7 +389,10 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 // 16-pair segments = the 32 j one staging warp wrote; count only where flagged
                 for (int seg = p0; seg < p1; seg += 16) {
                     const int e = min(seg + 16, p1);
-                    if (near_flag[k & 1][seg >> 4])
+                    if (count_only) {
+                        if (near_flag[k & 1][seg >> 4])
+                            ep_count_pairs(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, cf);
+                    } else if (near_flag[k & 1][seg >> 4])
                         ep_pairs<NR, true>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
                     else
                         ep_pairs<NR, false>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);

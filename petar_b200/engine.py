@@ -75,7 +75,7 @@ ABI_SYMBOLS = [
     "pb_upload_j", "pb_dispatch_index", "pb_dispatch_direct", "pb_retrieve", "pb_get_profile",
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
-    "pb_field_at_points",
+    "pb_field_at_points", "pb_dispatch_count_index",
 ]
 
 _lib = None
@@ -105,6 +105,7 @@ def load():
     L.pb_upload_j.argtypes = [_vp, C.c_int, C.POINTER(LayoutEpj), _vp, C.c_int, C.POINTER(LayoutSpj)]
     L.pb_dispatch_index.argtypes = [C.c_int, _vp, _vp, C.POINTER(LayoutEpi), _vp, _vp, _vp, _vp]
     L.pb_dispatch_direct.argtypes = [C.c_int, _vp, _vp, C.POINTER(LayoutEpi), _vp, _vp, C.POINTER(LayoutEpj), _vp, _vp, C.POINTER(LayoutSpj)]
+    L.pb_dispatch_count_index.argtypes = [C.c_int, _vp, _vp, C.POINTER(LayoutEpi), _vp, _vp]
     L.pb_retrieve.argtypes = [C.c_int, _vp, _vp, C.POINTER(LayoutForce)]
     L.pb_get_profile.argtypes = [C.POINTER(Profile), C.c_int]
     L.pb_replay.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -199,6 +200,40 @@ class CalcForceWithLinearCutoffCUDA:
 def RetrieveForceCUDA(tag, n_walk, ni, force, direct=False):
     """Retrieve functor (src/force_gpu_cuda.hpp:165-168): ASSIGNS force[iw][i].{acc,pot,n_ngb}."""
     return load_shim(direct).pb_shim_retrieve(int(tag), int(n_walk), _ptr(ni), _ptr(force))
+
+
+class SearchNeighborCUDAMultiWalk:
+    """EXTENSION: multiwalk dispatch functor for PeTar's neighbour-search tree
+    (tree_nb), the GPU form of SearchNeighborEpEpSimd (reference src/soft_force.hpp:239-283): same call
+    signature as the force functor minus the superparticle arguments."""
+
+    def __init__(self, my_rank=0):
+        self.my_rank = int(my_rank)
+
+    def __call__(self, tag, n_walk, epi, n_epi, id_epj, n_epj, epj, n_epj_tot, send_flag):
+        S = load_shim()
+        S.pb_shim_dispatch_count.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]
+        return S.pb_shim_dispatch_count(self.my_rank, int(tag), int(n_walk), _ptr(epi), _ptr(n_epi), _ptr(id_epj), _ptr(n_epj),
+                                        _ptr(epj), int(n_epj_tot), int(bool(send_flag)))
+
+
+def tree_neighbor_search(batch, n_walk_limit=200, force=None):
+    """What ``PeTar::treeNeighborSearch`` (reference src/petar.hpp:767-788) would do with the extension
+    functor: count neighbours over every walk's EP list; only ``n_ngb`` of ``force`` is assigned."""
+    f = np.zeros(batch.n_epi_total, dtype=ForceSoft) if force is None else force
+    none_u64, none_i32 = np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.int32)
+    disp = SearchNeighborCUDAMultiWalk(0)
+    assert disp(0, 0, none_u64, none_i32, none_u64, none_i32, batch.epj, len(batch.epj), True) == 0
+    prev = None
+    for w0 in range(0, batch.n_walk, n_walk_limit):
+        t = batch.pointer_tables(f, slice(w0, min(w0 + n_walk_limit, batch.n_walk)))
+        if prev is not None:
+            RetrieveForceCUDA(0, prev.n_walk, prev.n_epi, prev.force_ptrs)
+        assert disp(0, t.n_walk, t.epi_ptrs, t.n_epi, t.id_epj_ptrs, t.n_epj, batch.epj, len(batch.epj), False) == 0
+        prev = t
+    if prev is not None:
+        RetrieveForceCUDA(0, prev.n_walk, prev.n_epi, prev.force_ptrs)
+    return f
 
 
 def get_gravity_and_potential_at_point(x, y, z, particles, G=1.0):
