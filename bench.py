@@ -192,7 +192,7 @@ def run_reference(args, rank, world):
 def workload_config(args, wl, world):
     prm = wl["prm"]
     return {"workload": wl["name"], "n_particles": args.n, "n_tree_particles": wl["n_tree"], "theta": 0.3, "n_leaf_limit": 20,
-            "n_group_limit": 512, "n_walk_limit": 200, "r_out": prm["r_out"], "dt_soft": prm["dt_soft"], "eps": prm["eps"],
+            "n_group_limit": 512, "n_walk_limit": args.n_walk_limit, "r_out": prm["r_out"], "dt_soft": prm["dt_soft"], "eps": prm["eps"],
             "multipole": "quadrupole", "parallelism": f"domain_decomposition_x{world}",
             "l2_policy": "inputs larger than L2: every step re-reads all dispatches' index lists, i-particles and the j store"}
 
@@ -242,6 +242,7 @@ def main():
     ap.add_argument("--workload", default="kroupa_binaries", choices=["kroupa_binaries", "plummer"],
                     help="kroupa_binaries = BASELINE.json configs[2] stand-in (default); plummer = equal-mass Plummer (configs[1] shape)")
     ap.add_argument("--f-bin", type=float, default=0.1, help="fraction of stars in binaries (kroupa_binaries)")
+    ap.add_argument("--n-walk-limit", type=int, default=200, help="walks per dispatch; PeTar fixes 200 (src/petar.hpp:888)")
     ap.add_argument("--opt", action="append", default=[], help="extra library option key=value (pb_set_option), repeatable")
     args = ap.parse_args()
 
@@ -291,7 +292,7 @@ def main():
         torch.cuda.synchronize()
 
     # FDPS holds the per-group pointer tables ready when it calls dispatch; build them once
-    tables = engine.make_dispatch_tables(batch, force)
+    tables = engine.make_dispatch_tables(batch, force, args.n_walk_limit)
 
     def e2e_step():
         if stepper is None:

@@ -137,6 +137,7 @@ def load_shim(direct=False):
         S.pb_shim_dispatch.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int]
         S.pb_shim_retrieve.argtypes = [C.c_int, C.c_int, _vp, _vp]
+        S.pb_shim_dispatch_count.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]
         S.pb_shim_profile.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
         S.pb_shim_profile.restype = None
         _shim = S
@@ -212,7 +213,6 @@ class SearchNeighborCUDAMultiWalk:
 
     def __call__(self, tag, n_walk, epi, n_epi, id_epj, n_epj, epj, n_epj_tot, send_flag):
         S = load_shim()
-        S.pb_shim_dispatch_count.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]
         return S.pb_shim_dispatch_count(self.my_rank, int(tag), int(n_walk), _ptr(epi), _ptr(n_epi), _ptr(id_epj), _ptr(n_epj),
                                         _ptr(epj), int(n_epj_tot), int(bool(send_flag)))
 
