@@ -165,6 +165,40 @@ int  pb_field_at_points(const double* x, const double* y, const double* z, int n
                         const void* ptcl, int n_ptcl, size_t stride, size_t off_pos, size_t off_mass,
                         double G, double* ax, double* ay, double* az, double* pot);
 
+/* ---- device-side interaction lists (beyond the drop-in: needs the tree) ------
+ * Instead of receiving per-walk index lists from the host (0.7 GB per tree step at N = 1e6), the
+ * library is given the TREE once per step and builds id_epj / id_spj for every i-group on the GPU
+ * with the same opening rule FDPS's QuadrupoleWithSymmetrySearch walk applies,
+ *     open(cell) <=> dist^2(group particle box, cell c.m.) <= (cell length / theta)^2
+ *                    or group search box touches cell particle box, or vice versa,
+ * evaluated in fp64 without FMA contraction (decisions identical to the host walk), then runs the
+ * same force kernels on the lists without them ever crossing PCIe.
+ * Requirements: pb_upload_j published the j of this step with EP store order == the tree's sorted
+ * particle order and SP store slot c == multipole of cell c (single domain; LET superparticles
+ * inside leaves are not supported yet). */
+typedef struct pb_tree_cell {          /* 176 B */
+    double cm[3];                      /* centre of mass = expansion centre of the cell's superparticle */
+    double len;                        /* geometric cell length */
+    double in_lo[3], in_hi[3];         /* box of the particles inside */
+    double out_lo[3], out_hi[3];       /* box of their search spheres (pos +- 0.99 r_search) */
+    int    child[8];                   /* cell ids, -1 = none */
+    int    first, n;                   /* particle range in the sorted j array */
+    int    leaf, pad;
+} pb_tree_cell;
+
+typedef struct pb_tree_group {         /* 104 B: one i-group ("walk") */
+    int    first, n;                   /* its particles: sorted positions [first, first + n) */
+    double in_lo[3], in_hi[3], out_lo[3], out_hi[3];
+} pb_tree_group;
+
+int  pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta);
+/* Forces on all i-particles, given in group order (group 0's particles first, ...); ASSIGNS
+ * force[k].{acc,pot,n_ngb}.  Synchronous.  Both arrays are contiguous with the given layouts. */
+int  pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const pb_layout_force* lforce);
+/* Test hook: the lists the last pb_tree_force built.  n_ep/n_sp: per group counts (n_groups each);
+ * id_ep/id_sp: concatenated lists in group order, at most cap_* entries are written. */
+int  pb_tree_lists(int* n_ep, int* n_sp, int* id_ep, long long cap_ep, int* id_sp, long long cap_sp);
+
 /* ---- profiling ---------------------------------------------------------------------------- */
 int  pb_get_profile(pb_profile* out, int reset);
 

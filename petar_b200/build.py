@@ -50,10 +50,20 @@ def build_engine(force=False, verbose=False):
     """libpetar_b200.so: CUDA kernels + C ABI."""
     os.makedirs(LIB, exist_ok=True)
     target = os.path.join(LIB, "libpetar_b200.so")
-    srcs = [os.path.join(CSRC, f) for f in ("pb_kernels.cu", "pb_engine.cu")]
+    # pb_walk.cu (tree walk, fp64 geometry) is compiled without FMA contraction so that its opening
+    # decisions are bit-identical to a host walk; the force kernels keep the default
+    units = (("pb_kernels.cu", []), ("pb_engine.cu", []), ("pb_walk.cu", ["-fmad=false"]))
+    srcs = [os.path.join(CSRC, f) for f, _ in units]
     deps = srcs + [os.path.join(CSRC, "pb_device.h"), os.path.join(INC, "petar_b200.h")]
     if force or _newer(target, deps):
-        log = _run([_nvcc(), *NVCC_FLAGS, "-shared", "-I", INC, "-I", CSRC, "-o", target, *srcs, "-lgomp"], verbose)
+        objdir = os.path.join(HERE, "_build")
+        os.makedirs(objdir, exist_ok=True)
+        log, objs = "", []
+        for f, extra in units:
+            obj = os.path.join(objdir, f.replace(".cu", ".o"))
+            log += _run([_nvcc(), *NVCC_FLAGS, *extra, "-I", INC, "-I", CSRC, "-c", "-o", obj, os.path.join(CSRC, f)], verbose)
+            objs.append(obj)
+        log += _run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target, *objs, "-lgomp"], verbose)
         with open(os.path.join(LIB, "ptxas_engine.log"), "w") as f:
             f.write(log)
     return target

@@ -87,4 +87,10 @@ cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_bloc
 cudaError_t launch_reduce(cudaStream_t s, int n_iblocks, const IBlock* iblocks,
                           const double4* part4, const int* partn, ForceOut* out, double G);
 
+// device-side list building (pb_walk.cu); cells / groups are pb_tree_cell / pb_tree_group arrays
+cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
+                              int2* counts, int* scratch, int cap, int n_ctas, int* overflow);
+cudaError_t launch_walk_fill(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
+                             const Walk* walks, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow);
+
 } // namespace pb

@@ -112,6 +112,14 @@ struct Engine {
     bool recording = false;
     std::vector<Recorded> recs;
 
+    // device-side list building (pb_tree_*)
+    void* d_cells = nullptr; void* d_groups = nullptr; size_t cap_cells = 0, cap_groups = 0;
+    int n_cells = 0, n_groups = 0; double theta = 0.3;
+    std::vector<int> grp_n;                       // particles per group
+    int2* d_counts = nullptr; size_t cap_counts = 0; std::vector<int2> h_counts;
+    int* d_walk_scratch[kMaxStreams] = {nullptr}; int* d_overflow = nullptr;
+    int opt_tree_batch = 1024; int tree_last_batches = 0;
+
     pb_profile prof;
 };
 
@@ -257,6 +265,9 @@ struct WalkIn {              // per-walk host inputs (either mode)
     const int* ids; int nsj;
     const void* epj; const void* spj;   // direct mode
 };
+// ide / ids pointing here: the index lists are built on the device straight into the arena
+// (pb_tree_force); the host reserves the space and copies nothing
+const int g_devlist_marker = 0;
 
 struct Group { int walk, i_first, nib, jsplit; };
 
@@ -436,8 +447,8 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
         const float rnear = std::max(rsmax, rprec);
         W.rsi2max = rnear * rnear;
         if (!direct) {
-            if (W.nej && W.ej_off >= 0) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
-            if (W.nsj) memcpy(ids + W.sj_off, win[w].ids, sizeof(int) * (size_t)W.nsj);
+            if (W.nej && W.ej_off >= 0 && win[w].ide != &g_devlist_marker) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
+            if (W.nsj && win[w].ids != &g_devlist_marker) memcpy(ids + W.sj_off, win[w].ids, sizeof(int) * (size_t)W.nsj);
         } else {
             const size_t e0 = hp.lepj_off[w], s0 = hp.lspj_off[w];
             for (int j = 0; j < W.nej; j++) ide[W.ej_off + j] = (int)(e0 + j);
@@ -624,6 +635,8 @@ void pb_finalize(void) {
         S = Slot();
     }
     cudaFree(E.d_epj); cudaFree(E.d_spj); cudaFreeHost(E.h_jstage);
+    cudaFree(E.d_cells); cudaFree(E.d_groups); cudaFree(E.d_counts); cudaFree(E.d_overflow);
+    for (int s = 0; s < kMaxStreams; s++) cudaFree(E.d_walk_scratch[s]);
     cudaEventDestroy(E.ev_j_ready); cudaEventDestroy(E.ev_send0); cudaEventDestroy(E.ev_send1);
     cudaStreamDestroy(E.s_upload);
     const int coords = E.opt_coords, streams = E.opt_streams, jchunk = E.opt_jchunk, nr = E.opt_nr, cull = E.opt_cull, occ = E.opt_occ, lead = E.opt_lead;
@@ -645,6 +658,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "streams must be 1..%d", kMaxStreams); E.opt_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "jchunk"))  { if (v < 0 || v > (1 << 20)) return fail(PB_ERR_ARG, "jchunk out of range"); E.opt_jchunk = (int)v; return PB_OK; }
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
+    if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
     if (!strcmp(key, "lead"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "lead must be 0 or 1"); E.opt_lead = (int)v; return PB_OK; }
     if (!strcmp(key, "occupancy")) { if (v < 2 || v > 3) return fail(PB_ERR_ARG, "occupancy must be 2 or 3"); E.opt_occ = (int)v; return PB_OK; }
     if (!strcmp(key, "nr"))      { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nr must be 0 or 1"); E.opt_nr = (int)v; return PB_OK; }
@@ -903,6 +917,186 @@ int pb_field_at_points(const double* x, const double* y, const double* z, int n_
         if (ay) ay[i] = out[i].ay;
         if (az) az[i] = out[i].az;
         if (pot) pot[i] = out[i].pot;
+    }
+    return PB_OK;
+}
+
+// ---- device-side interaction lists --------------------------------------------
+namespace {
+constexpr int kWalkCap  = 65536;       // frontier capacity per warp (cells of one tree level an i-group touches)
+constexpr int kWalkCtas = 148;         // one CTA of 4 warps per SM; warps stride over the groups
+
+int ensure_walk_scratch(int slot) {
+    if (!E.d_walk_scratch[slot])
+        CU(cudaMalloc(&E.d_walk_scratch[slot], sizeof(int) * (size_t)kWalkCtas * 4 * 2 * kWalkCap));
+    if (!E.d_overflow) { CU(cudaMalloc(&E.d_overflow, sizeof(int))); CU(cudaMemset(E.d_overflow, 0, sizeof(int))); }
+    return PB_OK;
+}
+
+// wait for a slot's batch and scatter its results (contiguous, group order)
+int tree_finish_slot(Slot& S, char* force, const pb_layout_force& L, size_t i_first) {
+    CU(cudaEventSynchronize(S.ev[3]));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, S.ev[0], S.ev[1])); E.prof.t_send += 1e-3 * ms;
+    CU(cudaEventElapsedTime(&ms, S.ev[1], S.ev[2])); E.prof.t_calc += 1e-3 * ms;
+    CU(cudaEventElapsedTime(&ms, S.ev[2], S.ev[3])); E.prof.t_recv += 1e-3 * ms;
+    const double t0 = now_s();
+    const bool plain = L.stride == sizeof(ForceOut) && L.off_acc == 0 && L.off_pot == 24 && L.off_nngb == 32;
+    const size_t n = S.plan.n_i;
+    if (plain) {
+        memcpy(force + i_first * sizeof(ForceOut), S.h_out, sizeof(ForceOut) * n);
+    } else {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)n; i++) {
+            char* q = force + (i_first + (size_t)i) * L.stride;
+            memcpy(q + L.off_acc, &S.h_out[i].ax, 24);
+            memcpy(q + L.off_pot, &S.h_out[i].pot, 8);
+            memcpy(q + L.off_nngb, &S.h_out[i].n_ngb, 8);
+        }
+    }
+    E.prof.t_copy += now_s() - t0;
+    E.prof.t_unpack += now_s() - t0;
+    S.active = false;
+    return PB_OK;
+}
+} // namespace
+
+int pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    if (n_cells < 0 || n_groups < 0 || (n_cells && !cells) || (n_groups && !groups) || !(theta >= 0.0))
+        return fail(PB_ERR_ARG, "pb_tree_upload: bad argument");
+    if (E.outstanding) return fail(PB_ERR_PROTOCOL, "pb_tree_upload while a dispatch is outstanding");
+    CU(cudaDeviceSynchronize());
+    if ((size_t)n_cells > E.cap_cells) {
+        if (E.d_cells) CU(cudaFree(E.d_cells));
+        E.cap_cells = (size_t)n_cells + n_cells / 4 + 1024;
+        CU(cudaMalloc(&E.d_cells, E.cap_cells * sizeof(pb_tree_cell)));
+    }
+    if ((size_t)n_groups > E.cap_groups) {
+        if (E.d_groups) CU(cudaFree(E.d_groups));
+        E.cap_groups = (size_t)n_groups + n_groups / 4 + 1024;
+        CU(cudaMalloc(&E.d_groups, E.cap_groups * sizeof(pb_tree_group)));
+    }
+    if ((size_t)n_groups > E.cap_counts) {
+        if (E.d_counts) CU(cudaFree(E.d_counts));
+        E.cap_counts = (size_t)n_groups + n_groups / 4 + 1024;
+        CU(cudaMalloc(&E.d_counts, E.cap_counts * sizeof(int2)));
+    }
+    CU(cudaMemcpy(E.d_cells, cells, sizeof(pb_tree_cell) * (size_t)n_cells, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(E.d_groups, groups, sizeof(pb_tree_group) * (size_t)n_groups, cudaMemcpyHostToDevice));
+    E.prof.h2d_bytes += (long long)(sizeof(pb_tree_cell) * (size_t)n_cells + sizeof(pb_tree_group) * (size_t)n_groups);
+    E.n_cells = n_cells; E.n_groups = n_groups; E.theta = theta;
+    E.grp_n.resize(n_groups);
+    for (int g = 0; g < n_groups; g++) E.grp_n[g] = groups[g].n;
+    return PB_OK;
+}
+
+int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const pb_layout_force* lforce) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    if (E.outstanding) return fail(PB_ERR_PROTOCOL, "pb_tree_force while a dispatch is outstanding");
+    if (!E.j_published) return fail(PB_ERR_PROTOCOL, "pb_tree_force before pb_upload_j");
+    if (E.n_groups == 0) return PB_OK;
+    if (!E.d_cells) return fail(PB_ERR_PROTOCOL, "pb_tree_force before pb_tree_upload");
+    if (!epi || !lepi || !force || !lforce) return fail(PB_ERR_ARG, "pb_tree_force: null argument");
+    if (E.n_cells > E.n_spj) return fail(PB_ERR_PROTOCOL, "pb_tree_force: the SP store (%d) must hold one superparticle per cell (%d)", E.n_spj, E.n_cells);
+    const double theta_inv2 = E.theta > 0.0 ? 1.0 / (E.theta * E.theta) : 1e300;
+    const int n_slots = std::max(1, std::min(E.opt_streams, kMaxStreams));
+    for (int s = 0; s < n_slots; s++) if ((rc = ensure_walk_scratch(s)) != PB_OK) return rc;
+
+    // pass 1: list lengths of every group (the tree walk itself, on the device)
+    cudaStream_t s0 = E.slots[0].stream;
+    CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));
+    CU(launch_walk_count(s0, E.d_cells, E.d_groups, 0, E.n_groups, theta_inv2, E.d_counts, E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow));
+    E.h_counts.resize(E.n_groups);
+    CU(cudaMemcpyAsync(E.h_counts.data(), E.d_counts, sizeof(int2) * (size_t)E.n_groups, cudaMemcpyDeviceToHost, s0));
+    int h_over = 0;
+    CU(cudaMemcpyAsync(&h_over, E.d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s0));
+    CU(cudaStreamSynchronize(s0));
+    if (h_over) return fail(PB_ERR_ARG, "pb_tree_force: tree-walk frontier exceeded %d cells per level", kWalkCap);
+    E.prof.n_kernel_launch += 1;
+    E.prof.d2h_bytes += (long long)(sizeof(int2) * (size_t)E.n_groups);
+
+    // pass 2: per batch of groups — plan tasks from the counts, fill the lists on the device, force, reduce
+    const char* ebase = (const char*)epi;
+    std::vector<WalkIn> win;
+    static HostPlan hp[kMaxStreams];
+    size_t slot_i_first[kMaxStreams] = {0};
+    size_t i_first = 0;
+    int n_batches = 0;
+    long long n_i = 0, n_ej = 0, n_sj = 0, i_ep = 0, i_sp = 0;
+    for (int g0 = 0; g0 < E.n_groups; g0 += E.opt_tree_batch, n_batches++) {
+        const int nb = std::min(E.opt_tree_batch, E.n_groups - g0);
+        const int s = n_batches % n_slots;
+        Slot& S = E.slots[s];
+        if (S.active && (rc = tree_finish_slot(S, (char*)force, *lforce, slot_i_first[s])) != PB_OK) return rc;
+        const double t0 = now_s();
+        win.resize(nb);
+        size_t ni_batch = 0;
+        for (int w = 0; w < nb; w++) {
+            const int g = g0 + w;
+            win[w] = {ebase + (i_first + ni_batch) * lepi->stride, E.grp_n[g], &g_devlist_marker, E.h_counts[g].x,
+                      &g_devlist_marker, E.h_counts[g].y, nullptr, nullptr};
+            ni_batch += (size_t)E.grp_n[g];
+            n_i += E.grp_n[g]; n_ej += E.h_counts[g].x; n_sj += E.h_counts[g].y;
+            i_ep += (long long)E.grp_n[g] * E.h_counts[g].x; i_sp += (long long)E.grp_n[g] * E.h_counts[g].y;
+        }
+        plan_batch(win.data(), nb, false, n_slots, hp[s]);
+        if ((rc = grow_arena(S, hp[s].p.bytes)) != PB_OK) return rc;
+        if ((rc = grow_out(S, hp[s].p.n_i)) != PB_OK) return rc;
+        if ((rc = grow_part(S, hp[s].p.n_part)) != PB_OK) return rc;
+        pack_batch(win.data(), false, *lepi, nullptr, nullptr, hp[s], S.h_arena);
+        S.plan = hp[s].p;
+        E.prof.t_copy += now_s() - t0;
+        // only tables + i-particles cross PCIe; the index sections of the arena are filled in place
+        const size_t h2d = S.plan.off_ide;
+        CU(cudaStreamWaitEvent(S.stream, E.ev_j_ready, 0));
+        CU(cudaEventRecord(S.ev[0], S.stream));
+        CU(cudaMemcpyAsync(S.d_arena, S.h_arena, h2d, cudaMemcpyHostToDevice, S.stream));
+        CU(cudaEventRecord(S.ev[1], S.stream));
+        CU(launch_walk_fill(S.stream, E.d_cells, E.d_groups, g0, nb, theta_inv2, (const Walk*)(S.d_arena + S.plan.off_walks),
+                            (int*)(S.d_arena + S.plan.off_ide), (int*)(S.d_arena + S.plan.off_ids),
+                            E.d_walk_scratch[s], kWalkCap, kWalkCtas, E.d_overflow));
+        CU(launch_plan(S.stream, S.plan, S.d_arena, false, S.d_part4, S.d_partn, S.d_out));
+        CU(cudaEventRecord(S.ev[2], S.stream));
+        CU(cudaMemcpyAsync(S.h_out, S.d_out, sizeof(ForceOut) * S.plan.n_i, cudaMemcpyDeviceToHost, S.stream));
+        CU(cudaEventRecord(S.ev[3], S.stream));
+        E.prof.h2d_bytes += (long long)h2d;
+        E.prof.d2h_bytes += (long long)(sizeof(ForceOut) * S.plan.n_i);
+        E.prof.n_kernel_launch += 1 + (S.plan.n_tasks > 0) + (S.plan.n_iblocks > 0);
+        S.active = true;
+        slot_i_first[s] = i_first;
+        i_first += ni_batch;
+    }
+    for (int s = 0; s < n_slots; s++)
+        if (E.slots[s].active && (rc = tree_finish_slot(E.slots[s], (char*)force, *lforce, slot_i_first[s])) != PB_OK) return rc;
+    E.tree_last_batches = n_batches;
+    E.prof.n_walk += E.n_groups; E.prof.n_epi += n_i; E.prof.n_epj += n_ej; E.prof.n_spj += n_sj;
+    E.prof.n_call += n_batches; E.prof.n_interaction_ep += i_ep; E.prof.n_interaction_sp += i_sp;
+    return PB_OK;
+}
+
+int pb_tree_lists(int* n_ep, int* n_sp, int* id_ep, long long cap_ep, int* id_sp, long long cap_sp) {
+    if (!E.inited || E.h_counts.empty()) return fail(PB_ERR_PROTOCOL, "pb_tree_lists before pb_tree_force");
+    for (int g = 0; g < E.n_groups; g++) {
+        if (n_ep) n_ep[g] = E.h_counts[g].x;
+        if (n_sp) n_sp[g] = E.h_counts[g].y;
+    }
+    if (!id_ep && !id_sp) return PB_OK;
+    if (E.tree_last_batches != 1)
+        return fail(PB_ERR_PROTOCOL, "pb_tree_lists: lists are only kept when the last pb_tree_force ran as one batch (option tree_batch)");
+    // the single batch lives in slot 0's arena; lists are padded to 4 entries per group there
+    const Slot& S = E.slots[0];
+    std::vector<Walk> walks(S.plan.n_walk);
+    CU(cudaMemcpy(walks.data(), S.d_arena + S.plan.off_walks, sizeof(Walk) * walks.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> he(S.plan.n_ide), hs(S.plan.n_ids);
+    if (!he.empty()) CU(cudaMemcpy(he.data(), S.d_arena + S.plan.off_ide, sizeof(int) * he.size(), cudaMemcpyDeviceToHost));
+    if (!hs.empty()) CU(cudaMemcpy(hs.data(), S.d_arena + S.plan.off_ids, sizeof(int) * hs.size(), cudaMemcpyDeviceToHost));
+    long long ke = 0, ks = 0;
+    for (int g = 0; g < S.plan.n_walk; g++) {
+        for (int j = 0; j < walks[g].nej; j++, ke++) if (id_ep && ke < cap_ep) id_ep[ke] = he[walks[g].ej_off + j];
+        for (int j = 0; j < walks[g].nsj; j++, ks++) if (id_sp && ks < cap_sp) id_sp[ks] = hs[walks[g].sj_off + j];
     }
     return PB_OK;
 }

@@ -75,7 +75,7 @@ ABI_SYMBOLS = [
     "pb_upload_j", "pb_dispatch_index", "pb_dispatch_direct", "pb_retrieve", "pb_get_profile",
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
-    "pb_field_at_points", "pb_dispatch_count_index",
+    "pb_field_at_points", "pb_dispatch_count_index", "pb_tree_upload", "pb_tree_force", "pb_tree_lists",
 ]
 
 _lib = None
@@ -115,6 +115,9 @@ def load():
     L.pb_pack_epj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_epj_host_indexed.argtypes = [_vp, _vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_spj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutSpj), _vp]
+    L.pb_tree_upload.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double]
+    L.pb_tree_force.argtypes = [_vp, C.POINTER(LayoutEpi), _vp, C.POINTER(LayoutForce)]
+    L.pb_tree_lists.argtypes = [_vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong]
     L.pb_field_at_points.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]
     _lib = L
     return L
@@ -234,6 +237,32 @@ def tree_neighbor_search(batch, n_walk_limit=200, force=None):
     if prev is not None:
         RetrieveForceCUDA(0, prev.n_walk, prev.n_epi, prev.force_ptrs)
     return f
+
+
+def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, upload=True):
+    """Device-side list building: publish j, upload the tree, let the GPU build every
+    group's id_epj / id_spj and run the force kernels on them.  `batch` only supplies epj / spj / epi
+    (its host index lists are NOT used).  Returns ForceSoft[n_epi_total] in group order."""
+    L = load()
+    f = np.zeros(batch.n_epi_total, dtype=ForceSoft) if force is None else force
+    check(L.pb_set_params(eps * eps, r_out * r_out, G), "pb_set_params")
+    if upload:
+        check(L.pb_upload_j(batch.epj.ctypes.data, len(batch.epj), C.byref(LAYOUT_EPJ),
+                            batch.spj.ctypes.data, len(batch.spj), C.byref(LAYOUT_SPJ)), "pb_upload_j")
+        check(L.pb_tree_upload(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta)), "pb_tree_upload")
+    check(L.pb_tree_force(batch.epi.ctypes.data, C.byref(LAYOUT_EPI), f.ctypes.data, C.byref(LAYOUT_FORCE)), "pb_tree_force")
+    return f
+
+
+def tree_lists(n_groups):
+    """Test hook: (n_ep[g], n_sp[g], id_ep concatenated, id_sp concatenated) of the last tree_force."""
+    L = load()
+    ne, ns = np.zeros(n_groups, dtype=np.int32), np.zeros(n_groups, dtype=np.int32)
+    check(L.pb_tree_lists(ne.ctypes.data, ns.ctypes.data, None, 0, None, 0), "pb_tree_lists")
+    ide, ids = np.zeros(int(ne.sum()), dtype=np.int32), np.zeros(int(ns.sum()), dtype=np.int32)
+    check(L.pb_tree_lists(ne.ctypes.data, ns.ctypes.data, ide.ctypes.data if len(ide) else None, len(ide),
+                          ids.ctypes.data if len(ids) else None, len(ids)), "pb_tree_lists")
+    return ne, ns, ide, ids
 
 
 def get_gravity_and_potential_at_point(x, y, z, particles, G=1.0):

@@ -33,6 +33,7 @@ def lib():
         L.hz_sizes.argtypes = [_vp, _vp]
         L.hz_export.argtypes = [_vp] * 9
         L.hz_export_let_sp_src.argtypes = [_vp, _vp]
+        L.hz_export_tree.argtypes = [_vp, _vp, _vp]
         L.hz_local_boxes.argtypes = [_vp, _vp]
         L.hz_make_let.argtypes = [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp]
         L.hz_free.argtypes = [_vp]
@@ -155,6 +156,16 @@ class TreeHandle:
         lib().hz_export(self.h, epj_src.ctypes.data, epi_src.ctypes.data, spj.ctypes.data, i_off.ctypes.data,
                         ej_off.ctypes.data, sj_off.ctypes.data, id_epj.ctypes.data, id_spj.ctypes.data)
         return epj_src, epi_src, spj, i_off, ej_off, sj_off, id_epj, id_spj
+
+    def export_tree(self):
+        """(cells, groups) in the layout of pb_tree_cell / pb_tree_group, for the device-side list
+        builder (single-domain builds only)."""
+        from .types import TreeCell, TreeGroup
+        assert self._let[1] is None or len(self._let[1]) == 0, "device walk: single-domain trees only"
+        cells = np.zeros(self.n_nodes, dtype=TreeCell)
+        groups = np.zeros(self.n_walk, dtype=TreeGroup)
+        lib().hz_export_tree(self.h, cells.ctypes.data, groups.ctypes.data)
+        return cells, groups
 
     def let_sp_src(self):
         """for spj[n_nodes + k]: index of that entry in the `let["spj"]` array given at build time"""

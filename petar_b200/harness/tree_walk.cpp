@@ -380,6 +380,38 @@ void hz_export_let_sp_src(void* h, int* out) {
         if (G.sp_index[i] >= 0) out[G.sp_index[i]] = ~G.el[i].src;
 }
 
+// The tree itself, in the layout of pb_tree_cell / pb_tree_group (include/petar_b200.h), for the
+// device-side list builder.  Only meaningful for a single-domain build (no LET elements): cell c's
+// superparticle is spj[c], element range [first, first+n) indexes epj_sorted.
+struct ExportCell  { double cm[3], len, in_lo[3], in_hi[3], out_lo[3], out_hi[3]; int child[8]; int first, n, leaf, pad; };
+struct ExportGroup { int first, n; double in_lo[3], in_hi[3], out_lo[3], out_hi[3]; };
+
+void hz_export_tree(void* h, void* cells_out, void* groups_out) {
+    Result* R = (Result*)h;
+    const Tree& G = R->gt();
+    ExportCell* c = (ExportCell*)cells_out;
+    for (size_t i = 0; i < G.nodes.size(); i++) {
+        const Node& nd = G.nodes[i];
+        for (int k = 0; k < 3; k++) {
+            c[i].cm[k] = nd.cm[k];
+            c[i].in_lo[k] = nd.inner.lo[k]; c[i].in_hi[k] = nd.inner.hi[k];
+            c[i].out_lo[k] = nd.outer.lo[k]; c[i].out_hi[k] = nd.outer.hi[k];
+        }
+        c[i].len = 2.0 * nd.half;
+        for (int k = 0; k < 8; k++) c[i].child[k] = nd.child[k];
+        c[i].first = nd.first; c[i].n = nd.n; c[i].leaf = nd.leaf ? 1 : 0; c[i].pad = 0;
+    }
+    ExportGroup* g = (ExportGroup*)groups_out;
+    for (size_t i = 0; i < R->groups.size(); i++) {
+        const Group& gr = R->groups[i];
+        g[i].first = gr.first; g[i].n = gr.n;
+        for (int k = 0; k < 3; k++) {
+            g[i].in_lo[k] = gr.inner.lo[k]; g[i].in_hi[k] = gr.inner.hi[k];
+            g[i].out_lo[k] = gr.outer.lo[k]; g[i].out_hi[k] = gr.outer.hi[k];
+        }
+    }
+}
+
 // Local boxes of this domain: out[0..5] = particle box lo/hi, out[6..11] = search box lo/hi
 void hz_local_boxes(void* h, double* out) {
     Result* R = (Result*)h;

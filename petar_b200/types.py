@@ -30,6 +30,18 @@ EPJSoft = np.dtype(
 SPJQuad = np.dtype([("mass", "<f8"), ("pos", "<f8", (3,)), ("quad", "<f8", (6,))], align=True)  # xx,yy,zz,xy,xz,yz
 ForceSoft = np.dtype([("acc", "<f8", (3,)), ("pot", "<f8"), ("n_ngb", "<i8")], align=True)
 
+# device-side list building (include/petar_b200.h: pb_tree_cell, pb_tree_group)
+TreeCell = np.dtype(
+    [("cm", "<f8", (3,)), ("len", "<f8"), ("in_lo", "<f8", (3,)), ("in_hi", "<f8", (3,)), ("out_lo", "<f8", (3,)), ("out_hi", "<f8", (3,)),
+     ("child", "<i4", (8,)), ("first", "<i4"), ("n", "<i4"), ("leaf", "<i4"), ("pad", "<i4")],
+    align=True,
+)
+TreeGroup = np.dtype(
+    [("first", "<i4"), ("n", "<i4"), ("in_lo", "<f8", (3,)), ("in_hi", "<f8", (3,)), ("out_lo", "<f8", (3,)), ("out_hi", "<f8", (3,))],
+    align=True,
+)
+assert TreeCell.itemsize == 176 and TreeGroup.itemsize == 104
+
 assert EPISoft.itemsize == 48
 assert EPJSoft.itemsize == 120
 assert SPJQuad.itemsize == 80
