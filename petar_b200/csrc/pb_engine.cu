@@ -923,8 +923,8 @@ int pb_field_at_points(const double* x, const double* y, const double* z, int n_
 
 // ---- device-side interaction lists --------------------------------------------
 namespace {
-constexpr int kWalkCap  = 65536;       // frontier capacity per warp (cells of one tree level an i-group touches)
-constexpr int kWalkCtas = 148;         // one CTA of 4 warps per SM; warps stride over the groups
+constexpr int kWalkCap  = 32768;       // frontier capacity per warp (cells of one tree level an i-group touches)
+constexpr int kWalkCtas = 148 * 4;     // 4 CTAs of 4 warps per SM (the walk is latency-bound); warps stride over the groups
 
 int ensure_walk_scratch(int slot) {
     if (!E.d_walk_scratch[slot])
@@ -1020,34 +1020,42 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
 
     // pass 2: per batch of groups — plan tasks from the counts, fill the lists on the device, force, reduce
     const char* ebase = (const char*)epi;
-    std::vector<WalkIn> win;
-    static HostPlan hp[kMaxStreams];
-    size_t slot_i_first[kMaxStreams] = {0};
-    size_t i_first = 0;
-    int n_batches = 0;
+    const double tp0 = now_s();
+    std::vector<WalkIn> win(E.n_groups);
+    std::vector<size_t> grp_i_first(E.n_groups + 1, 0);
     long long n_i = 0, n_ej = 0, n_sj = 0, i_ep = 0, i_sp = 0;
-    for (int g0 = 0; g0 < E.n_groups; g0 += E.opt_tree_batch, n_batches++) {
+    for (int g = 0; g < E.n_groups; g++) {
+        win[g] = {ebase + grp_i_first[g] * lepi->stride, E.grp_n[g], &g_devlist_marker, E.h_counts[g].x,
+                  &g_devlist_marker, E.h_counts[g].y, nullptr, nullptr};
+        grp_i_first[g + 1] = grp_i_first[g] + (size_t)E.grp_n[g];
+        n_i += E.grp_n[g]; n_ej += E.h_counts[g].x; n_sj += E.h_counts[g].y;
+        i_ep += (long long)E.grp_n[g] * E.h_counts[g].x; i_sp += (long long)E.grp_n[g] * E.h_counts[g].y;
+    }
+    const int n_batches = (E.n_groups + E.opt_tree_batch - 1) / E.opt_tree_batch;
+    static std::vector<HostPlan> plans;
+    if ((int)plans.size() < n_batches) plans.resize(n_batches);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < n_batches; b++) {                      // all batches planned at once, in parallel
+        const int g0 = b * E.opt_tree_batch;
+        plan_batch(win.data() + g0, std::min(E.opt_tree_batch, E.n_groups - g0), false, n_slots, plans[b]);
+    }
+    E.prof.t_plan += now_s() - tp0;
+    E.prof.t_copy += now_s() - tp0;
+    size_t slot_i_first[kMaxStreams] = {0};
+    for (int b = 0; b < n_batches; b++) {
+        const int g0 = b * E.opt_tree_batch;
         const int nb = std::min(E.opt_tree_batch, E.n_groups - g0);
-        const int s = n_batches % n_slots;
+        const int s = b % n_slots;
         Slot& S = E.slots[s];
         if (S.active && (rc = tree_finish_slot(S, (char*)force, *lforce, slot_i_first[s])) != PB_OK) return rc;
         const double t0 = now_s();
-        win.resize(nb);
-        size_t ni_batch = 0;
-        for (int w = 0; w < nb; w++) {
-            const int g = g0 + w;
-            win[w] = {ebase + (i_first + ni_batch) * lepi->stride, E.grp_n[g], &g_devlist_marker, E.h_counts[g].x,
-                      &g_devlist_marker, E.h_counts[g].y, nullptr, nullptr};
-            ni_batch += (size_t)E.grp_n[g];
-            n_i += E.grp_n[g]; n_ej += E.h_counts[g].x; n_sj += E.h_counts[g].y;
-            i_ep += (long long)E.grp_n[g] * E.h_counts[g].x; i_sp += (long long)E.grp_n[g] * E.h_counts[g].y;
-        }
-        plan_batch(win.data(), nb, false, n_slots, hp[s]);
-        if ((rc = grow_arena(S, hp[s].p.bytes)) != PB_OK) return rc;
-        if ((rc = grow_out(S, hp[s].p.n_i)) != PB_OK) return rc;
-        if ((rc = grow_part(S, hp[s].p.n_part)) != PB_OK) return rc;
-        pack_batch(win.data(), false, *lepi, nullptr, nullptr, hp[s], S.h_arena);
-        S.plan = hp[s].p;
+        HostPlan& hp = plans[b];
+        if ((rc = grow_arena(S, hp.p.bytes)) != PB_OK) return rc;
+        if ((rc = grow_out(S, hp.p.n_i)) != PB_OK) return rc;
+        if ((rc = grow_part(S, hp.p.n_part)) != PB_OK) return rc;
+        pack_batch(win.data() + g0, false, *lepi, nullptr, nullptr, hp, S.h_arena);
+        S.plan = hp.p;
+        E.prof.t_pack += now_s() - t0;
         E.prof.t_copy += now_s() - t0;
         // only tables + i-particles cross PCIe; the index sections of the arena are filled in place
         const size_t h2d = S.plan.off_ide;
@@ -1066,8 +1074,7 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
         E.prof.d2h_bytes += (long long)(sizeof(ForceOut) * S.plan.n_i);
         E.prof.n_kernel_launch += 1 + (S.plan.n_tasks > 0) + (S.plan.n_iblocks > 0);
         S.active = true;
-        slot_i_first[s] = i_first;
-        i_first += ni_batch;
+        slot_i_first[s] = grp_i_first[g0];
     }
     for (int s = 0; s < n_slots; s++)
         if (E.slots[s].active && (rc = tree_finish_slot(E.slots[s], (char*)force, *lforce, slot_i_first[s])) != PB_OK) return rc;
