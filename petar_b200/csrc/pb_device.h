@@ -91,6 +91,6 @@ cudaError_t launch_reduce(cudaStream_t s, int n_iblocks, const IBlock* iblocks,
 cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
                               int2* counts, int* scratch, int cap, int n_ctas, int* overflow);
 cudaError_t launch_walk_fill(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
-                             const Walk* walks, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow);
+                             const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow);
 
 } // namespace pb

@@ -69,6 +69,8 @@ struct Plan {                // layout of one sub-batch inside an arena
     size_t off_walks = 0, off_tasks = 0, off_iblocks = 0, off_epi = 0, off_ide = 0, off_ids = 0;
     size_t off_lepj = 0, off_lspj = 0, bytes = 0;
     int    count_only = 0;                    // neighbour search only: EP lists as kind-2 tasks, no SP, eps2 = 0
+    const int* ext_ide = nullptr;             // index lists living outside the arena (built on the device for the whole step)
+    const int* ext_ids = nullptr;
 };
 
 struct Slot {
@@ -115,9 +117,12 @@ struct Engine {
     // device-side list building (pb_tree_*)
     void* d_cells = nullptr; void* d_groups = nullptr; size_t cap_cells = 0, cap_groups = 0;
     int n_cells = 0, n_groups = 0; double theta = 0.3;
+    char* h_tstage = nullptr; size_t cap_tstage = 0;     // pinned staging of the tree
     std::vector<int> grp_n;                       // particles per group
     int2* d_counts = nullptr; size_t cap_counts = 0; std::vector<int2> h_counts;
     int* d_walk_scratch[kMaxStreams] = {nullptr}; int* d_overflow = nullptr;
+    int* d_tree_ide = nullptr; int* d_tree_ids = nullptr; size_t cap_tree_ide = 0, cap_tree_ids = 0;
+    int2* d_tree_off = nullptr; std::vector<int2> h_tree_off; cudaEvent_t ev_fill = nullptr;
     int opt_tree_batch = 1024; int tree_last_batches = 0;
 
     pb_profile prof;
@@ -292,7 +297,7 @@ struct HostPlan {
     std::vector<size_t> lepj_off, lspj_off;   // direct mode: first local j of each walk
 };
 
-void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active, HostPlan& hp) {
+void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active, HostPlan& hp, const int2* ext_off = nullptr) {
     hp.walks.resize(n_walk);
     hp.tasks.clear(); hp.iblocks.clear();
     hp.lepj_off.assign(n_walk, 0); hp.lspj_off.assign(n_walk, 0);
@@ -306,11 +311,12 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
         const bool dense = !direct && win[w].ide == nullptr && win[w].nej > 0;
         W.ej_off = dense ? -1 : (int)ide;  W.nej = win[w].nej;
         W.sj_off = (int)ids;  W.nsj = win[w].nsj;
+        if (ext_off) { W.ej_off = ext_off[w].x; W.sj_off = ext_off[w].y; }     // lists live in a step-wide device buffer
         W.ohx = W.ohy = W.ohz = W.olx = W.oly = W.olz = 0.f;
         W.hx = W.hy = W.hz = INFINITY; W.rsi2max = 0.f;
         i_off += (size_t)win[w].ni;
-        if (!dense) ide += align_up((size_t)win[w].nej, 4);
-        ids += align_up((size_t)win[w].nsj, 4);
+        if (!dense && !ext_off) ide += align_up((size_t)win[w].nej, 4);
+        if (!ext_off) ids += align_up((size_t)win[w].nsj, 4);
         if (direct) {
             hp.lepj_off[w] = lepj; hp.lspj_off[w] = lspj;
             lepj += (size_t)win[w].nej; lspj += (size_t)win[w].nsj;
@@ -478,7 +484,8 @@ cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, boo
     cudaError_t e = launch_force(st, p.n_tasks, E.opt_nr, E.opt_occ,
                                  (const Walk*)(d_arena + p.off_walks), (const Task*)(d_arena + p.off_tasks),
                                  (const float4*)(d_arena + p.off_epi),
-                                 (const int*)(d_arena + p.off_ide), (const int*)(d_arena + p.off_ids),
+                                 p.ext_ide ? p.ext_ide : (const int*)(d_arena + p.off_ide),
+                                 p.ext_ids ? p.ext_ids : (const int*)(d_arena + p.off_ids),
                                  epj, spj, part4, partn, prm);
     if (e != cudaSuccess || force_only) return e;
     return launch_reduce(st, p.n_iblocks, (const IBlock*)(d_arena + p.off_iblocks), part4, partn, out, E.G);
@@ -635,8 +642,10 @@ void pb_finalize(void) {
         S = Slot();
     }
     cudaFree(E.d_epj); cudaFree(E.d_spj); cudaFreeHost(E.h_jstage);
-    cudaFree(E.d_cells); cudaFree(E.d_groups); cudaFree(E.d_counts); cudaFree(E.d_overflow);
+    cudaFree(E.d_cells); cudaFree(E.d_groups); cudaFree(E.d_counts); cudaFree(E.d_overflow); cudaFreeHost(E.h_tstage);
     for (int s = 0; s < kMaxStreams; s++) cudaFree(E.d_walk_scratch[s]);
+    cudaFree(E.d_tree_ide); cudaFree(E.d_tree_ids); cudaFree(E.d_tree_off);
+    if (E.ev_fill) cudaEventDestroy(E.ev_fill);
     cudaEventDestroy(E.ev_j_ready); cudaEventDestroy(E.ev_send0); cudaEventDestroy(E.ev_send1);
     cudaStreamDestroy(E.s_upload);
     const int coords = E.opt_coords, streams = E.opt_streams, jchunk = E.opt_jchunk, nr = E.opt_nr, cull = E.opt_cull, occ = E.opt_occ, lead = E.opt_lead;
@@ -982,9 +991,27 @@ int pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* 
         if (E.d_counts) CU(cudaFree(E.d_counts));
         E.cap_counts = (size_t)n_groups + n_groups / 4 + 1024;
         CU(cudaMalloc(&E.d_counts, E.cap_counts * sizeof(int2)));
+        if (E.d_tree_off) { CU(cudaFree(E.d_tree_off)); E.d_tree_off = nullptr; }
     }
-    CU(cudaMemcpy(E.d_cells, cells, sizeof(pb_tree_cell) * (size_t)n_cells, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(E.d_groups, groups, sizeof(pb_tree_group) * (size_t)n_groups, cudaMemcpyHostToDevice));
+    // stage through pinned memory with all host threads, then one async DMA on the upload stream
+    // (a pageable cudaMemcpy of the ~50 MB tree would cost more than the walk itself)
+    const size_t bc = sizeof(pb_tree_cell) * (size_t)n_cells, bg = sizeof(pb_tree_group) * (size_t)n_groups;
+    if (bc + bg > E.cap_tstage) {
+        if (E.h_tstage) CU(cudaFreeHost(E.h_tstage));
+        E.cap_tstage = bc + bg + (bc + bg) / 4;
+        CU(cudaMallocHost(&E.h_tstage, E.cap_tstage));
+    }
+    {
+        const size_t chunk = 1 << 20;
+        const long long nchunk = (long long)((bc + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < nchunk; k++)
+            memcpy(E.h_tstage + (size_t)k * chunk, (const char*)cells + (size_t)k * chunk, std::min(chunk, bc - (size_t)k * chunk));
+        memcpy(E.h_tstage + bc, groups, bg);
+    }
+    CU(cudaMemcpyAsync(E.d_cells, E.h_tstage, bc, cudaMemcpyHostToDevice, E.s_upload));
+    CU(cudaMemcpyAsync(E.d_groups, E.h_tstage + bc, bg, cudaMemcpyHostToDevice, E.s_upload));
+    CU(cudaEventRecord(E.ev_j_ready, E.s_upload));        // dispatch streams wait for j AND tree
     E.prof.h2d_bytes += (long long)(sizeof(pb_tree_cell) * (size_t)n_cells + sizeof(pb_tree_group) * (size_t)n_groups);
     E.n_cells = n_cells; E.n_groups = n_groups; E.theta = theta;
     E.grp_n.resize(n_groups);
@@ -1003,7 +1030,8 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
     if (E.n_cells > E.n_spj) return fail(PB_ERR_PROTOCOL, "pb_tree_force: the SP store (%d) must hold one superparticle per cell (%d)", E.n_spj, E.n_cells);
     const double theta_inv2 = E.theta > 0.0 ? 1.0 / (E.theta * E.theta) : 1e300;
     const int n_slots = std::max(1, std::min(E.opt_streams, kMaxStreams));
-    for (int s = 0; s < n_slots; s++) if ((rc = ensure_walk_scratch(s)) != PB_OK) return rc;
+    if ((rc = ensure_walk_scratch(0)) != PB_OK) return rc;
+    if (!E.ev_fill) CU(cudaEventCreateWithFlags(&E.ev_fill, cudaEventDisableTiming));
 
     // pass 1: list lengths of every group (the tree walk itself, on the device)
     cudaStream_t s0 = E.slots[0].stream;
@@ -1018,7 +1046,24 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
     E.prof.n_kernel_launch += 1;
     E.prof.d2h_bytes += (long long)(sizeof(int2) * (size_t)E.n_groups);
 
-    // pass 2: per batch of groups — plan tasks from the counts, fill the lists on the device, force, reduce
+    // pass 2: one launch writes every group's lists into a step-wide device buffer
+    E.h_tree_off.resize(E.n_groups);
+    size_t tot_e = 0, tot_s = 0;
+    for (int g = 0; g < E.n_groups; g++) {
+        E.h_tree_off[g] = make_int2((int)tot_e, (int)tot_s);
+        tot_e += align_up((size_t)E.h_counts[g].x, 4);
+        tot_s += align_up((size_t)E.h_counts[g].y, 4);
+    }
+    if (tot_e >= (1ull << 31) || tot_s >= (1ull << 31)) return fail(PB_ERR_ARG, "pb_tree_force: more than 2^31 list entries in one step");
+    if (tot_e > E.cap_tree_ide) { if (E.d_tree_ide) CU(cudaFree(E.d_tree_ide)); E.cap_tree_ide = tot_e + tot_e / 8 + 4096; CU(cudaMalloc(&E.d_tree_ide, sizeof(int) * E.cap_tree_ide)); }
+    if (tot_s > E.cap_tree_ids) { if (E.d_tree_ids) CU(cudaFree(E.d_tree_ids)); E.cap_tree_ids = tot_s + tot_s / 8 + 4096; CU(cudaMalloc(&E.d_tree_ids, sizeof(int) * E.cap_tree_ids)); }
+    if (!E.d_tree_off) CU(cudaMalloc(&E.d_tree_off, sizeof(int2) * E.cap_counts));   // freed whenever d_counts is re-sized
+    CU(cudaMemcpyAsync(E.d_tree_off, E.h_tree_off.data(), sizeof(int2) * (size_t)E.n_groups, cudaMemcpyHostToDevice, s0));
+    CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, E.n_groups, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
+                        E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow));
+    CU(cudaEventRecord(E.ev_fill, s0));
+    E.prof.n_kernel_launch += 1;
+    // pass 3: per batch of groups — plan tasks from the counts, force, reduce
     const char* ebase = (const char*)epi;
     const double tp0 = now_s();
     std::vector<WalkIn> win(E.n_groups);
@@ -1037,7 +1082,8 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < n_batches; b++) {                      // all batches planned at once, in parallel
         const int g0 = b * E.opt_tree_batch;
-        plan_batch(win.data() + g0, std::min(E.opt_tree_batch, E.n_groups - g0), false, n_slots, plans[b]);
+        plan_batch(win.data() + g0, std::min(E.opt_tree_batch, E.n_groups - g0), false, n_slots, plans[b], E.h_tree_off.data() + g0);
+        plans[b].p.ext_ide = E.d_tree_ide; plans[b].p.ext_ids = E.d_tree_ids;
     }
     E.prof.t_plan += now_s() - tp0;
     E.prof.t_copy += now_s() - tp0;
@@ -1059,22 +1105,20 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
         E.prof.t_copy += now_s() - t0;
         // only tables + i-particles cross PCIe; the index sections of the arena are filled in place
         const size_t h2d = S.plan.off_ide;
-        CU(cudaStreamWaitEvent(S.stream, E.ev_j_ready, 0));
+        CU(cudaStreamWaitEvent(S.stream, E.ev_fill, 0));
         CU(cudaEventRecord(S.ev[0], S.stream));
         CU(cudaMemcpyAsync(S.d_arena, S.h_arena, h2d, cudaMemcpyHostToDevice, S.stream));
         CU(cudaEventRecord(S.ev[1], S.stream));
-        CU(launch_walk_fill(S.stream, E.d_cells, E.d_groups, g0, nb, theta_inv2, (const Walk*)(S.d_arena + S.plan.off_walks),
-                            (int*)(S.d_arena + S.plan.off_ide), (int*)(S.d_arena + S.plan.off_ids),
-                            E.d_walk_scratch[s], kWalkCap, kWalkCtas, E.d_overflow));
         CU(launch_plan(S.stream, S.plan, S.d_arena, false, S.d_part4, S.d_partn, S.d_out));
         CU(cudaEventRecord(S.ev[2], S.stream));
         CU(cudaMemcpyAsync(S.h_out, S.d_out, sizeof(ForceOut) * S.plan.n_i, cudaMemcpyDeviceToHost, S.stream));
         CU(cudaEventRecord(S.ev[3], S.stream));
         E.prof.h2d_bytes += (long long)h2d;
         E.prof.d2h_bytes += (long long)(sizeof(ForceOut) * S.plan.n_i);
-        E.prof.n_kernel_launch += 1 + (S.plan.n_tasks > 0) + (S.plan.n_iblocks > 0);
+        E.prof.n_kernel_launch += (S.plan.n_tasks > 0) + (S.plan.n_iblocks > 0);
         S.active = true;
         slot_i_first[s] = grp_i_first[g0];
+        (void)nb;
     }
     for (int s = 0; s < n_slots; s++)
         if (E.slots[s].active && (rc = tree_finish_slot(E.slots[s], (char*)force, *lforce, slot_i_first[s])) != PB_OK) return rc;
@@ -1091,19 +1135,14 @@ int pb_tree_lists(int* n_ep, int* n_sp, int* id_ep, long long cap_ep, int* id_sp
         if (n_sp) n_sp[g] = E.h_counts[g].y;
     }
     if (!id_ep && !id_sp) return PB_OK;
-    if (E.tree_last_batches != 1)
-        return fail(PB_ERR_PROTOCOL, "pb_tree_lists: lists are only kept when the last pb_tree_force ran as one batch (option tree_batch)");
-    // the single batch lives in slot 0's arena; lists are padded to 4 entries per group there
-    const Slot& S = E.slots[0];
-    std::vector<Walk> walks(S.plan.n_walk);
-    CU(cudaMemcpy(walks.data(), S.d_arena + S.plan.off_walks, sizeof(Walk) * walks.size(), cudaMemcpyDeviceToHost));
-    std::vector<int> he(S.plan.n_ide), hs(S.plan.n_ids);
-    if (!he.empty()) CU(cudaMemcpy(he.data(), S.d_arena + S.plan.off_ide, sizeof(int) * he.size(), cudaMemcpyDeviceToHost));
-    if (!hs.empty()) CU(cudaMemcpy(hs.data(), S.d_arena + S.plan.off_ids, sizeof(int) * hs.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> he(E.cap_tree_ide ? (size_t)E.h_tree_off.back().x + align_up((size_t)E.h_counts.back().x, 4) : 0);
+    std::vector<int> hs(E.cap_tree_ids ? (size_t)E.h_tree_off.back().y + align_up((size_t)E.h_counts.back().y, 4) : 0);
+    if (!he.empty()) CU(cudaMemcpy(he.data(), E.d_tree_ide, sizeof(int) * he.size(), cudaMemcpyDeviceToHost));
+    if (!hs.empty()) CU(cudaMemcpy(hs.data(), E.d_tree_ids, sizeof(int) * hs.size(), cudaMemcpyDeviceToHost));
     long long ke = 0, ks = 0;
-    for (int g = 0; g < S.plan.n_walk; g++) {
-        for (int j = 0; j < walks[g].nej; j++, ke++) if (id_ep && ke < cap_ep) id_ep[ke] = he[walks[g].ej_off + j];
-        for (int j = 0; j < walks[g].nsj; j++, ks++) if (id_sp && ks < cap_sp) id_sp[ks] = hs[walks[g].sj_off + j];
+    for (int g = 0; g < E.n_groups; g++) {
+        for (int j = 0; j < E.h_counts[g].x; j++, ke++) if (id_ep && ke < cap_ep) id_ep[ke] = he[(size_t)E.h_tree_off[g].x + j];
+        for (int j = 0; j < E.h_counts[g].y; j++, ks++) if (id_sp && ks < cap_sp) id_sp[ks] = hs[(size_t)E.h_tree_off[g].y + j];
     }
     return PB_OK;
 }

@@ -48,12 +48,12 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 
 } // namespace
 
-// FILL = false: counts[g] = {n_ep, n_sp}.  FILL = true: ids written at walks[g - g0].ej_off / .sj_off.
+// FILL = false: counts[g] = {n_ep, n_sp}.  FILL = true: ids written at id_e + offs[g].x / id_s + offs[g].y.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restrict__ groups,
             int g0, int n_groups, double theta_inv2,
-            int2* __restrict__ counts, const Walk* __restrict__ walks, int* __restrict__ id_e, int* __restrict__ id_s,
+            int2* __restrict__ counts, const int2* __restrict__ offs, int* __restrict__ id_e, int* __restrict__ id_s,
             int* __restrict__ scratch, int cap, int* __restrict__ overflow)
 {
     const int lane = threadIdx.x & 31;
@@ -69,7 +69,7 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
         __syncwarp();
         int ncur = 1, nep = 0, nsp = 0;
         int* oe = nullptr; int* os = nullptr;
-        if (FILL) { oe = id_e + walks[g].ej_off; os = id_s + walks[g].sj_off; }
+        if (FILL) { const int2 o = offs[g0 + g]; oe = id_e + o.x; os = id_s + o.y; }
         while (ncur > 0) {
             int nnext = 0;
             for (int base = 0; base < ncur; base += 32) {
@@ -137,10 +137,10 @@ cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* gro
 }
 
 cudaError_t launch_walk_fill(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
-                             const Walk* walks, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow) {
+                             const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow) {
     if (n_groups <= 0) return cudaSuccess;
     walk_kernel<true><<<n_ctas, 128, 0, s>>>((const pb_tree_cell*)cells, (const pb_tree_group*)groups, g0, n_groups, theta_inv2,
-                                             nullptr, walks, id_e, id_s, scratch, cap, overflow);
+                                             nullptr, offs, id_e, id_s, scratch, cap, overflow);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,7 @@ def lib():
         L.hz_export.argtypes = [_vp] * 9
         L.hz_export_let_sp_src.argtypes = [_vp, _vp]
         L.hz_export_tree.argtypes = [_vp, _vp, _vp]
+        L.hz_timing.argtypes = [_vp, _vp]
         L.hz_local_boxes.argtypes = [_vp, _vp]
         L.hz_make_let.argtypes = [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp]
         L.hz_free.argtypes = [_vp]
@@ -166,6 +167,12 @@ class TreeHandle:
         groups = np.zeros(self.n_walk, dtype=TreeGroup)
         lib().hz_export_tree(self.h, cells.ctypes.data, groups.ctypes.data)
         return cells, groups
+
+    def timing(self):
+        """(seconds building the tree, seconds walking it for all groups) on the host, OpenMP."""
+        out = np.zeros(2)
+        lib().hz_timing(self.h, out.ctypes.data)
+        return float(out[0]), float(out[1])
 
     def let_sp_src(self):
         """for spj[n_nodes + k]: index of that entry in the `let["spj"]` array given at build time"""

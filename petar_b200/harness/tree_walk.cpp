@@ -248,6 +248,7 @@ void walk(const Tree& t, int node, const Box& tin, const Box& tout, double theta
 struct Result {
     Tree local, global;
     bool has_let = false;
+    double t_tree = 0.0, t_walk = 0.0;          // wall-clock seconds of the tree build(s) and of all group walks
     std::vector<Group> groups;
     std::vector<long long> i_off, ej_off, sj_off;
     std::vector<int> id_epj, id_spj;
@@ -293,6 +294,7 @@ void* hz_build(int n_loc, const double* pos, const double* mass, const double* r
                double theta, int n_leaf_limit, int n_group_limit)
 {
     Result* R = new Result();
+    const double t_begin = omp_get_wtime();
     fill_elems(R->local.el, n_loc, pos, mass, rsearch, 0, 0, nullptr);
     double cen[3], half;
     bounding_cube(R->local.el, cen, half);
@@ -310,11 +312,14 @@ void* hz_build(int n_loc, const double* pos, const double* mass, const double* r
     const int ng = (int)R->groups.size();
     const double theta_inv2 = theta > 0.0 ? 1.0 / (theta * theta) : 1e300;
     std::vector<std::vector<int>> le(ng), ls(ng);
+    R->t_tree = omp_get_wtime() - t_begin;
+    const double t_w0 = omp_get_wtime();
 #pragma omp parallel for schedule(dynamic, 4)
     for (int g = 0; g < ng; g++) {
         le[g].reserve(4096); ls[g].reserve(2048);
         if (!G.nodes.empty()) walk(G, 0, R->groups[g].inner, R->groups[g].outer, theta_inv2, le[g], ls[g]);
     }
+    R->t_walk = omp_get_wtime() - t_w0;
     R->i_off.assign(ng + 1, 0); R->ej_off.assign(ng + 1, 0); R->sj_off.assign(ng + 1, 0);
     for (int g = 0; g < ng; g++) {
         R->i_off[g + 1] = R->i_off[g] + R->groups[g].n;
@@ -370,6 +375,9 @@ void hz_export(void* h, int* epj_src, int* epi_src, pb_SPJQuad* spj,
     if (!R->id_epj.empty()) memcpy(id_epj, R->id_epj.data(), sizeof(int) * R->id_epj.size());
     if (!R->id_spj.empty()) memcpy(id_spj, R->id_spj.data(), sizeof(int) * R->id_spj.size());
 }
+
+// out[0] = seconds spent building the tree(s), out[1] = seconds spent walking it for all groups (OpenMP)
+void hz_timing(void* h, double* out) { Result* R = (Result*)h; out[0] = R->t_tree; out[1] = R->t_walk; }
 
 // For the LET part of spj (entries n_nodes .. n_nodes+n_let_sp-1, Morton order): the index each
 // entry had in the caller's let_sp array.

@@ -78,7 +78,8 @@ def test_device_walk_fullsize_report():
     inter = sum(batch.interactions())
     print(f"[N=1e6 config 3 stand-in, {len(cells)} cells, {len(groups)} groups] device-walk step {dt_dev * 1e3:.1f} ms "
           f"({inter / dt_dev * 1e-9:.0f} Gint/s, H2D {prof['h2d_bytes'] / 1e6:.0f} MB) vs host-list step {dt_host * 1e3:.1f} ms "
-          f"({inter / dt_host * 1e-9:.0f} Gint/s, lists prebuilt); interactions/step {inter:.3e}")
+          f"({inter / dt_host * 1e-9:.0f} Gint/s, lists prebuilt; building them on the host took {batch.tree.timing()[1] * 1e3:.0f} ms "
+          f"with OpenMP on {__import__('os').cpu_count()} cores); interactions/step {inter:.3e}")
     assert np.array_equal(f["n_ngb"], force["n_ngb"])
     assert np.abs(f["acc"] - force["acc"]).max() <= 2e-6 * np.abs(force["acc"]).max()
     assert prof["n_interaction_ep"] == batch.interactions()[0] and prof["n_interaction_sp"] == batch.interactions()[1]
