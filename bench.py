@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per step of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-device-walk", action="store_true", help="skip the informational device-side list building leg")
     ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--nr", type=int, default=0)
     ap.add_argument("--cull", type=int, default=1)
@@ -331,6 +332,30 @@ def main():
     barrier()
     sec_e2e = (time.perf_counter() - t0) / args.steps
     prof = engine.get_profile()
+
+    # ---- informational: the same step with the interaction lists built on the GPU from the tree
+    # (not the drop-in path — FDPS would have to hand over its tree) ----
+    device_walk = None
+    if world == 1 and not args.no_device_walk:
+        try:
+            cells, groups = batch.tree.export_tree()
+            engine.tree_force(batch, cells, groups, eps, r_out, G, force=force)              # warm-up / allocations
+            engine.get_profile(reset=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                engine.tree_force(batch, cells, groups, eps, r_out, G, force=force)
+            barrier()
+            sec_dw = (time.perf_counter() - t0) / args.steps
+            pdw = engine.get_profile()
+            device_walk = {"ms_per_step": sec_dw * 1e3, "value": (I_ep + I_sp) / sec_dw * 1e-9, "unit": "Ginteractions/s",
+                           "h2d_bytes_per_step": pdw["h2d_bytes"] / args.steps, "d2h_bytes_per_step": pdw["d2h_bytes"] / args.steps,
+                           "n_cells": int(len(cells)), "n_groups": int(len(groups)),
+                           "host_walk_ms_for_context": batch.tree.timing()[1] * 1e3,
+                           "note": "j + tree uploaded from host buffers every step, lists built on the GPU (pb_tree_upload / pb_tree_force); "
+                                   "host_walk_ms = the harness's OpenMP walk that produced the lists the e2e leg is given for free"}
+        except Exception as ex:  # noqa: BLE001
+            device_walk = {"unavailable": repr(ex)}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- max over ranks, totals over ranks ----
@@ -379,6 +404,8 @@ def main():
                          "note": "bound is the non-tensor FP32/issue pipe, not HBM or tensor: ~300-500 flop per HBM byte"},
             "clocks": clocks,
         }
+        if device_walk is not None:
+            line["device_walk"] = device_walk
         if stepper is not None and stepper.n_steps:
             line["e2e"]["rank0_step_phases_ms"] = {k: v * 1e3 / stepper.n_steps for k, v in stepper.host_s.items()}
             line["e2e"]["omp_threads_per_rank"] = int(os.environ.get("OMP_NUM_THREADS", "0"))
