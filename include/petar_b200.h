@@ -191,6 +191,9 @@ typedef struct pb_tree_group {         /* 104 B: one i-group ("walk") */
     double in_lo[3], in_hi[3], out_lo[3], out_hi[3];
 } pb_tree_group;
 
+/* Per tree step: pb_tree_upload, pb_upload_j (either order), then pb_tree_force.  pb_tree_upload
+ * returns as soon as the copy and the walk's counting pass are queued, so calling it FIRST lets the
+ * GPU count list lengths while the host packs the j-particles. */
 int  pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta);
 /* Forces on all i-particles, given in group order (group 0's particles first, ...); ASSIGNS
  * force[k].{acc,pot,n_ngb}.  Synchronous.  Both arrays are contiguous with the given layouts. */

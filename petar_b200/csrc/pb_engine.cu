@@ -123,6 +123,8 @@ struct Engine {
     int* d_walk_scratch[kMaxStreams] = {nullptr}; int* d_overflow = nullptr;
     int* d_tree_ide = nullptr; int* d_tree_ids = nullptr; size_t cap_tree_ide = 0, cap_tree_ids = 0;
     int2* d_tree_off = nullptr; std::vector<int2> h_tree_off; cudaEvent_t ev_fill = nullptr;
+    int2* h_counts_p = nullptr; size_t cap_counts_p = 0; int* h_over_p = nullptr;   // pinned landing zone of the count pass
+    cudaEvent_t ev_count = nullptr; bool count_pending = false;
     int opt_tree_batch = 1024; int tree_last_batches = 0;
 
     pb_profile prof;
@@ -645,6 +647,8 @@ void pb_finalize(void) {
     cudaFree(E.d_cells); cudaFree(E.d_groups); cudaFree(E.d_counts); cudaFree(E.d_overflow); cudaFreeHost(E.h_tstage);
     for (int s = 0; s < kMaxStreams; s++) cudaFree(E.d_walk_scratch[s]);
     cudaFree(E.d_tree_ide); cudaFree(E.d_tree_ids); cudaFree(E.d_tree_off);
+    cudaFreeHost(E.h_counts_p); cudaFreeHost(E.h_over_p);
+    if (E.ev_count) cudaEventDestroy(E.ev_count);
     if (E.ev_fill) cudaEventDestroy(E.ev_fill);
     cudaEventDestroy(E.ev_j_ready); cudaEventDestroy(E.ev_send0); cudaEventDestroy(E.ev_send1);
     cudaStreamDestroy(E.s_upload);
@@ -1016,6 +1020,30 @@ int pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* 
     E.n_cells = n_cells; E.n_groups = n_groups; E.theta = theta;
     E.grp_n.resize(n_groups);
     for (int g = 0; g < n_groups; g++) E.grp_n[g] = groups[g].n;
+    // pass 1 of the device walk starts right away — it needs the tree only, so it runs while the
+    // host is still packing this step's j (pb_upload_j): list lengths of every group
+    E.count_pending = false;
+    if (n_groups > 0) {
+        int rc2;
+        if ((rc2 = ensure_walk_scratch(0)) != PB_OK) return rc2;
+        if (!E.ev_count) CU(cudaEventCreateWithFlags(&E.ev_count, cudaEventDisableTiming));
+        if ((size_t)n_groups > E.cap_counts_p) {
+            if (E.h_counts_p) CU(cudaFreeHost(E.h_counts_p));
+            E.cap_counts_p = E.cap_counts;
+            CU(cudaMallocHost(&E.h_counts_p, sizeof(int2) * E.cap_counts_p));
+        }
+        if (!E.h_over_p) CU(cudaMallocHost(&E.h_over_p, sizeof(int)));
+        const double theta_inv2 = theta > 0.0 ? 1.0 / (theta * theta) : 1e300;
+        cudaStream_t s0 = E.slots[0].stream;
+        CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));
+        CU(launch_walk_count(s0, E.d_cells, E.d_groups, 0, n_groups, theta_inv2, E.d_counts, E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow));
+        CU(cudaMemcpyAsync(E.h_counts_p, E.d_counts, sizeof(int2) * (size_t)n_groups, cudaMemcpyDeviceToHost, s0));
+        CU(cudaMemcpyAsync(E.h_over_p, E.d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s0));
+        CU(cudaEventRecord(E.ev_count, s0));
+        E.count_pending = true;
+        E.prof.n_kernel_launch += 1;
+        E.prof.d2h_bytes += (long long)(sizeof(int2) * (size_t)n_groups);
+    }
     return PB_OK;
 }
 
@@ -1033,18 +1061,16 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
     if ((rc = ensure_walk_scratch(0)) != PB_OK) return rc;
     if (!E.ev_fill) CU(cudaEventCreateWithFlags(&E.ev_fill, cudaEventDisableTiming));
 
-    // pass 1: list lengths of every group (the tree walk itself, on the device)
+    // pass 1 (list lengths) was launched by pb_tree_upload; collect it
     cudaStream_t s0 = E.slots[0].stream;
-    CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));
-    CU(launch_walk_count(s0, E.d_cells, E.d_groups, 0, E.n_groups, theta_inv2, E.d_counts, E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow));
-    E.h_counts.resize(E.n_groups);
-    CU(cudaMemcpyAsync(E.h_counts.data(), E.d_counts, sizeof(int2) * (size_t)E.n_groups, cudaMemcpyDeviceToHost, s0));
-    int h_over = 0;
-    CU(cudaMemcpyAsync(&h_over, E.d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s0));
-    CU(cudaStreamSynchronize(s0));
-    if (h_over) return fail(PB_ERR_ARG, "pb_tree_force: tree-walk frontier exceeded %d cells per level", kWalkCap);
-    E.prof.n_kernel_launch += 1;
-    E.prof.d2h_bytes += (long long)(sizeof(int2) * (size_t)E.n_groups);
+    if (E.count_pending) {
+        CU(cudaEventSynchronize(E.ev_count));
+        E.count_pending = false;
+        if (*E.h_over_p) return fail(PB_ERR_ARG, "pb_tree_force: tree-walk frontier exceeded %d cells per level", kWalkCap);
+        E.h_counts.assign(E.h_counts_p, E.h_counts_p + E.n_groups);
+    } else if ((int)E.h_counts.size() != E.n_groups) {
+        return fail(PB_ERR_PROTOCOL, "pb_tree_force: call pb_tree_upload for this step first");
+    }
 
     // pass 2: one launch writes every group's lists into a step-wide device buffer
     E.h_tree_off.resize(E.n_groups);

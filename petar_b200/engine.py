@@ -247,9 +247,11 @@ def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, uploa
     f = np.zeros(batch.n_epi_total, dtype=ForceSoft) if force is None else force
     check(L.pb_set_params(eps * eps, r_out * r_out, G), "pb_set_params")
     if upload:
+        # tree first: its upload also starts the walk's counting pass, which then runs on the GPU
+        # while the host packs the j-particles
+        check(L.pb_tree_upload(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta)), "pb_tree_upload")
         check(L.pb_upload_j(batch.epj.ctypes.data, len(batch.epj), C.byref(LAYOUT_EPJ),
                             batch.spj.ctypes.data, len(batch.spj), C.byref(LAYOUT_SPJ)), "pb_upload_j")
-        check(L.pb_tree_upload(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta)), "pb_tree_upload")
     check(L.pb_tree_force(batch.epi.ctypes.data, C.byref(LAYOUT_EPI), f.ctypes.data, C.byref(LAYOUT_FORCE)), "pb_tree_force")
     return f
 
