@@ -63,7 +63,8 @@ def build_engine(force=False, verbose=False):
             obj = os.path.join(objdir, f.replace(".cu", ".o"))
             log += _run([_nvcc(), *NVCC_FLAGS, *extra, "-I", INC, "-I", CSRC, "-c", "-o", obj, os.path.join(CSRC, f)], verbose)
             objs.append(obj)
-        log += _run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target, *objs, "-lgomp"], verbose)
+        log += _run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xlinker", "-soname=libpetar_b200.so",
+                     "-o", target, *objs, "-lgomp"], verbose)
         with open(os.path.join(LIB, "ptxas_engine.log"), "w") as f:
             f.write(log)
     return target

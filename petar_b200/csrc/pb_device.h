@@ -10,7 +10,14 @@ constexpr int kWarpsPerCta  = 8;                    // 256 threads
 constexpr int kThreads      = kWarpsPerCta * 32;
 constexpr int kTileJ        = kThreads;             // j staged per tile: one per thread
 constexpr int kTilePairs    = kTileJ / 2;           // the inner loops consume j in pairs (packed fp32x2)
-constexpr int kPairUnroll   = 4;                    // pairs per unrolled inner-loop step
+#ifndef PB_EP_UNROLL
+#define PB_EP_UNROLL 4
+#endif
+#ifndef PB_SP_UNROLL
+#define PB_SP_UNROLL 2
+#endif
+constexpr int kPairUnroll   = PB_EP_UNROLL;         // EP pairs per unrolled inner-loop step (tuning: tools/build_variants.py)
+constexpr int kSpUnroll     = PB_SP_UNROLL;         // SP pairs per unrolled inner-loop step
 
 // One walk (= FDPS i-group with its interaction lists) of a dispatch.  64 B.
 struct __align__(16) Walk {

@@ -283,7 +283,7 @@ __device__ __forceinline__ void sp_pairs(const SpTile& t, int p0, int p1,
                                          float xi, float yi, float zi, float eps2,
                                          float2& ax, float2& ay, float2& az, float2& pt) {
     const float2 vxi = bc(xi), vyi = bc(yi), vzi = bc(zi), e2 = bc(eps2);
-#pragma unroll 2
+#pragma unroll kSpUnroll
     for (int p = p0; p < p1; ++p) {
         const float4 Q0 = t.q0[p], Q1 = t.q1[p], Q2 = t.q2[p], Q3 = t.q3[p], Q4 = t.q4[p];
         const float2 mtr = t.q5[p];
@@ -421,7 +421,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             const int id_nn = ep_load_id(ids, (k + 2) * kTileJ + tid, task.j_count);
             if (busy) {
                 const int nv  = min(kTileJ, task.j_count - k * kTileJ);
-                const int npu = (((nv + 1) >> 1) + 1) & ~1;
+                const int npu = ((nv + 1) >> 1);          // pairs with at least one real j (padding pairs are inert anyway)
                 const int p0  = js * ppw, p1 = min(p0 + ppw, npu);
                 float2 ax = bc(0.f), ay = bc(0.f), az = bc(0.f), pt = bc(0.f);
                 sp_pairs<NR>(sm.sp[k & 1], p0, p1, pi.x, pi.y, pi.z, prm.eps2, ax, ay, az, pt);

@@ -96,7 +96,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    L = C.CDLL(_need(os.path.join(LIBDIR, "libpetar_b200.so")), mode=C.RTLD_GLOBAL)
+    # PETAR_B200_LIB: load another build of the same library (kernel tuning experiments, tools/)
+    L = C.CDLL(_need(os.environ.get("PETAR_B200_LIB") or os.path.join(LIBDIR, "libpetar_b200.so")), mode=C.RTLD_GLOBAL)
     L.pb_init.argtypes = [C.c_int, C.c_int]
     L.pb_finalize.restype = None
     L.pb_last_error.restype = C.c_char_p

@@ -1,0 +1,18 @@
+"""Small end-to-end invocations of every kernel path, for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from petar_b200 import engine, harness as hz
+from petar_b200.types import EPJSoft
+
+batch, _, prm, _ = hz.kroupa_binary_case(3000)
+f = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"], n_walk_limit=16)
+g = engine.tree_neighbor_search(batch, n_walk_limit=16)
+cells, groups = batch.tree.export_tree()
+h = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"])
+part = np.zeros(len(batch.epj), dtype=EPJSoft)
+part["pos"], part["mass"] = batch.epj["pos"], batch.epj["mass"]
+pts = np.random.default_rng(0).normal(size=(100, 3))
+ax, ay, az, phi = engine.get_gravity_and_potential_at_point(pts[:, 0], pts[:, 1], pts[:, 2], part)
+assert np.array_equal(f["n_ngb"], h["n_ngb"]) and np.isfinite(ax).all()
+print("sanitize_small ok", f["n_ngb"].sum(), g["n_ngb"].sum())
