@@ -33,7 +33,8 @@ import time
 # each rank its share of the host cores (must happen before any OpenMP runtime is loaded)
 _world = int(os.environ.get("WORLD_SIZE", "1"))
 if _world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _world))
+    _ref_arm = "reference" in sys.argv          # the reference arm runs on rank 0 alone: it gets every host core
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // (1 if _ref_arm else _world)))
 
 import numpy as np  # noqa: E402
 
