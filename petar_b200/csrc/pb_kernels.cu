@@ -96,12 +96,7 @@ constexpr float kPadPos = 1.0e10f;    // padded j: far away, zero mass, never a 
 // ------------------------------------------------------------------------------------------
 struct EpRegs { float4 a, b; };       // one gathered j: {xh,yh,zh,m}, {xl,yl,zl,rs}
 
-// index of list element j of the chunk; ids == nullptr marks a DENSE list (all of the j store in
-// order: the direct-sum field query), where element j is simply store slot dense_base + j
-__device__ __forceinline__ int ep_load_id(const int* __restrict__ ids, int j, int j_count, int dense_base = 0) {
-    if (j >= j_count) return -1;
-    return ids ? __ldg(ids + j) : dense_base + j;
-}
+// (list indices come through IdPipe below; id < 0 marks a padding slot past the end of a chunk)
 __device__ __forceinline__ EpRegs ep_load_j(const float4* __restrict__ epj, int id) {
     EpRegs r;
     if (id >= 0) {
@@ -323,6 +318,87 @@ __device__ __forceinline__ void sp_pairs(const SpTile& t, int p0, int p1,
 }
 
 // ------------------------------------------------------------------------------------------
+// Index tiles through TMA: a chunk's index list is contiguous and 16-byte aligned, so each 1 KB
+// tile of it is one `cp.async.bulk` (1-D TMA bulk copy, SASS UBLKCP) into a 3-deep shared-memory
+// ring, completion signalled on an mbarrier — issued by one thread three tiles ahead, no
+// registers held, no per-thread global loads.  (The j records themselves are an indexed gather
+// and stay 16-byte loads from L2.)  PB_TMA_IDS=0 builds the plain-load variant.
+// ------------------------------------------------------------------------------------------
+#ifndef PB_TMA_IDS
+#define PB_TMA_IDS 1
+#endif
+
+constexpr int kIdRing = 3;      // ring slots
+constexpr int kIdDirect = 2;    // tiles 0,1 of a chunk are read directly
+
+struct IdRing {
+    alignas(16) int buf[kIdRing][kTileJ];
+    alignas(8) unsigned long long bar[kIdRing];
+};
+
+struct IdPipe {
+    const int* ids;      // nullptr: dense list (element j is store slot dbase + j)
+    int j_count, n_tiles, dbase;
+    IdRing* ring;
+
+    // ring entry r holds tile r + kIdDirect (the first kIdDirect tiles are plain loads: nothing to wait for
+    // in the prologue, and the barrier that publishes the mbarrier init is the one the loop needs anyway)
+    __device__ __forceinline__ void issue(int r) const {               // one thread
+        const int tile = r + kIdDirect;
+        const unsigned bytes = (unsigned)(((min(kTileJ, j_count - tile * kTileJ) + 3) & ~3) * 4);
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&ring->bar[r % kIdRing]);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring->buf[r % kIdRing][0]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(ids + (size_t)tile * kTileJ), "r"(bytes), "r"(bar) : "memory");
+    }
+    // call by all threads; a __syncthreads() must separate it from the first get(tile >= kIdDirect)
+    __device__ __forceinline__ void init(const int* ids_, int j_count_, int n_tiles_, int dbase_, IdRing* ring_, int tid) {
+        ids = ids_; j_count = j_count_; n_tiles = n_tiles_; dbase = dbase_; ring = ring_;
+#if PB_TMA_IDS
+        if (ids && tid == 0) {
+            for (int b = 0; b < kIdRing; ++b) {
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&ring->bar[b]);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(1) : "memory");
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int r = 0; r < min(kIdRing, n_tiles - kIdDirect); ++r) issue(r);
+        }
+#endif
+    }
+    // id of list element tile*kTileJ + tid, or -1 past the end of the chunk
+    __device__ __forceinline__ int get(int tile, int tid) const {
+        const int j = tile * kTileJ + tid;
+        if (tile >= n_tiles) return -1;
+        if (!ids) return j < j_count ? dbase + j : -1;
+#if PB_TMA_IDS
+        if (tile < kIdDirect) return j < j_count ? __ldg(ids + j) : -1;
+        const int r = tile - kIdDirect;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&ring->bar[r % kIdRing]);
+        const unsigned parity = (unsigned)((r / kIdRing) & 1);
+        asm volatile("{\n"
+                     ".reg .pred P1;\n"
+                     "LAB_WAIT:\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                     "@P1 bra DONE;\n"
+                     "bra LAB_WAIT;\n"
+                     "DONE:\n"
+                     "}" :: "r"(bar), "r"(parity) : "memory");
+        return j < j_count ? ring->buf[r % kIdRing][tid] : -1;
+#else
+        return j < j_count ? __ldg(ids + j) : -1;
+#endif
+    }
+    // after the block barrier that ends iteration k: every thread has read tiles <= k+2 = ring entries
+    // <= k, so the slot of entry k is free for entry k + kIdRing
+    __device__ __forceinline__ void refill(int k, int tid) const {
+#if PB_TMA_IDS
+        if (ids && tid == 0 && k + kIdRing + kIdDirect < n_tiles) issue(k + kIdRing);
+#endif
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // the force kernel
 // ------------------------------------------------------------------------------------------
 template <int NR, int MINB>
@@ -335,6 +411,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
 {
     __shared__ Smem sm;
     __shared__ int near_flag[2][kWarpsPerCta];   // per tile buffer, per staging warp (= 16-pair segment)
+    __shared__ IdRing ring;                      // index tiles, filled by TMA bulk copies
 
     const Task task = tasks[blockIdx.x];
     const Walk w    = walks[task.walk];
@@ -367,10 +444,13 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
         const bool count_only = (task.kind == 2);     // neighbour search only (tree_nb): no force math
         const int* ids = (w.ej_off >= 0) ? id_epj + w.ej_off + task.j_begin : nullptr;   // ej_off < 0: dense list
         const int dbase = task.j_begin;
-        // software pipeline: ids run two tiles ahead, gathered j one tile ahead
-        int id_cur = ep_load_id(ids, tid, task.j_count, dbase);
+        // software pipeline: index tiles arrive by TMA up to five tiles ahead, ids are picked up two
+        // tiles ahead, the gathered j records one tile ahead
+        IdPipe idp;
+        idp.init(ids, task.j_count, n_tiles, dbase, &ring, tid);
+        int id_cur = idp.get(0, tid);
         EpRegs jr  = ep_load_j(epj, id_cur);
-        int id_nxt = ep_load_id(ids, kTileJ + tid, task.j_count, dbase);
+        int id_nxt = idp.get(1, tid);
         {
             const bool nr_ = ep_store(sm.ep[0], tid, id_cur, jr, w, prm.abs_mode);
             const unsigned bal = __ballot_sync(0xffffffffu, nr_);
@@ -380,7 +460,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
         for (int k = 0; k < n_tiles; ++k) {
             const bool more = (k + 1 < n_tiles);
             if (more) jr = ep_load_j(epj, id_nxt);
-            const int id_nn = ep_load_id(ids, (k + 2) * kTileJ + tid, task.j_count, dbase);
+            const int id_nn = idp.get(k + 2, tid);
             if (busy) {
                 const int nv  = min(kTileJ, task.j_count - k * kTileJ);
                 const int npu = (((nv + 1) >> 1) + kPairUnroll - 1) & ~(kPairUnroll - 1);
@@ -407,18 +487,21 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             }
             id_nxt = id_nn;
             __syncthreads();
+            idp.refill(k, tid);
         }
     } else {
         const int* ids = id_spj + w.sj_off + task.j_begin;
-        int id_cur = ep_load_id(ids, tid, task.j_count);
+        IdPipe idp;
+        idp.init(ids, task.j_count, n_tiles, 0, &ring, tid);
+        int id_cur = idp.get(0, tid);
         SpRegs jr  = sp_load_j(spj, id_cur);
-        int id_nxt = ep_load_id(ids, kTileJ + tid, task.j_count);
+        int id_nxt = idp.get(1, tid);
         sp_store(sm.sp[0], tid, id_cur, jr, w, prm.eps2);
         __syncthreads();
         for (int k = 0; k < n_tiles; ++k) {
             const bool more = (k + 1 < n_tiles);
             if (more) jr = sp_load_j(spj, id_nxt);
-            const int id_nn = ep_load_id(ids, (k + 2) * kTileJ + tid, task.j_count);
+            const int id_nn = idp.get(k + 2, tid);
             if (busy) {
                 const int nv  = min(kTileJ, task.j_count - k * kTileJ);
                 const int npu = ((nv + 1) >> 1);          // pairs with at least one real j (padding pairs are inert anyway)
@@ -430,6 +513,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             if (more) sp_store(sm.sp[(k + 1) & 1], tid, id_nxt, jr, w, prm.eps2);
             id_nxt = id_nn;
             __syncthreads();
+            idp.refill(k, tid);
         }
     }
 
