@@ -226,7 +226,7 @@ __device__ __forceinline__ void ep_count_pairs(const EpTile& t, int p0, int p1,
 // With the traceless tensor Q' = 3Q - tr I (formed in fp64 on the host) and
 // S = dx.Q'dx - eps2 tr  this is, term for term and for any eps2, the same as
 //   acc -= (m r^-3 + 2.5 S r^-7) dx - r^-5 Q'dx ; pot -= m r^-1 + 0.5 S r^-5
-// (3 qrr - tr r2 = S because r2 = dx.dx + eps2) — 34 instead of 38 packed FP operations per
+// (3 qrr - tr r2 = S because r2 = dx.dx + eps2) — 33 instead of 38 packed FP operations per
 // pair of interactions.  The reference's own SIMD path uses the same traceless form
 // (src/phantomquad_for_p3t_x86.hpp:144-163).
 // ------------------------------------------------------------------------------------------
@@ -294,15 +294,15 @@ __device__ __forceinline__ void sp_pairs(const SpTile& t, int p0, int p1,
         r2 = __ffma2_rn(dy, dy, r2);
         r2 = __ffma2_rn(dz, dz, r2);
         const float2 rinv = rsqrt2<NR>(r2);
-        float2 qrx = __fmul2_rn(qxx, dx); qrx = __ffma2_rn(qxy, dy, qrx); qrx = __ffma2_rn(qxz, dz, qrx);
-        float2 qry = __fmul2_rn(qxy, dx); qry = __ffma2_rn(qyy, dy, qry); qry = __ffma2_rn(qyz, dz, qry);
-        float2 qrz = __fmul2_rn(qxz, dx); qrz = __ffma2_rn(qyz, dy, qrz); qrz = __ffma2_rn(qzz, dz, qrz);
+        // column order: three independent operations share dx, then dy, then dz (operand reuse)
+        float2 qrx = __fmul2_rn(qxx, dx), qry = __fmul2_rn(qxy, dx), qrz = __fmul2_rn(qxz, dx);
+        qrx = __ffma2_rn(qxy, dy, qrx); qry = __ffma2_rn(qyy, dy, qry); qrz = __ffma2_rn(qyz, dy, qrz);
+        qrx = __ffma2_rn(qxz, dz, qrx); qry = __ffma2_rn(qyz, dz, qry); qrz = __ffma2_rn(qzz, dz, qrz);
         float2 S = __ffma2_rn(qrx, dx, mtr); S = __ffma2_rn(qry, dy, S); S = __ffma2_rn(qrz, dz, S);
         const float2 rinv2 = __fmul2_rn(rinv, rinv);
-        const float2 mr1   = __fmul2_rn(mj, rinv);
-        const float2 mr3   = __fmul2_rn(mr1, rinv2);
-        const float2 rinv4 = __fmul2_rn(rinv2, rinv2);
-        const float2 rinv5 = __fmul2_rn(rinv4, rinv);
+        const float2 rinv3 = __fmul2_rn(rinv2, rinv);
+        const float2 rinv5 = __fmul2_rn(rinv3, rinv2);
+        const float2 mr3   = __fmul2_rn(mj, rinv3);
         const float2 S5    = __fmul2_rn(rinv5, S);
         const float2 S7    = __fmul2_rn(S5, rinv2);
         const float2 A     = __ffma2_rn(bc(2.5f), S7, mr3);
@@ -313,7 +313,7 @@ __device__ __forceinline__ void sp_pairs(const SpTile& t, int p0, int p1,
         az = __ffma2_rn(nA, dz, az); az = __ffma2_rn(rinv5, qrz, az);
         // pot accumulates +(m r^-1 + 0.5 S r^-5); negated at the end
         pt = __ffma2_rn(bc(0.5f), S5, pt);
-        pt = __fadd2_rn(pt, mr1);
+        pt = __ffma2_rn(mj, rinv, pt);
     }
 }
 
