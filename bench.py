@@ -390,8 +390,9 @@ def main():
                                           "host_plan": prof["t_plan"] * 1e3 / args.steps, "host_pack": prof["t_pack"] * 1e3 / args.steps,
                                           "host_unpack": prof["t_unpack"] * 1e3 / args.steps, "host_enqueue": prof["t_enqueue"] * 1e3 / args.steps, "h2d": prof["t_send"] * 1e3 / args.steps,
                                           "kernels": prof["t_calc"] * 1e3 / args.steps, "d2h": prof["t_recv"] * 1e3 / args.steps,
+                                          "gpu_idle_between_walk_groups": prof["t_gap"] * 1e3 / args.steps,
                                           "note": "device intervals of concurrent streams overlap; they do not add up to ms_per_step"},
-                    "api": "CalcForceWithLinearCutoffCUDAMultiWalk / RetrieveForceCUDA (C++ shim -> C ABI), host buffers"},
+                    "api": "CalcForceWithLinearCutoffCUDAMultiWalk / RetrieveForceCUDA driven by the FDPS-style walk-group loop (C++ shim -> C ABI), host buffers"},
             # value leg (K x all kernels) + its force-only timing pass (K x force kernels) + e2e leg (counted by the library)
             "gpu_launches": int(launches_per_step * args.steps + (launches_per_step // 2) * args.steps + prof["n_kernel_launch"]),
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,

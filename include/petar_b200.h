@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 1
+#define PB_ABI_VERSION 2
 
 typedef enum pb_status {
     PB_OK = 0,
@@ -92,6 +92,9 @@ typedef struct pb_profile {
     /* host sub-phases of t_copy (seconds): task planning, packing into pinned staging, result
      * scatter; and the time spent enqueueing copies/kernels (not part of t_copy) */
     double t_plan, t_pack, t_unpack, t_enqueue;
+    /* device-timed idle between walk groups: from the end of one dispatch's last kernel to the first
+     * kernel of the next dispatch (the tag_max = 1 protocol drains the GPU at every retrieve) */
+    double t_gap;
 } pb_profile;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */
@@ -117,8 +120,11 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "nr"         Newton-Raphson steps after MUFU.RSQ (0 default, or 1).
  *   "cull"       1 (default): skip the neighbour test for j-tile segments that cannot reach any
  *                i-particle of the walk (results identical); 0: test every pair.
- *   "occupancy"  resident CTAs per SM the force kernel is compiled for: 2 (default, 119 registers)
+ *   "occupancy"  resident CTAs per SM the force kernel is compiled for: 2 (default, 122 registers)
  *                or 3 (80 registers).
+ *   "lead"       the first of a dispatch's per-stream sub-batches is 1/(1+lead) the size of the others
+ *                (the GPU idles until its copy lands): 0 = equal sizes, 1 (default), up to 15.
+ *   "tree_batch" groups per force launch of pb_tree_force (default 1024).
  * Returns PB_ERR_ARG for an unknown key or value. */
 int  pb_set_option(const char* key, long long value);
 

@@ -217,6 +217,34 @@ int pb_shim_retrieve(int tag, int n_walk, const int* ni, void** force) {
     return RetrieveForceCUDA(tag, n_walk, ni, (ForceSoft**)force);
 }
 
+#ifdef PARTICLE_SIMULATOR_GPU_MULIT_WALK_INDEX
+// The loop FDPS calcForceAllAndWriteBackMultiWalkIndex(dispatch, retrieve, tag_max = 1, ...) runs around the
+// two functors (call site src/petar.hpp:894-899), over walk groups whose lists already exist: one dispatch
+// with send_flag = true publishing all j, then per group retrieve(previous) + dispatch(this), and a last
+// retrieve.  Group g's tables are the arrays FDPS holds when it calls dispatch: epi[g][iw], n_epi[g][iw], ...
+int pb_shim_walk_group_loop(int my_rank, double eps2, double rcut2, double G, int n_group, const int* n_walk,
+                            const void* const* epi, const void* const* n_epi,
+                            const void* const* id_epj, const void* const* n_epj,
+                            const void* const* id_spj, const void* const* n_spj, const void* const* force,
+                            const void* epj, int n_epj_tot, const void* spj, int n_spj_tot, int send_flag) {
+    int ret = 0;
+    if (send_flag) {
+        CalcForceWithLinearCutoffCUDAMultiWalk f(my_rank, eps2, rcut2, G);
+        ret += f(0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                 (const EPJSoft*)epj, n_epj_tot, (const SPJSoft*)spj, n_spj_tot, true);
+    }
+    for (int g = 0; g < n_group; g++) {
+        if (g > 0) ret += RetrieveForceCUDA(0, n_walk[g - 1], (const int*)n_epi[g - 1], (ForceSoft**)force[g - 1]);
+        CalcForceWithLinearCutoffCUDAMultiWalk f(my_rank, eps2, rcut2, G);     // a temporary per call, as PeTar does
+        ret += f(0, n_walk[g], (const EPISoft**)epi[g], (const int*)n_epi[g], (const int**)id_epj[g], (const int*)n_epj[g],
+                 (const int**)id_spj[g], (const int*)n_spj[g],
+                 (const EPJSoft*)epj, n_epj_tot, (const SPJSoft*)spj, n_spj_tot, false);
+    }
+    if (n_group > 0) ret += RetrieveForceCUDA(0, n_walk[n_group - 1], (const int*)n_epi[n_group - 1], (ForceSoft**)force[n_group - 1]);
+    return ret;
+}
+#endif
+
 #ifdef GPU_PROFILE
 void pb_shim_profile(double t[4], long long n[5], int clear) {
     t[0] = gpu_profile.copy.time; t[1] = gpu_profile.send.time; t[2] = gpu_profile.recv.time; t[3] = gpu_profile.calc.time;

@@ -123,6 +123,8 @@ struct Engine {
     int* d_walk_scratch[kMaxStreams] = {nullptr}; int* d_overflow = nullptr;
     int* d_tree_ide = nullptr; int* d_tree_ids = nullptr; size_t cap_tree_ide = 0, cap_tree_ids = 0;
     int2* d_tree_off = nullptr; std::vector<int2> h_tree_off; cudaEvent_t ev_fill = nullptr;
+    // end of the last kernel of the two most recent dispatches (gap timer, pb_profile.t_gap)
+    cudaEvent_t ev_end[2] = {nullptr, nullptr}; int end_cur = 0; bool end_prev_valid = false; int out_first_slot = -1;
     int2* h_counts_p = nullptr; size_t cap_counts_p = 0; int* h_over_p = nullptr;   // pinned landing zone of the count pass
     cudaEvent_t ev_count = nullptr; bool count_pending = false;
     int opt_tree_batch = 1024; int tree_last_batches = 0;
@@ -506,10 +508,11 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         cum[w + 1] = cum[w] + (double)win[w].ni * ((double)win[w].nej + 2.0 * (double)win[w].nsj) + 1.0;
     std::vector<int> cut(n_slots + 1, 0);
     cut[n_slots] = n_walk;
-    // the first sub-batch is half the size of the others: the GPU is idle until its copy lands
-    const double unit = cum[n_walk] / (n_slots - 0.5);
+    // the first sub-batch is 1/(1+lead) the size of the others: the GPU is idle until its copy lands
+    const double w0 = 1.0 / (1.0 + std::max(0, E.opt_lead));
+    const double unit = cum[n_walk] / (n_slots - 1 + w0);
     for (int s = 1; s < n_slots; s++) {
-        const double target = E.opt_lead ? unit * (s - 0.5) : cum[n_walk] * s / n_slots;
+        const double target = unit * (s - 1 + w0);
         cut[s] = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
         cut[s] = std::max(cut[s], cut[s - 1]);
         cut[s] = std::min(cut[s], n_walk);
@@ -537,6 +540,10 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         if (S.active) plan_batch(win + S.w_begin, S.w_end - S.w_begin, direct, n_slots, hp[s]);
     }
     E.prof.t_plan += now_s() - tp0;
+    int first_active = -1, last_active = -1;
+    for (int s = 0; s < n_slots; s++)
+        if (E.slots[s].active) { if (first_active < 0) first_active = s; last_active = s; }
+    E.out_first_slot = first_active;
     for (int s = 0; s < n_slots; s++) {
         Slot& S = E.slots[s];
         if (!S.active) continue;
@@ -556,6 +563,7 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         CU(cudaEventRecord(S.ev[1], S.stream));
         CU(launch_plan(S.stream, S.plan, S.d_arena, direct, S.d_part4, S.d_partn, S.d_out));
         CU(cudaEventRecord(S.ev[2], S.stream));
+        if (s == last_active) CU(cudaEventRecord(E.ev_end[E.end_cur], S.stream));
         CU(cudaMemcpyAsync(S.h_out, S.d_out, sizeof(ForceOut) * S.plan.n_i, cudaMemcpyDeviceToHost, S.stream));
         CU(cudaEventRecord(S.ev[3], S.stream));
         E.prof.h2d_bytes += (long long)S.plan.bytes;
@@ -620,6 +628,8 @@ int pb_init(int my_rank, int device) {
     CU(cudaEventCreateWithFlags(&E.ev_j_ready, cudaEventDisableTiming));
     CU(cudaEventCreate(&E.ev_send0));
     CU(cudaEventCreate(&E.ev_send1));
+    CU(cudaEventCreate(&E.ev_end[0]));
+    CU(cudaEventCreate(&E.ev_end[1]));
     for (int s = 0; s < kMaxStreams; s++) {
         CU(cudaStreamCreateWithFlags(&E.slots[s].stream, cudaStreamNonBlocking));
         for (int k = 0; k < 4; k++) CU(cudaEventCreate(&E.slots[s].ev[k]));
@@ -651,6 +661,7 @@ void pb_finalize(void) {
     if (E.ev_count) cudaEventDestroy(E.ev_count);
     if (E.ev_fill) cudaEventDestroy(E.ev_fill);
     cudaEventDestroy(E.ev_j_ready); cudaEventDestroy(E.ev_send0); cudaEventDestroy(E.ev_send1);
+    cudaEventDestroy(E.ev_end[0]); cudaEventDestroy(E.ev_end[1]); E.end_prev_valid = false;
     cudaStreamDestroy(E.s_upload);
     const int coords = E.opt_coords, streams = E.opt_streams, jchunk = E.opt_jchunk, nr = E.opt_nr, cull = E.opt_cull, occ = E.opt_occ, lead = E.opt_lead;
     const double eps2 = E.eps2, rcut2 = E.rcut2, G = E.G;
@@ -672,7 +683,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "jchunk"))  { if (v < 0 || v > (1 << 20)) return fail(PB_ERR_ARG, "jchunk out of range"); E.opt_jchunk = (int)v; return PB_OK; }
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
-    if (!strcmp(key, "lead"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "lead must be 0 or 1"); E.opt_lead = (int)v; return PB_OK; }
+    if (!strcmp(key, "lead"))    { if (v < 0 || v > 15) return fail(PB_ERR_ARG, "lead must be in [0, 15]"); E.opt_lead = (int)v; return PB_OK; }
     if (!strcmp(key, "occupancy")) { if (v < 2 || v > 3) return fail(PB_ERR_ARG, "occupancy must be 2 or 3"); E.opt_occ = (int)v; return PB_OK; }
     if (!strcmp(key, "nr"))      { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nr must be 0 or 1"); E.opt_nr = (int)v; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_set_option: unknown key '%s'", key);
@@ -708,6 +719,7 @@ int pb_upload_j_range(const void* epj, int epj_first, int n_epj, const pb_layout
     if (n_epj) pack_epj(epj, n_epj, *lepj, he);
     if (n_spj) pack_spj(spj, n_spj, *lspj, hs);
     E.prof.t_copy += now_s() - t0;
+    E.end_prev_valid = false;                             // a new tree step: no gap to the previous dispatch
     CU(cudaEventRecord(E.ev_send0, E.s_upload));
     if (n_epj) CU(cudaMemcpyAsync(E.d_epj + 2 * (size_t)epj_first, he, (size_t)PB_EPJ_DEV_BYTES * n_epj, cudaMemcpyHostToDevice, E.s_upload));
     if (n_spj) CU(cudaMemcpyAsync(E.d_spj + 4 * (size_t)spj_first, hs, (size_t)PB_SPJ_DEV_BYTES * n_spj, cudaMemcpyHostToDevice, E.s_upload));
@@ -872,6 +884,14 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, E.ev_send0, E.ev_send1) == cudaSuccess) E.prof.t_send += 1e-3 * ms;
         E.send_timed = false;
+    }
+    if (E.out_first_slot >= 0) {
+        // GPU idle since the previous walk group's last kernel (same tree step only)
+        float ms = 0.f;
+        if (E.end_prev_valid && cudaEventElapsedTime(&ms, E.ev_end[E.end_cur ^ 1], E.slots[E.out_first_slot].ev[1]) == cudaSuccess && ms > 0.f)
+            E.prof.t_gap += 1e-3 * ms;
+        E.end_prev_valid = true;
+        E.end_cur ^= 1;
     }
     E.outstanding = false;
     return PB_OK;

@@ -54,7 +54,8 @@ class Profile(C.Structure):
                 ("n_walk", C.c_longlong), ("n_epi", C.c_longlong), ("n_epj", C.c_longlong), ("n_spj", C.c_longlong),
                 ("n_call", C.c_longlong), ("n_interaction_ep", C.c_longlong), ("n_interaction_sp", C.c_longlong),
                 ("n_kernel_launch", C.c_longlong), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
-                ("t_plan", C.c_double), ("t_pack", C.c_double), ("t_unpack", C.c_double), ("t_enqueue", C.c_double)]
+                ("t_plan", C.c_double), ("t_pack", C.c_double), ("t_unpack", C.c_double), ("t_enqueue", C.c_double),
+                ("t_gap", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -142,6 +143,8 @@ def load_shim(direct=False):
                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int]
         S.pb_shim_retrieve.argtypes = [C.c_int, C.c_int, _vp, _vp]
         S.pb_shim_dispatch_count.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]
+        S.pb_shim_walk_group_loop.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, _vp,
+                                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int]
         S.pb_shim_profile.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
         S.pb_shim_profile.restype = None
         _shim = S
@@ -288,20 +291,44 @@ def get_gravity_and_potential_at_point(x, y, z, particles, G=1.0):
 N_WALK_LIMIT = 200   # reference src/petar.hpp:888
 
 
+class DispatchTables(list):
+    """Per-walk-group pointer tables (list of walks.PointerTables) plus, for the C++ loop driver,
+    the arrays of pointers to them."""
+
+    def finish(self):
+        def col(name):
+            return np.array([getattr(t, name).ctypes.data for t in self], dtype=np.uint64)
+        self.n_walk = np.array([t.n_walk for t in self], dtype=np.int32)
+        self.cols = [col(k) for k in ("epi_ptrs", "n_epi", "id_epj_ptrs", "n_epj", "id_spj_ptrs", "n_spj", "force_ptrs")]
+        return self
+
+
 def make_dispatch_tables(batch, force, n_walk_limit=N_WALK_LIMIT):
     """The per-walk-group pointer tables FDPS holds ready when it calls dispatch (built once for a
     prebuilt WalkBatch so that the emulated FDPS loop does not pay numpy bookkeeping per group)."""
-    return [batch.pointer_tables(force, slice(w0, min(w0 + n_walk_limit, batch.n_walk)))
-            for w0 in range(0, batch.n_walk, n_walk_limit)]
+    return DispatchTables(batch.pointer_tables(force, slice(w0, min(w0 + n_walk_limit, batch.n_walk)))
+                          for w0 in range(0, batch.n_walk, n_walk_limit)).finish()
 
 
-def calc_force_all_and_write_back(batch, eps, r_out, G, n_walk_limit=N_WALK_LIMIT, my_rank=0, force=None, send=True, tables=None):
+def calc_force_all_and_write_back(batch, eps, r_out, G, n_walk_limit=N_WALK_LIMIT, my_rank=0, force=None, send=True, tables=None,
+                                  python_loop=False):
     """Emulates ``tree_soft.calcForceAllAndWriteBackMultiWalkIndex(dispatch, retrieve, 1, ..., n_walk_limit)``
     (src/petar.hpp:888-899) over a prebuilt WalkBatch: one dispatch with send_flag=true publishing all
     j, then per walk group dispatch(send_flag=false) and — after the next group's lists would have
     been built — retrieve of the previous group.  Returns ForceSoft[n_epi_total].
-    `tables` (optional): make_dispatch_tables(batch, force, n_walk_limit), reused across steps."""
+    `tables` (optional): make_dispatch_tables(batch, force, n_walk_limit), reused across steps.
+    The loop itself runs in C++ (pb_shim_walk_group_loop in the shim, calling the functors the way FDPS
+    does); python_loop=True drives the same functors call by call from Python instead."""
     f = np.zeros(batch.n_epi_total, dtype=ForceSoft) if force is None else force
+    if tables is None:
+        tables = make_dispatch_tables(batch, f, n_walk_limit)
+    if not python_loop:
+        S = load_shim()
+        c = tables.cols
+        rc = S.pb_shim_walk_group_loop(int(my_rank), float(eps * eps), float(r_out * r_out), float(G), len(tables), _ptr(tables.n_walk),
+                                       *(_ptr(a) for a in c), _ptr(batch.epj), len(batch.epj), _ptr(batch.spj), len(batch.spj), int(bool(send)))
+        assert rc == 0
+        return f
     disp = CalcForceWithLinearCutoffCUDAMultiWalk(my_rank, eps * eps, r_out * r_out, G)
     none_u64 = np.zeros(0, dtype=np.uint64)
     none_i32 = np.zeros(0, dtype=np.int32)
@@ -310,8 +337,6 @@ def calc_force_all_and_write_back(batch, eps, r_out, G, n_walk_limit=N_WALK_LIMI
                   batch.epj, len(batch.epj), batch.spj, len(batch.spj), True)
         assert rc == 0
     prev = None
-    if tables is None:
-        tables = make_dispatch_tables(batch, f, n_walk_limit)
     for t in tables:
         if prev is not None:
             RetrieveForceCUDA(0, prev.n_walk, prev.n_epi, prev.force_ptrs)

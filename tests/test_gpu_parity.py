@@ -294,6 +294,9 @@ def test_ragged_and_tiny_walks():
     assert np.median(ea) < 3e-6 and ea.max() < TOL_MAX
     assert np.array_equal(f[~nz]["acc"], ref[~nz]["acc"])
     assert count_mismatch_report(batch, f, ref, "ragged") <= 2
+    # the C++ loop driver in the shim and the call-by-call Python loop drive the same functors
+    f_py = engine.calc_force_all_and_write_back(batch, 1e-3, 0.03, 0.7, n_walk_limit=4, python_loop=True)
+    assert f_py.tobytes() == f.tobytes()
 
 
 def test_protocol_errors():
