@@ -256,6 +256,41 @@ int  pb_pack_epj_host(const void* epj, int n, const pb_layout_epj* l, void* out3
 int  pb_pack_epj_host_indexed(const void* epj, const long long* idx, int n, const pb_layout_epj* l, void* out32);
 int  pb_pack_spj_host(const void* spj, int n, const pb_layout_spj* l, void* out64);
 
+/* ---- changeover correction of the soft force ----------------------------------
+ * Replaces the particle loop of SystemHard::correctForceWithCutoffTreeNeighborOMP (reference
+ * src/hard.hpp:3366-3377): for every particle i, correctForceWithCutoffTreeNeighborOneParticleImp
+ * (:1655-1691) — the self-potential term, then calcAccPotShortWithLinearCutoff (:1408-1476) for every
+ * neighbour whose id differs, in list order.  acc, pot_tot and pot_soft of the i-particles are updated in
+ * place, bit-identical to the reference function applied in the same order (fp64 on the device).
+ *
+ * i-particles (FPSoft) and neighbours (EPJSoft) are described by field offsets: pos (3 doubles), mass,
+ * the changeover radii (ChangeOver::r_in_/r_out_ or EPJSoft::r_in/r_out), id (int64) and
+ * group_data.artificial = {mass_backup, status} (doubles); off_acc / off_pot_tot / off_pot_soft are
+ * used for the i side only.  Neighbour lists are CSR: nb_idx[nb_off[i] .. nb_off[i+1]) index ptcl_j.
+ *
+ * replay_fp32 = 1: the linear-cutoff term is re-evaluated in float from absolute coordinates, the
+ *   reference's `USE_GPU` branch (use with option "coords" = 1, whose force kernel computes that term
+ *   from the same float coordinates);  replay_fp32 = 0: all in double, the reference's `#else` branch
+ *   (use with the default coordinates: the force kernel's own term is accurate to fp32 rounding of the
+ *   true separation, so the exact term is what cancels it best).
+ * status_no_cm: the status value of a group member without c.m. particle, -PS::LARGE_FLOAT
+ *   (= -FLT_MAX/16, src/ptcl.hpp:214-221). */
+typedef struct pb_layout_corr {
+    size_t stride;
+    size_t off_pos, off_mass, off_r_in, off_r_out, off_id, off_mass_backup, off_status;
+    size_t off_acc, off_pot_tot, off_pot_soft;
+} pb_layout_corr;
+
+typedef struct pb_corr_params {
+    double eps2, r_out, G;      /* EPISoft::eps^2, EPISoft::r_out, ForceSoft::grav_const */
+    double status_no_cm;
+    int    replay_fp32;
+} pb_corr_params;
+
+int  pb_correct_changeover(int n_i, void* ptcl_i, const pb_layout_corr* li,
+                           int n_j, const void* ptcl_j, const pb_layout_corr* lj,
+                           const int* nb_off, const int* nb_idx, const pb_corr_params* prm);
+
 #ifdef __cplusplus
 }
 #endif

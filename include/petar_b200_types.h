@@ -72,8 +72,23 @@ typedef struct pb_ForceSoft {
     int64_t   n_ngb;
 } pb_ForceSoft;
 
+/* The fields of FPSoft / EPJSoft that the changeover correction reads (pos, mass, changeover radii, id,
+ * group_data.artificial = {mass_backup, status}: reference src/ptcl.hpp, src/artificial_particles.hpp:20-28)
+ * and updates (acc, pot_tot, pot_soft: src/soft_ptcl.hpp:27-60).  A stand-in layout for the oracle, the
+ * harness and the tests; the ABI (pb_correct_changeover) takes field offsets, not this struct. */
+typedef struct pb_PtclCorr {
+    int64_t   id;
+    double    mass;
+    pb_f64vec pos;
+    double    r_in, r_out;            /* ChangeOver::r_in_, r_out_ (FPSoft) or EPJSoft::r_in, r_out */
+    double    mass_backup, status;    /* ArtificialParticleInformation */
+    pb_f64vec acc;
+    double    pot_tot, pot_soft;
+} pb_PtclCorr;
+
 #ifdef __cplusplus
 }
+static_assert(sizeof(pb_PtclCorr)  == 112, "PtclCorr must be 112 bytes");
 static_assert(sizeof(pb_EPISoft)   == 48,  "EPISoft mirror must be 48 bytes");
 static_assert(sizeof(pb_EPJSoft)   == 120, "EPJSoft mirror must be 120 bytes");
 static_assert(sizeof(pb_SPJQuad)   == 80,  "SPJQuadrupoleInAndOut mirror must be 80 bytes");

@@ -16,7 +16,7 @@ import subprocess
 
 import numpy as np
 
-from petar_b200.types import EPISoft, EPJSoft, SPJQuad, ForceSoft
+from petar_b200.types import EPISoft, EPJSoft, SPJQuad, ForceSoft, PtclCorr, LARGE_FLOAT
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _vp = C.c_void_p
@@ -73,6 +73,9 @@ def oracle_lib():
         L.orc_mt_real2.restype = C.c_double
         L.orc_calc_rsearch.argtypes = [_vp, C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_calc_rsearch.restype = C.c_double
+        L.orc_changeover_w.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_changeover_pair.argtypes = [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.orc_correct_force_tree_neighbor.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
         _oracle = L
     return _oracle
 
@@ -242,3 +245,52 @@ def ref_cuda_step(batch, eps, r_out, G, n_walk_limit=200):
     if rc != 0:
         raise RuntimeError("reference CUDA baseline failed")
     return force, float(ms[0]), float(ms[1])
+
+
+# ---- changeover correction (oracle_changeover.c; reference src/hard.hpp:1408-1476, 1655-1691) ----
+def changeover_w(r_in, r_out, dr):
+    a, p = C.c_double(), C.c_double()
+    oracle_lib().orc_changeover_w(r_in, r_out, dr, C.byref(a), C.byref(p))
+    return a.value, p.value
+
+
+def changeover_pair(pi, pj, eps, r_out, G, replay_fp32):
+    """pi, pj: 1-element PtclCorr arrays; pi is updated in place."""
+    oracle_lib().orc_changeover_pair(_chk(pi, PtclCorr), _chk(pj, PtclCorr), eps * eps, r_out, G, int(replay_fp32))
+
+
+def correct_force_tree_neighbor(p, nb_off, nb_idx, pj, eps, r_out, G, replay_fp32, status_no_cm=-LARGE_FLOAT):
+    """In-place correction of p[*].acc / pot_tot / pot_soft over CSR neighbour lists (indices into pj)."""
+    assert nb_off.dtype == np.int32 and nb_idx.dtype == np.int32 and len(nb_off) == len(p) + 1
+    oracle_lib().orc_correct_force_tree_neighbor(_chk(p, PtclCorr), len(p), nb_off.ctypes.data, nb_idx.ctypes.data if len(nb_idx) else None,
+                                                 _chk(pj, PtclCorr), eps * eps, r_out, G, status_no_cm, int(replay_fp32))
+    return p
+
+
+_ref_co = {}
+
+
+def ref_changeover_available():
+    return all(os.path.exists(os.path.join(_HERE, "_ref", f"libpetar_ref_changeover_{k}.so")) for k in ("f32", "f64"))
+
+
+def ref_changeover_lib(replay_fp32):
+    """The reference's own ChangeOver class and calcAccPotShortWithLinearCutoff (ref_changeover.cpp),
+    built with -DUSE_GPU (float replay) or -DP3T_64BIT (all double)."""
+    key = "f32" if replay_fp32 else "f64"
+    if key not in _ref_co:
+        L = C.CDLL(os.path.join(_HERE, "_ref", f"libpetar_ref_changeover_{key}.so"))
+        L.ref_changeover_w.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_changeover_pair.argtypes = [_vp, _vp, C.c_double, C.c_double, C.c_double]
+        _ref_co[key] = L
+    return _ref_co[key]
+
+
+def ref_changeover_w(r_in, r_out, dr):
+    a, p = C.c_double(), C.c_double()
+    ref_changeover_lib(False).ref_changeover_w(r_in, r_out, dr, C.byref(a), C.byref(p))
+    return a.value, p.value
+
+
+def ref_changeover_pair(pi, pj, eps, r_out, G, replay_fp32):
+    ref_changeover_lib(replay_fp32).ref_changeover_pair(_chk(pi, PtclCorr), _chk(pj, PtclCorr), eps, r_out, G)

@@ -96,6 +96,17 @@ void orc_simdtest_set_spj(double N, pb_SPJQuad* sp);
 void orc_simdtest_inputs(int n_epi, int n_epj, int n_spj,
                          pb_EPISoft* epi, pb_EPJSoft* epj, pb_SPJQuad* spj);
 
+/* ---- changeover correction of the soft force (oracle_changeover.c) --------------------------- */
+/* reference src/changeover.hpp:69-78 (setR), :318-334 (calcAcc0W), :294-309 (calcPotW) */
+void orc_changeover_w(double r_in, double r_out, double dr, double* acc0w, double* potw);
+/* reference src/hard.hpp:1408-1476 calcAccPotShortWithLinearCutoff(Tpi&, const EPJSoft&); replay_fp32 selects
+ * the `USE_GPU` branch (float replay of the linear-cutoff term) or the all-double `#else` branch */
+void orc_changeover_pair(pb_PtclCorr* pi, const pb_PtclCorr* pj, double eps2, double r_out, double G, int replay_fp32);
+/* reference src/hard.hpp:1655-1691 for every particle (loop of :3366-3377); neighbours in CSR form,
+ * indices into pj; status_no_cm = -PS::LARGE_FLOAT (a member without c.m. particle) */
+void orc_correct_force_tree_neighbor(pb_PtclCorr* p, int n, const int* nb_off, const int* nb_idx, const pb_PtclCorr* pj,
+                                     double eps2, double r_out, double G, double status_no_cm, int replay_fp32);
+
 #ifdef __cplusplus
 }
 #endif

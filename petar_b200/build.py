@@ -50,9 +50,10 @@ def build_engine(force=False, verbose=False):
     """libpetar_b200.so: CUDA kernels + C ABI."""
     os.makedirs(LIB, exist_ok=True)
     target = os.path.join(LIB, "libpetar_b200.so")
-    # pb_walk.cu (tree walk, fp64 geometry) is compiled without FMA contraction so that its opening
-    # decisions are bit-identical to a host walk; the force kernels keep the default
-    units = (("pb_kernels.cu", []), ("pb_engine.cu", []), ("pb_walk.cu", ["-fmad=false"]))
+    # pb_walk.cu (tree walk, fp64 geometry) and pb_corr.cu (changeover correction, fp64) are compiled
+    # without FMA contraction so that their results are bit-identical to host code; the force kernels
+    # keep the default
+    units = (("pb_kernels.cu", []), ("pb_engine.cu", []), ("pb_walk.cu", ["-fmad=false"]), ("pb_corr.cu", ["-fmad=false"]))
     srcs = [os.path.join(CSRC, f) for f, _ in units]
     deps = srcs + [os.path.join(CSRC, "pb_device.h"), os.path.join(INC, "petar_b200.h")]
     if force or _newer(target, deps):

@@ -100,4 +100,12 @@ cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* gro
 cudaError_t launch_walk_fill(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
                              const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow);
 
+// changeover correction (pb_corr.cu): the fields of one neighbour / one corrected particle, fp64
+struct CorrJ { double x, y, z, mass, r_in, r_out, mass_bk, status; long long id; };       // 72 B
+struct CorrI { CorrJ p; double ax, ay, az, pot_tot, pot_soft; };                            // 112 B
+struct CorrOut { double ax, ay, az, pot_tot, pot_soft; };                                   // 40 B
+struct CorrParams { double eps2, r_out, G, status_no_cm; int replay_fp32; };
+cudaError_t launch_corr(cudaStream_t s, int n_i, const CorrI* pi, const CorrJ* pj,
+                        const int* nb_off, const int* nb_idx, CorrOut* out, CorrParams prm);
+
 } // namespace pb

@@ -123,6 +123,7 @@ struct Engine {
     int* d_walk_scratch[kMaxStreams] = {nullptr}; int* d_overflow = nullptr;
     int* d_tree_ide = nullptr; int* d_tree_ids = nullptr; size_t cap_tree_ide = 0, cap_tree_ids = 0;
     int2* d_tree_off = nullptr; std::vector<int2> h_tree_off; cudaEvent_t ev_fill = nullptr;
+    char* h_corr = nullptr; char* d_corr = nullptr; size_t cap_corr = 0;   // changeover correction: pinned staging + device mirror
     // end of the last kernel of the two most recent dispatches (gap timer, pb_profile.t_gap)
     cudaEvent_t ev_end[2] = {nullptr, nullptr}; int end_cur = 0; bool end_prev_valid = false; int out_first_slot = -1;
     int2* h_counts_p = nullptr; size_t cap_counts_p = 0; int* h_over_p = nullptr;   // pinned landing zone of the count pass
@@ -654,6 +655,9 @@ void pb_finalize(void) {
         S = Slot();
     }
     cudaFree(E.d_epj); cudaFree(E.d_spj); cudaFreeHost(E.h_jstage);
+    if (E.h_corr) cudaFreeHost(E.h_corr);
+    if (E.d_corr) cudaFree(E.d_corr);
+    E.h_corr = nullptr; E.d_corr = nullptr; E.cap_corr = 0;
     cudaFree(E.d_cells); cudaFree(E.d_groups); cudaFree(E.d_counts); cudaFree(E.d_overflow); cudaFreeHost(E.h_tstage);
     for (int s = 0; s < kMaxStreams; s++) cudaFree(E.d_walk_scratch[s]);
     cudaFree(E.d_tree_ide); cudaFree(E.d_tree_ids); cudaFree(E.d_tree_off);
@@ -951,6 +955,98 @@ int pb_field_at_points(const double* x, const double* y, const double* z, int n_
         if (az) az[i] = out[i].az;
         if (pot) pot[i] = out[i].pot;
     }
+    return PB_OK;
+}
+
+// ---- changeover correction ---------------------------------------------------
+namespace {
+inline long long ldi(const char* p, size_t off) { long long v; memcpy(&v, p + off, sizeof(v)); return v; }
+inline CorrJ corr_load(const char* p, const pb_layout_corr& L) {
+    CorrJ j;
+    j.x = ld(p, L.off_pos, 0); j.y = ld(p, L.off_pos, 1); j.z = ld(p, L.off_pos, 2);
+    j.mass = ld(p, L.off_mass); j.r_in = ld(p, L.off_r_in); j.r_out = ld(p, L.off_r_out);
+    j.mass_bk = ld(p, L.off_mass_backup); j.status = ld(p, L.off_status); j.id = ldi(p, L.off_id);
+    return j;
+}
+}
+
+int pb_correct_changeover(int n_i, void* ptcl_i, const pb_layout_corr* li,
+                          int n_j, const void* ptcl_j, const pb_layout_corr* lj,
+                          const int* nb_off, const int* nb_idx, const pb_corr_params* prm) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    if (n_i < 0 || n_j < 0 || !prm || (n_i && (!ptcl_i || !li || !nb_off)) || (n_j && (!ptcl_j || !lj)))
+        return fail(PB_ERR_ARG, "pb_correct_changeover: bad argument");
+    if (n_i == 0) return PB_OK;
+    const long long n_nb = nb_off[n_i];
+    if (nb_off[0] != 0 || n_nb < 0 || (n_nb && !nb_idx)) return fail(PB_ERR_ARG, "pb_correct_changeover: bad neighbour offsets");
+    int bad = 0;
+#pragma omp parallel for reduction(| : bad)
+    for (int i = 0; i < n_i; i++) {
+        if (nb_off[i + 1] < nb_off[i]) bad |= 1;
+        else for (int k = nb_off[i]; k < nb_off[i + 1]; k++) if (nb_idx[k] < 0 || nb_idx[k] >= n_j) bad |= 2;
+    }
+    if (bad) return fail(PB_ERR_ARG, "pb_correct_changeover: neighbour list %s", (bad & 1) ? "offsets decrease" : "index outside ptcl_j");
+
+    // one staging buffer: [CorrI n_i][CorrJ n_j][nb_off n_i+1][nb_idx n_nb] -> device; [CorrOut n_i] back
+    const double t0 = now_s();
+    const size_t o_i = 0;
+    const size_t o_j = align_up(o_i + sizeof(CorrI) * (size_t)n_i, 256);
+    const size_t o_off = align_up(o_j + sizeof(CorrJ) * (size_t)n_j, 256);
+    const size_t o_idx = align_up(o_off + sizeof(int) * ((size_t)n_i + 1), 256);
+    const size_t o_out = align_up(o_idx + sizeof(int) * (size_t)n_nb, 256);
+    const size_t bytes = align_up(o_out + sizeof(CorrOut) * (size_t)n_i, 256);
+    if (bytes > E.cap_corr) {
+        if (E.h_corr) CU(cudaFreeHost(E.h_corr));
+        if (E.d_corr) CU(cudaFree(E.d_corr));
+        E.h_corr = nullptr; E.d_corr = nullptr; E.cap_corr = 0;
+        const size_t cap = bytes + bytes / 8;
+        CU(cudaMallocHost(&E.h_corr, cap));
+        CU(cudaMalloc(&E.d_corr, cap));
+        E.cap_corr = cap;
+    }
+    CorrI* hi = (CorrI*)(E.h_corr + o_i);
+    CorrJ* hj = (CorrJ*)(E.h_corr + o_j);
+    const char* bi = (const char*)ptcl_i;
+    const char* bj = (const char*)ptcl_j;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n_i; i++) {
+        const char* p = bi + (size_t)i * li->stride;
+        CorrI I;
+        I.p = corr_load(p, *li);
+        I.ax = ld(p, li->off_acc, 0); I.ay = ld(p, li->off_acc, 1); I.az = ld(p, li->off_acc, 2);
+        I.pot_tot = ld(p, li->off_pot_tot); I.pot_soft = ld(p, li->off_pot_soft);
+        hi[i] = I;
+    }
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < n_j; j++) hj[j] = corr_load(bj + (size_t)j * lj->stride, *lj);
+    memcpy(E.h_corr + o_off, nb_off, sizeof(int) * ((size_t)n_i + 1));
+    if (n_nb) memcpy(E.h_corr + o_idx, nb_idx, sizeof(int) * (size_t)n_nb);
+    E.prof.t_copy += now_s() - t0;
+
+    cudaStream_t st = E.slots[0].stream;
+    CU(cudaMemcpyAsync(E.d_corr, E.h_corr, o_out, cudaMemcpyHostToDevice, st));
+    CorrParams P;
+    P.eps2 = prm->eps2; P.r_out = prm->r_out; P.G = prm->G; P.status_no_cm = prm->status_no_cm; P.replay_fp32 = prm->replay_fp32 ? 1 : 0;
+    CU(launch_corr(st, n_i, (const CorrI*)(E.d_corr + o_i), (const CorrJ*)(E.d_corr + o_j), (const int*)(E.d_corr + o_off),
+                   (const int*)(E.d_corr + o_idx), (CorrOut*)(E.d_corr + o_out), P));
+    CU(cudaMemcpyAsync(E.h_corr + o_out, E.d_corr + o_out, sizeof(CorrOut) * (size_t)n_i, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    E.prof.n_kernel_launch += 1;
+    E.prof.h2d_bytes += (long long)o_out;
+    E.prof.d2h_bytes += (long long)(sizeof(CorrOut) * (size_t)n_i);
+
+    const double t1 = now_s();
+    const CorrOut* ho = (const CorrOut*)(E.h_corr + o_out);
+    char* wi = (char*)ptcl_i;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n_i; i++) {
+        char* p = wi + (size_t)i * li->stride;
+        memcpy(p + li->off_acc, &ho[i].ax, 24);
+        memcpy(p + li->off_pot_tot, &ho[i].pot_tot, 8);
+        memcpy(p + li->off_pot_soft, &ho[i].pot_soft, 8);
+    }
+    E.prof.t_copy += now_s() - t1;
     return PB_OK;
 }
 

@@ -19,7 +19,7 @@ import os
 
 import numpy as np
 
-from .types import EPISoft, EPJSoft, SPJQuad, ForceSoft
+from .types import EPISoft, EPJSoft, SPJQuad, ForceSoft, PtclCorr, LARGE_FLOAT
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBDIR = os.path.join(_HERE, "lib")
@@ -47,6 +47,15 @@ class LayoutSpj(C.Structure):
 
 class LayoutForce(C.Structure):
     _fields_ = [("stride", C.c_size_t), ("off_acc", C.c_size_t), ("off_pot", C.c_size_t), ("off_nngb", C.c_size_t)]
+
+
+class LayoutCorr(C.Structure):
+    _fields_ = [(k, C.c_size_t) for k in ("stride", "off_pos", "off_mass", "off_r_in", "off_r_out", "off_id", "off_mass_backup",
+                                          "off_status", "off_acc", "off_pot_tot", "off_pot_soft")]
+
+
+class CorrParams(C.Structure):
+    _fields_ = [("eps2", C.c_double), ("r_out", C.c_double), ("G", C.c_double), ("status_no_cm", C.c_double), ("replay_fp32", C.c_int)]
 
 
 class Profile(C.Structure):
@@ -77,6 +86,7 @@ ABI_SYMBOLS = [
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
     "pb_field_at_points", "pb_dispatch_count_index", "pb_tree_upload", "pb_tree_force", "pb_tree_lists",
+    "pb_correct_changeover",
 ]
 
 _lib = None
@@ -120,6 +130,7 @@ def load():
     L.pb_tree_upload.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double]
     L.pb_tree_force.argtypes = [_vp, C.POINTER(LayoutEpi), _vp, C.POINTER(LayoutForce)]
     L.pb_tree_lists.argtypes = [_vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong]
+    L.pb_correct_changeover.argtypes = [C.c_int, _vp, C.POINTER(LayoutCorr), C.c_int, _vp, C.POINTER(LayoutCorr), _vp, _vp, C.POINTER(CorrParams)]
     L.pb_field_at_points.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]
     _lib = L
     return L
@@ -269,6 +280,30 @@ def tree_lists(n_groups):
     check(L.pb_tree_lists(ne.ctypes.data, ns.ctypes.data, ide.ctypes.data if len(ide) else None, len(ide),
                           ids.ctypes.data if len(ids) else None, len(ids)), "pb_tree_lists")
     return ne, ns, ide, ids
+
+
+def layout_corr(dt, r_in="r_in", r_out="r_out", with_outputs=True):
+    """pb_layout_corr of a structured dtype that has pos, mass, <r_in>, <r_out>, id, mass_backup, status
+    (and acc, pot_tot, pot_soft on the i side)."""
+    f = dt.fields
+    out = [f[k][1] for k in ("acc", "pot_tot", "pot_soft")] if with_outputs else [0, 0, 0]
+    return LayoutCorr(dt.itemsize, f["pos"][1], f["mass"][1], f[r_in][1], f[r_out][1], f["id"][1], f["mass_backup"][1], f["status"][1], *out)
+
+
+def correct_force_with_cutoff_tree_neighbor(ptcl, nb_off, nb_idx, ptcl_j, eps, r_out, G, replay_fp32=False,
+                                            status_no_cm=-LARGE_FLOAT):
+    """The particle loop of ``SystemHard::correctForceWithCutoffTreeNeighborOMP`` (reference
+    src/hard.hpp:3366-3377, one particle: :1655-1691, one pair: :1408-1476) on the device: ``ptcl``
+    (structured array, e.g. types.PtclCorr) has acc / pot_tot / pot_soft corrected in place over the CSR
+    neighbour lists ``nb_idx[nb_off[i]:nb_off[i+1]]`` (indices into ``ptcl_j``)."""
+    nb_off = np.ascontiguousarray(nb_off, dtype=np.int32)
+    nb_idx = np.ascontiguousarray(nb_idx, dtype=np.int32)
+    assert len(nb_off) == len(ptcl) + 1 and ptcl.flags["C_CONTIGUOUS"] and ptcl_j.flags["C_CONTIGUOUS"]
+    li, lj = layout_corr(ptcl.dtype), layout_corr(ptcl_j.dtype, with_outputs=False)
+    prm = CorrParams(eps * eps, r_out, G, status_no_cm, int(bool(replay_fp32)))
+    check(load().pb_correct_changeover(len(ptcl), _ptr(ptcl), C.byref(li), len(ptcl_j), _ptr(ptcl_j), C.byref(lj),
+                                       _ptr(nb_off), _ptr(nb_idx), C.byref(prm)), "pb_correct_changeover")
+    return ptcl
 
 
 def get_gravity_and_potential_at_point(x, y, z, particles, G=1.0):

@@ -311,7 +311,7 @@ def kroupa_binary_particles(n_star, f_bin=0.1, seed=1):
     ptype = np.ones(len(mass_all), dtype=np.int32)
     ptype[11 * n_bin:14 * n_bin] = 0                     # orbit samples: artificial, not c.m., mass > 0
     return dict(pos=pos_all, mass=mass_all, vel=vel_all, rs=rs, r_in=r_in, r_out=r_out, ptype=ptype, prm=prm,
-                n_star=n_star, n_bin=n_bin)
+                n_star=n_star, n_bin=n_bin, m_members=(m1, m2))
 
 
 def kroupa_binary_case(n_star, f_bin=0.1, seed=1, theta=THETA, n_group_limit=N_GROUP_LIMIT, n_leaf_limit=N_LEAF_LIMIT):
@@ -320,3 +320,54 @@ def kroupa_binary_case(n_star, f_bin=0.1, seed=1, theta=THETA, n_group_limit=N_G
     batch, epi_src = build_walk_batch(P["pos"], P["mass"], P["rs"], vel=P["vel"], r_in=P["r_in"], r_out=P["r_out"], ptype=P["ptype"],
                                       theta=theta, n_group_limit=n_group_limit, n_leaf_limit=n_leaf_limit)
     return batch, epi_src, P["prm"], P
+
+
+# ---------------------------------------------------------------------------------------------
+# inputs of the changeover correction
+# ---------------------------------------------------------------------------------------------
+def corr_particles(P):
+    """types.PtclCorr array for the particle set of :func:`kroupa_binary_particles` (same order): members
+    carry status < 0 (minus the address of their c.m. particle) and their true mass as backup, the c.m.
+    particle status > 0 with the binary mass as backup, probes and orbit samples status > 0 without
+    backup, singles status = backup = 0 (reference src/artificial_particles.hpp:20-102)."""
+    from .types import PtclCorr
+    n, nb = len(P["mass"]), P["n_bin"]
+    p = np.zeros(n, dtype=PtclCorr)
+    p["id"] = np.arange(1, n + 1)
+    p["mass"], p["pos"], p["r_in"], p["r_out"] = P["mass"], P["pos"], P["r_in"], P["r_out"]
+    if nb:
+        m_star = P.get("m_members")
+        cm_adr = 10 * nb + np.arange(nb)
+        for half in (0, 1):
+            sl = slice(half * nb, (half + 1) * nb)
+            p["status"][sl] = -(cm_adr + 1.0)
+            p["mass_backup"][sl] = m_star[half] if m_star is not None else 1.0 / P["n_star"]
+        p["status"][2 * nb:10 * nb] = 1.0                    # tidal-tensor probes
+        p["status"][10 * nb:11 * nb] = 2.0                   # c.m.
+        p["mass_backup"][10 * nb:11 * nb] = 3.0 * P["mass"][11 * nb:12 * nb]
+        p["status"][11 * nb:14 * nb] = 3.0                   # orbit samples
+    return p
+
+
+def neighbor_lists(pos, rs):
+    """CSR neighbour lists with FDPS's symmetric search criterion |x_i - x_j| < max(rs_i, rs_j), the
+    particle itself included (as getNeighborListOneParticle returns it), ascending j.  scipy k-d tree."""
+    from scipy.spatial import cKDTree
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    rs = np.ascontiguousarray(rs, dtype=np.float64)
+    n = len(pos)
+    tree = cKDTree(pos)
+    hits = tree.query_ball_point(pos, rs, workers=-1, return_sorted=False)   # j within rs_i of i
+    cnt = np.fromiter((len(h) for h in hits), dtype=np.int64, count=n)
+    ii = np.repeat(np.arange(n, dtype=np.int64), cnt)
+    jj = np.fromiter((j for h in hits for j in h), dtype=np.int64, count=int(cnt.sum()))
+    d2 = ((pos[ii] - pos[jj]) ** 2).sum(axis=1)
+    keep = d2 < rs[ii] ** 2                                                  # strict, as the search kernel tests
+    ii, jj = ii[keep], jj[keep]
+    key = np.unique(np.concatenate([ii * n + jj, jj * n + ii]))              # symmetrise: j sees i if i sees j
+    ii, jj = key // n, key % n
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(off, ii + 1, 1)
+    off = np.cumsum(off)
+    assert off[-1] < 2 ** 31
+    return off.astype(np.int32), jj.astype(np.int32)

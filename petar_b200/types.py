@@ -42,6 +42,15 @@ TreeGroup = np.dtype(
 )
 assert TreeCell.itemsize == 176 and TreeGroup.itemsize == 104
 
+# the fields of FPSoft / EPJSoft the changeover correction reads and updates (include/petar_b200_types.h: pb_PtclCorr)
+PtclCorr = np.dtype(
+    [("id", "<i8"), ("mass", "<f8"), ("pos", "<f8", (3,)), ("r_in", "<f8"), ("r_out", "<f8"),
+     ("mass_backup", "<f8"), ("status", "<f8"), ("acc", "<f8", (3,)), ("pot_tot", "<f8"), ("pot_soft", "<f8")],
+    align=True,
+)
+assert PtclCorr.itemsize == 112
+LARGE_FLOAT = float(np.finfo(np.float32).max) * 0.0625   # FDPS PS::LARGE_FLOAT
+
 assert EPISoft.itemsize == 48
 assert EPJSoft.itemsize == 120
 assert SPJQuad.itemsize == 80

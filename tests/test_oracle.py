@@ -214,3 +214,64 @@ def test_empty_lists():
     assert np.all(f["acc"] == 0) and f["pot"][0] == 0 and f["n_ngb"][0] == 0
     f = ob.force_epsp_quad(epi, np.zeros(0, dtype=SPJQuad), 0.0, 1.0)
     assert np.all(f["acc"] == 0)
+
+
+# ---- changeover correction: the restatement against the reference's own function ----------------
+needs_ref_co = pytest.mark.skipif(not ob.ref_changeover_available(), reason="oracle/_ref changeover libraries not built")
+
+
+@needs_ref_co
+def test_changeover_functions_bit_exact_vs_reference():
+    rng = np.random.default_rng(1)
+    for _ in range(5000):
+        r_in = 10 ** rng.uniform(-5, -2); r_out = r_in * rng.uniform(2, 20); dr = 10 ** rng.uniform(-6, -1)
+        assert ob.changeover_w(r_in, r_out, dr) == ob.ref_changeover_w(r_in, r_out, dr)
+    # the three regimes: inside r_in, the polynomial, beyond r_out
+    a0, p0 = ob.changeover_w(1e-3, 1e-2, 5e-4); a1, p1 = ob.changeover_w(1e-3, 1e-2, 2e-2)
+    assert a0 == 1.0 and p0 == 1.0 and a1 == 0.0 and p1 == (1.0 + 9.0 / 11.0) / 1e-2 * 2e-2
+
+
+@needs_ref_co
+@pytest.mark.parametrize("replay_fp32", [False, True])
+def test_changeover_pair_bit_exact_vs_reference(replay_fp32):
+    """oracle_changeover.c against calcAccPotShortWithLinearCutoff (reference src/hard.hpp:1408-1476) as
+    compiled in oracle/_ref from the reference sources, USE_GPU and P3T_64BIT branches."""
+    from petar_b200.types import PtclCorr
+    rng = np.random.default_rng(2)
+    r_out_g = 2e-3
+    for t in range(6000):
+        pi, pj = np.zeros(1, PtclCorr), np.zeros(1, PtclCorr)
+        pi["pos"] = rng.uniform(-1, 1, 3)
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        pj["pos"] = pi["pos"] + 10 ** rng.uniform(-5, -2) * d
+        for q in (pi, pj):
+            f = rng.uniform(1, 3)
+            q["mass"], q["r_in"], q["r_out"] = 10 ** rng.uniform(-7, -4), r_out_g / 10 * f, r_out_g * f
+        if t % 3 == 1:
+            pj["status"], pj["mass_backup"], pj["mass"] = -5.0, pj["mass"], 0.0
+        if t % 3 == 2:
+            pj["status"] = 3.0
+        pi["acc"], pi["pot_tot"], pi["pot_soft"] = rng.normal(size=3), rng.normal(), rng.normal()
+        a, b = pi.copy(), pi.copy()
+        eps = (0.0, 1e-4)[t % 2]
+        ob.changeover_pair(a, pj, eps, r_out_g, 0.7, replay_fp32)
+        ob.ref_changeover_pair(b, pj, eps, r_out_g, 0.7, replay_fp32)
+        assert a.tobytes() == b.tobytes()
+
+
+def test_changeover_neighbor_loop_matches_pairwise_application():
+    from petar_b200.types import PtclCorr, LARGE_FLOAT
+    from petar_b200 import harness
+    P = harness.kroupa_binary_particles(3000, f_bin=0.2)
+    p = harness.corr_particles(P)
+    off, idx = harness.neighbor_lists(P["pos"], P["rs"])
+    assert (p["status"] < 0).any() and (p["status"] > 0).any() and np.diff(off).max() > 3
+    out = ob.correct_force_tree_neighbor(p.copy(), off, idx, p, 0.0, P["prm"]["r_out"], 1.0, False)
+    for i in np.random.default_rng(0).choice(len(p), 200, replace=False):
+        q = p[i:i + 1].copy()
+        if q["status"][0] == 0.0 and q["mass_backup"][0] == 0.0:
+            q["pot_tot"] += q["mass"] / P["prm"]["r_out"]; q["pot_soft"] += q["mass"] / P["prm"]["r_out"]
+        for j in idx[off[i]:off[i + 1]]:
+            if p["id"][j] != q["id"][0]:
+                ob.changeover_pair(q, p[j:j + 1].copy(), 0.0, P["prm"]["r_out"], 1.0, False)
+        assert q.tobytes() == out[i:i + 1].tobytes()

@@ -22,7 +22,7 @@ def build_variant(name, defs):
     subprocess.run([B._nvcc(), *[f for f in B.NVCC_FLAGS if f not in ("-Xptxas", "-v")], *defs, "-I", B.INC, "-I", B.CSRC,
                     "-c", "-o", obj, os.path.join(B.CSRC, "pb_kernels.cu")], check=True)
     subprocess.run([B._nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xlinker", "-soname=libpetar_b200.so", "-o",
-                    os.path.join(d, "libpetar_b200.so"), obj, os.path.join(objdir, "pb_engine.o"), os.path.join(objdir, "pb_walk.o"), "-lgomp"], check=True)
+                    os.path.join(d, "libpetar_b200.so"), obj, os.path.join(objdir, "pb_engine.o"), os.path.join(objdir, "pb_walk.o"), os.path.join(objdir, "pb_corr.o"), "-lgomp"], check=True)
     print("built", d)
 
 
