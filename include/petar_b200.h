@@ -125,6 +125,8 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "lead"       the first of a dispatch's per-stream sub-batches is 1/(1+lead) the size of the others
  *                (the GPU idles until its copy lands): 0 = equal sizes, 1 (default), up to 15.
  *   "tree_batch" groups per force launch of pb_tree_force (default 1024).
+ *   "nb_lists"   1: pb_dispatch_count_index also collects the neighbour PAIRS (see pb_retrieve_neighbors);
+ *                0 (default): counts only.
  * Returns PB_ERR_ARG for an unknown key or value. */
 int  pb_set_option(const char* key, long long value);
 
@@ -255,6 +257,14 @@ int  pb_pack_epj_host(const void* epj, int n, const pb_layout_epj* l, void* out3
  * local particle array). */
 int  pb_pack_epj_host_indexed(const void* epj, const long long* idx, int n, const pb_layout_epj* l, void* out32);
 int  pb_pack_spj_host(const void* spj, int n, const pb_layout_spj* l, void* out64);
+
+/* Neighbour lists of the last retrieved pb_dispatch_count_index (option "nb_lists" = 1): what
+ * tree_nb.getNeighborListOneParticle would return for every i-particle of that dispatch (reference call
+ * sites src/hard.hpp:1663, src/search_cluster.hpp), the particle itself included.  CSR over the
+ * i-particles in dispatch order (walk 0's particles first): nb_off has sum(n_epi) + 1 entries, nb_idx holds
+ * indices into the epj array of pb_upload_j, ascending within each list.  Call with nb_idx = NULL to learn
+ * *n_pairs first.  Valid until the next count dispatch. */
+int  pb_retrieve_neighbors(long long* n_pairs, int* nb_off, int* nb_idx, long long cap);
 
 /* ---- changeover correction of the soft force ----------------------------------
  * Replaces the particle loop of SystemHard::correctForceWithCutoffTreeNeighborOMP (reference

@@ -68,6 +68,12 @@ struct Params {
     float eps2;
     float rcut2;
     int   abs_mode;       // 1: absolute-coordinate mode (no lo parts: dx = float(xj) - float(xi))
+    // neighbour-list emission (count-only launches with option "nb_lists"): every pair that passes the
+    // neighbour test appends the key (i_base + i index in the sub-batch) << 32 | j store index
+    int   i_base;
+    unsigned int pair_cap;
+    unsigned long long* pairs;
+    unsigned int* pair_cursor;
 };
 
 // Two-float position relative to the walk origin: hi + lo = (xh + xl) - (oh + ol) to ~2^-46,
@@ -89,7 +95,7 @@ cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_bloc
                          const Walk* walks, const Task* tasks,
                          const float4* epi, const int* id_epj, const int* id_spj,
                          const float4* epj, const float4* spj,
-                         double4* part4, int* partn, Params p);
+                         double4* part4, int* partn, Params p, bool emit_pairs = false);
 
 cudaError_t launch_reduce(cudaStream_t s, int n_iblocks, const IBlock* iblocks,
                           const double4* part4, const int* partn, ForceOut* out, double G);

@@ -13,6 +13,7 @@
 //   * every CUDA return code is checked; errors surface through pb_last_error().
 #include "petar_b200.h"
 #include "pb_device.h"
+#include <cub/cub.cuh>
 
 #include <algorithm>
 #include <chrono>
@@ -82,6 +83,12 @@ struct Slot {
     Plan plan;
     int  w_begin = 0, w_end = 0;
     bool active = false;
+    // neighbour-list emission (count-only dispatches with option "nb_lists")
+    unsigned long long* d_pairs = nullptr; unsigned long long* d_pairs_sorted = nullptr; unsigned long long* h_pairs = nullptr;
+    size_t cap_pairs = 0;
+    unsigned int* d_cursor = nullptr; unsigned int* h_cursor = nullptr;
+    void* d_cubtmp = nullptr; size_t cap_cubtmp = 0;
+    bool emit = false; int i_base = 0;
 };
 
 struct Recorded {
@@ -129,6 +136,9 @@ struct Engine {
     int2* h_counts_p = nullptr; size_t cap_counts_p = 0; int* h_over_p = nullptr;   // pinned landing zone of the count pass
     cudaEvent_t ev_count = nullptr; bool count_pending = false;
     int opt_tree_batch = 1024; int tree_last_batches = 0;
+    int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
+    std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
+    long long nb_n_i = 0;
 
     pb_profile prof;
 };
@@ -179,6 +189,25 @@ int grow_part(Slot& s, size_t n) {
     CU(cudaMalloc(&s.d_part4, cap * sizeof(double4)));
     CU(cudaMalloc(&s.d_partn, cap * sizeof(int)));
     s.cap_part = cap;
+    return PB_OK;
+}
+
+int grow_pairs(Slot& s, size_t n) {
+    if (!s.d_cursor) {
+        CU(cudaMalloc(&s.d_cursor, sizeof(unsigned int)));
+        CU(cudaMallocHost(&s.h_cursor, sizeof(unsigned int)));
+    }
+    if (n <= s.cap_pairs) return PB_OK;
+    const size_t cap = align_up(n + n / 2, 4096);
+    CU(cudaStreamSynchronize(s.stream));
+    if (s.d_pairs) CU(cudaFree(s.d_pairs));
+    if (s.d_pairs_sorted) CU(cudaFree(s.d_pairs_sorted));
+    if (s.h_pairs) CU(cudaFreeHost(s.h_pairs));
+    s.d_pairs = s.d_pairs_sorted = s.h_pairs = nullptr; s.cap_pairs = 0;
+    CU(cudaMalloc(&s.d_pairs, cap * sizeof(unsigned long long)));
+    CU(cudaMalloc(&s.d_pairs_sorted, cap * sizeof(unsigned long long)));
+    CU(cudaMallocHost(&s.h_pairs, cap * sizeof(unsigned long long)));
+    s.cap_pairs = cap;
     return PB_OK;
 }
 
@@ -479,11 +508,15 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
 }
 
 cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, bool direct,
-                        double4* part4, int* partn, ForceOut* out, bool force_only = false) {
+                        double4* part4, int* partn, ForceOut* out, bool force_only = false, const Slot* emit = nullptr) {
     Params prm;
     prm.eps2 = p.count_only ? 0.f : (float)E.eps2;        // SearchNeighborEpEpNoSimd tests r2 without eps
     prm.rcut2 = (float)E.rcut2;
     prm.abs_mode = E.opt_coords == 1 ? 1 : 0;
+    prm.i_base = emit ? emit->i_base : 0;
+    prm.pair_cap = emit ? (unsigned int)std::min<size_t>(emit->cap_pairs, 0xffffffffu) : 0u;
+    prm.pairs = emit ? emit->d_pairs : nullptr;
+    prm.pair_cursor = emit ? emit->d_cursor : nullptr;
     const float4* epj = direct ? (const float4*)(d_arena + p.off_lepj) : E.d_epj;
     const float4* spj = direct ? (const float4*)(d_arena + p.off_lspj) : E.d_spj;
     cudaError_t e = launch_force(st, p.n_tasks, E.opt_nr, E.opt_occ,
@@ -491,9 +524,41 @@ cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, boo
                                  (const float4*)(d_arena + p.off_epi),
                                  p.ext_ide ? p.ext_ide : (const int*)(d_arena + p.off_ide),
                                  p.ext_ids ? p.ext_ids : (const int*)(d_arena + p.off_ids),
-                                 epj, spj, part4, partn, prm);
+                                 epj, spj, part4, partn, prm, emit != nullptr);
     if (e != cudaSuccess || force_only) return e;
     return launch_reduce(st, p.n_iblocks, (const IBlock*)(d_arena + p.off_iblocks), part4, partn, out, E.G);
+}
+
+// neighbour pairs of one finished sub-batch: rerun with a larger buffer if it overflowed, sort the keys on the
+// device (deterministic lists: ascending i, then ascending j), append them to the dispatch-wide host store
+int collect_pairs(Slot& S) {
+    unsigned int n = *S.h_cursor;
+    while ((size_t)n > S.cap_pairs) {
+        int rc = grow_pairs(S, (size_t)n + n / 4);
+        if (rc != PB_OK) return rc;
+        CU(cudaMemsetAsync(S.d_cursor, 0, sizeof(unsigned int), S.stream));
+        CU(launch_plan(S.stream, S.plan, S.d_arena, false, S.d_part4, S.d_partn, S.d_out, true, &S));
+        CU(cudaMemcpyAsync(S.h_cursor, S.d_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
+        CU(cudaStreamSynchronize(S.stream));
+        E.prof.n_kernel_launch += 1;
+        n = *S.h_cursor;
+    }
+    if (n == 0) return PB_OK;
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, S.d_pairs, S.d_pairs_sorted, (int)n, 0, 64, S.stream));
+    if (tmp > S.cap_cubtmp) {
+        if (S.d_cubtmp) CU(cudaFree(S.d_cubtmp));
+        S.d_cubtmp = nullptr; S.cap_cubtmp = 0;
+        CU(cudaMalloc(&S.d_cubtmp, tmp + tmp / 2));
+        S.cap_cubtmp = tmp + tmp / 2;
+    }
+    CU(cub::DeviceRadixSort::SortKeys(S.d_cubtmp, tmp, S.d_pairs, S.d_pairs_sorted, (int)n, 0, 64, S.stream));
+    CU(cudaMemcpyAsync(S.h_pairs, S.d_pairs_sorted, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, S.stream));
+    CU(cudaStreamSynchronize(S.stream));
+    E.prof.n_kernel_launch += 1;
+    E.prof.d2h_bytes += (long long)(sizeof(unsigned long long) * n);
+    E.nb_keys.insert(E.nb_keys.end(), S.h_pairs, S.h_pairs + n);
+    return PB_OK;
 }
 
 int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_epi& Li,
@@ -545,6 +610,8 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
     for (int s = 0; s < n_slots; s++)
         if (E.slots[s].active) { if (first_active < 0) first_active = s; last_active = s; }
     E.out_first_slot = first_active;
+    int i_base_next = 0;
+    if (E.count_only) { E.nb_keys.clear(); E.nb_n_i = 0; }
     for (int s = 0; s < n_slots; s++) {
         Slot& S = E.slots[s];
         if (!S.active) continue;
@@ -562,9 +629,17 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         CU(cudaEventRecord(S.ev[0], S.stream));
         CU(cudaMemcpyAsync(S.d_arena, S.h_arena, S.plan.bytes, cudaMemcpyHostToDevice, S.stream));
         CU(cudaEventRecord(S.ev[1], S.stream));
-        CU(launch_plan(S.stream, S.plan, S.d_arena, direct, S.d_part4, S.d_partn, S.d_out));
+        S.emit = E.count_only && E.opt_nb_lists;
+        if (S.emit) {
+            S.i_base = i_base_next;
+            if ((rc = grow_pairs(S, 12 * S.plan.n_i + 65536)) != PB_OK) return rc;
+            CU(cudaMemsetAsync(S.d_cursor, 0, sizeof(unsigned int), S.stream));
+        }
+        i_base_next += (int)S.plan.n_i;
+        CU(launch_plan(S.stream, S.plan, S.d_arena, direct, S.d_part4, S.d_partn, S.d_out, false, S.emit ? &S : nullptr));
         CU(cudaEventRecord(S.ev[2], S.stream));
         if (s == last_active) CU(cudaEventRecord(E.ev_end[E.end_cur], S.stream));
+        if (S.emit) CU(cudaMemcpyAsync(S.h_cursor, S.d_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
         CU(cudaMemcpyAsync(S.h_out, S.d_out, sizeof(ForceOut) * S.plan.n_i, cudaMemcpyDeviceToHost, S.stream));
         CU(cudaEventRecord(S.ev[3], S.stream));
         E.prof.h2d_bytes += (long long)S.plan.bytes;
@@ -650,6 +725,8 @@ void pb_finalize(void) {
         cudaFreeHost(S.h_arena); cudaFree(S.d_arena);
         cudaFreeHost(S.h_out); cudaFree(S.d_out);
         cudaFree(S.d_part4); cudaFree(S.d_partn);
+        cudaFree(S.d_pairs); cudaFree(S.d_pairs_sorted); cudaFreeHost(S.h_pairs);
+        cudaFree(S.d_cursor); cudaFreeHost(S.h_cursor); cudaFree(S.d_cubtmp);
         for (int k = 0; k < 4; k++) cudaEventDestroy(S.ev[k]);
         cudaStreamDestroy(S.stream);
         S = Slot();
@@ -686,6 +763,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "streams must be 1..%d", kMaxStreams); E.opt_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "jchunk"))  { if (v < 0 || v > (1 << 20)) return fail(PB_ERR_ARG, "jchunk out of range"); E.opt_jchunk = (int)v; return PB_OK; }
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
+    if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
     if (!strcmp(key, "lead"))    { if (v < 0 || v > 15) return fail(PB_ERR_ARG, "lead must be in [0, 15]"); E.opt_lead = (int)v; return PB_OK; }
     if (!strcmp(key, "occupancy")) { if (v < 2 || v > 3) return fail(PB_ERR_ARG, "occupancy must be 2 or 3"); E.opt_occ = (int)v; return PB_OK; }
@@ -882,6 +960,11 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
         }
         E.prof.t_copy += now_s() - t0;
         E.prof.t_unpack += now_s() - t0;
+        if (S.emit) {
+            int rc = collect_pairs(S);
+            if (rc != PB_OK) return rc;
+            E.nb_n_i += (long long)S.plan.n_i;
+        }
         S.active = false;
     }
     if (E.send_timed) {
@@ -902,6 +985,24 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
 }
 
 // ---- direct-sum field query ---------------------------------------------------
+int pb_retrieve_neighbors(long long* n_pairs, int* nb_off, int* nb_idx, long long cap) {
+    if (!E.inited) return fail(PB_ERR_PROTOCOL, "pb_retrieve_neighbors before any dispatch");
+    if (E.outstanding) return fail(PB_ERR_PROTOCOL, "pb_retrieve_neighbors while a dispatch is outstanding");
+    const long long n = (long long)E.nb_keys.size();
+    if (n_pairs) *n_pairs = n;
+    if (nb_off) {
+        for (long long i = 0; i <= E.nb_n_i; i++) nb_off[i] = 0;
+        for (long long k = 0; k < n; k++) nb_off[(E.nb_keys[k] >> 32) + 1]++;
+        for (long long i = 0; i < E.nb_n_i; i++) nb_off[i + 1] += nb_off[i];
+    }
+    if (nb_idx) {
+        if (cap < n) return fail(PB_ERR_ARG, "pb_retrieve_neighbors: %lld pairs do not fit in %lld entries", n, cap);
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < n; k++) nb_idx[k] = (int)(E.nb_keys[k] & 0xffffffffull);
+    }
+    return PB_OK;
+}
+
 int pb_field_at_points(const double* x, const double* y, const double* z, int n_points,
                        const void* ptcl, int n_ptcl, size_t stride, size_t off_pos, size_t off_mass,
                        double G, double* ax, double* ay, double* az, double* pot) {

@@ -194,9 +194,11 @@ __device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
 // Neighbour search only (the kernel behind PeTar's second tree, tree_nb —
 // SearchNeighborEpEpNoSimd, reference src/soft_force.hpp:11-34): n += (r2 < max(rs_i, rs_j)^2),
 // exact two-float dx.  Only called for near segments; far segments cannot hold a neighbour.
+template <bool EMIT>
 __device__ __forceinline__ void ep_count_pairs(const EpTile& t, int p0, int p1,
                                                float xi, float yi, float zi, float xil, float yil, float zil, float rsi2,
-                                               float eps2, float2& cf) {
+                                               float eps2, float2& cf,
+                                               const int* jid, unsigned int i_global, const Params& prm) {
     const float2 nxi = bc(-xi), nyi = bc(-yi), nzi = bc(-zi), e2 = bc(eps2);
     const float2 nxil = bc(-xil), nyil = bc(-yil), nzil = bc(-zil);
 #pragma unroll kPairUnroll
@@ -210,9 +212,16 @@ __device__ __forceinline__ void ep_count_pairs(const EpTile& t, int p0, int p1,
         float2 r2 = __ffma2_rn(dx, dx, e2);
         r2 = __ffma2_rn(dy, dy, r2);
         r2 = __ffma2_rn(dz, dz, r2);
-        const float2 f = make_float2((r2.x < fmaxf(C.x, rsi2)) ? 1.f : 0.f,
-                                     (r2.y < fmaxf(C.y, rsi2)) ? 1.f : 0.f);
-        cf = __fadd2_rn(cf, f);
+        const bool h0 = r2.x < fmaxf(C.x, rsi2), h1 = r2.y < fmaxf(C.y, rsi2);
+        cf = __fadd2_rn(cf, make_float2(h0 ? 1.f : 0.f, h1 ? 1.f : 0.f));
+        if (EMIT && (h0 || h1) && i_global != 0xffffffffu) {
+            // rare (well under 1 % of the tested pairs): one slot per hit from the launch-wide cursor
+            const unsigned int n = (unsigned int)h0 + (unsigned int)h1;
+            const unsigned int at = atomicAdd(prm.pair_cursor, n);
+            const unsigned long long hi = (unsigned long long)i_global << 32;
+            if (h0 && at < prm.pair_cap) prm.pairs[at] = hi | (unsigned int)jid[2 * p];
+            if (h1 && at + (unsigned int)h0 < prm.pair_cap) prm.pairs[at + (unsigned int)h0] = hi | (unsigned int)jid[2 * p + 1];
+        }
     }
 }
 
@@ -401,7 +410,7 @@ struct IdPipe {
 // ------------------------------------------------------------------------------------------
 // the force kernel
 // ------------------------------------------------------------------------------------------
-template <int NR, int MINB>
+template <int NR, int MINB, bool EMIT = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
              const float4* __restrict__ epi,
@@ -412,6 +421,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
     __shared__ Smem sm;
     __shared__ int near_flag[2][kWarpsPerCta];   // per tile buffer, per staging warp (= 16-pair segment)
     __shared__ IdRing ring;                      // index tiles, filled by TMA bulk copies
+    __shared__ int jid[EMIT ? 2 : 1][EMIT ? kTileJ : 1];   // store index of every staged j (neighbour-list emission only)
 
     const Task task = tasks[blockIdx.x];
     const Walk w    = walks[task.walk];
@@ -455,6 +465,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             const bool nr_ = ep_store(sm.ep[0], tid, id_cur, jr, w, prm.abs_mode);
             const unsigned bal = __ballot_sync(0xffffffffu, nr_);
             if (lane == 0) near_flag[0][warp] = (bal != 0u);
+            if (EMIT) jid[0][tid] = id_cur;
         }
         __syncthreads();
         for (int k = 0; k < n_tiles; ++k) {
@@ -471,7 +482,8 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                     const int e = min(seg + 16, p1);
                     if (count_only) {
                         if (near_flag[k & 1][seg >> 4])
-                            ep_count_pairs(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, cf);
+                            ep_count_pairs<EMIT>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, cf,
+                                                 jid[EMIT ? (k & 1) : 0], ivalid ? (unsigned int)(prm.i_base + w.i_off + i_loc) : 0xffffffffu, prm);
                     } else if (near_flag[k & 1][seg >> 4])
                         ep_pairs<NR, true>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
                     else
@@ -484,6 +496,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 const bool nr_ = ep_store(sm.ep[(k + 1) & 1], tid, id_nxt, jr, w, prm.abs_mode);
                 const unsigned bal = __ballot_sync(0xffffffffu, nr_);
                 if (lane == 0) near_flag[(k + 1) & 1][warp] = (bal != 0u);
+                if (EMIT) jid[(k + 1) & 1][tid] = id_nxt;
             }
             id_nxt = id_nn;
             __syncthreads();
@@ -555,12 +568,13 @@ cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_bloc
                          const Walk* walks, const Task* tasks,
                          const float4* epi, const int* id_epj, const int* id_spj,
                          const float4* epj, const float4* spj,
-                         double4* part4, int* partn, Params p)
+                         double4* part4, int* partn, Params p, bool emit_pairs)
 {
     if (n_tasks <= 0) return cudaSuccess;
-#define PB_LAUNCH(NR_, MB_) force_kernel<NR_, MB_><<<n_tasks, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p)
-    if (nr_steps >= 1) { if (min_blocks >= 3) PB_LAUNCH(1, 3); else PB_LAUNCH(1, 2); }
-    else               { if (min_blocks >= 3) PB_LAUNCH(0, 3); else PB_LAUNCH(0, 2); }
+#define PB_LAUNCH(...) force_kernel<__VA_ARGS__><<<n_tasks, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p)
+    if (emit_pairs)          PB_LAUNCH(0, 2, true);        // neighbour lists: count-only tasks, no rsqrt involved
+    else if (nr_steps >= 1) { if (min_blocks >= 3) PB_LAUNCH(1, 3); else PB_LAUNCH(1, 2); }
+    else                    { if (min_blocks >= 3) PB_LAUNCH(0, 3); else PB_LAUNCH(0, 2); }
 #undef PB_LAUNCH
     return cudaGetLastError();
 }

@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
     "pb_field_at_points", "pb_dispatch_count_index", "pb_tree_upload", "pb_tree_force", "pb_tree_lists",
-    "pb_correct_changeover",
+    "pb_correct_changeover", "pb_retrieve_neighbors",
 ]
 
 _lib = None
@@ -131,6 +131,7 @@ def load():
     L.pb_tree_force.argtypes = [_vp, C.POINTER(LayoutEpi), _vp, C.POINTER(LayoutForce)]
     L.pb_tree_lists.argtypes = [_vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong]
     L.pb_correct_changeover.argtypes = [C.c_int, _vp, C.POINTER(LayoutCorr), C.c_int, _vp, C.POINTER(LayoutCorr), _vp, _vp, C.POINTER(CorrParams)]
+    L.pb_retrieve_neighbors.argtypes = [C.POINTER(C.c_longlong), _vp, _vp, C.c_longlong]
     L.pb_field_at_points.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]
     _lib = L
     return L
@@ -235,23 +236,61 @@ class SearchNeighborCUDAMultiWalk:
                                         _ptr(epj), int(n_epj_tot), int(bool(send_flag)))
 
 
-def tree_neighbor_search(batch, n_walk_limit=200, force=None):
+def retrieve_neighbors(n_i):
+    """CSR neighbour lists (nb_off[n_i + 1], nb_idx) of the last retrieved count dispatch (option nb_lists)."""
+    L = load()
+    n = C.c_longlong(0)
+    off = np.zeros(n_i + 1, dtype=np.int32)
+    check(L.pb_retrieve_neighbors(C.byref(n), off.ctypes.data, None, 0), "pb_retrieve_neighbors")
+    idx = np.zeros(n.value, dtype=np.int32)
+    if n.value:
+        check(L.pb_retrieve_neighbors(C.byref(n), None, idx.ctypes.data, n.value), "pb_retrieve_neighbors")
+    return off, idx
+
+
+def tree_neighbor_search(batch, n_walk_limit=200, force=None, lists=False):
     """What ``PeTar::treeNeighborSearch`` (reference src/petar.hpp:767-788) would do with the extension
-    functor: count neighbours over every walk's EP list; only ``n_ngb`` of ``force`` is assigned."""
+    functor: count neighbours over every walk's EP list; only ``n_ngb`` of ``force`` is assigned.
+    lists=True also returns the neighbour lists themselves, (f, nb_off, nb_idx): CSR over the i-particles in
+    batch order, indices into batch.epj — what ``getNeighborListOneParticle`` returns particle by particle."""
     f = np.zeros(batch.n_epi_total, dtype=ForceSoft) if force is None else force
     none_u64, none_i32 = np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.int32)
     disp = SearchNeighborCUDAMultiWalk(0)
-    assert disp(0, 0, none_u64, none_i32, none_u64, none_i32, batch.epj, len(batch.epj), True) == 0
-    prev = None
-    for w0 in range(0, batch.n_walk, n_walk_limit):
-        t = batch.pointer_tables(f, slice(w0, min(w0 + n_walk_limit, batch.n_walk)))
+    if lists:
+        set_option("nb_lists", 1)
+    offs, idxs = [], []
+
+    def collect(t):
+        RetrieveForceCUDA(0, t.n_walk, t.n_epi, t.force_ptrs)
+        if lists:
+            o, i = retrieve_neighbors(int(t.n_epi.sum()))
+            offs.append(o); idxs.append(i)
+
+    try:
+        assert disp(0, 0, none_u64, none_i32, none_u64, none_i32, batch.epj, len(batch.epj), True) == 0
+        prev = None
+        for w0 in range(0, batch.n_walk, n_walk_limit):
+            t = batch.pointer_tables(f, slice(w0, min(w0 + n_walk_limit, batch.n_walk)))
+            if prev is not None:
+                collect(prev)
+            assert disp(0, t.n_walk, t.epi_ptrs, t.n_epi, t.id_epj_ptrs, t.n_epj, batch.epj, len(batch.epj), False) == 0
+            prev = t
         if prev is not None:
-            RetrieveForceCUDA(0, prev.n_walk, prev.n_epi, prev.force_ptrs)
-        assert disp(0, t.n_walk, t.epi_ptrs, t.n_epi, t.id_epj_ptrs, t.n_epj, batch.epj, len(batch.epj), False) == 0
-        prev = t
-    if prev is not None:
-        RetrieveForceCUDA(0, prev.n_walk, prev.n_epi, prev.force_ptrs)
-    return f
+            collect(prev)
+    finally:
+        if lists:
+            set_option("nb_lists", 0)
+    if not lists:
+        return f
+    nb_idx = np.concatenate(idxs) if idxs else np.zeros(0, dtype=np.int32)
+    nb_off = np.zeros(batch.n_epi_total + 1, dtype=np.int64)
+    k = 0
+    base = 0
+    for o in offs:
+        n = len(o) - 1
+        nb_off[k + 1:k + n + 1] = base + o[1:]
+        k += n; base += int(o[-1])
+    return f, nb_off.astype(np.int32), nb_idx
 
 
 def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, upload=True):
