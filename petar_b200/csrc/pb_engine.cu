@@ -208,7 +208,24 @@ int grow_pairs(Slot& s, size_t n) {
     CU(cudaMalloc(&s.d_pairs_sorted, cap * sizeof(unsigned long long)));
     CU(cudaMallocHost(&s.h_pairs, cap * sizeof(unsigned long long)));
     s.cap_pairs = cap;
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, s.d_pairs, s.d_pairs_sorted, (int)cap, 0, 64, s.stream));
+    if (tmp > s.cap_cubtmp) {
+        if (s.d_cubtmp) CU(cudaFree(s.d_cubtmp));
+        s.d_cubtmp = nullptr; s.cap_cubtmp = 0;
+        CU(cudaMalloc(&s.d_cubtmp, tmp));
+        s.cap_cubtmp = tmp;
+    }
     return PB_OK;
+}
+
+// sort the whole pair buffer of a sub-batch (unused entries are all-ones and stay at the end): queued behind the
+// kernel in dispatch, so no host round trip sits between the kernel and the sort
+cudaError_t sort_pairs(Slot& s, size_t n_i_dispatch) {
+    int bits = 1;
+    while (((size_t)1 << bits) <= n_i_dispatch + 1) bits++;
+    size_t tmp = s.cap_cubtmp;
+    return cub::DeviceRadixSort::SortKeys(s.d_cubtmp, tmp, s.d_pairs, s.d_pairs_sorted, (int)s.cap_pairs, 0, std::min(64, 32 + bits), s.stream);
 }
 
 int grow_jstore(size_t n_epj, size_t n_spj) {
@@ -529,34 +546,30 @@ cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, boo
     return launch_reduce(st, p.n_iblocks, (const IBlock*)(d_arena + p.off_iblocks), part4, partn, out, E.G);
 }
 
-// neighbour pairs of one finished sub-batch: rerun with a larger buffer if it overflowed, sort the keys on the
-// device (deterministic lists: ascending i, then ascending j), append them to the dispatch-wide host store
-int collect_pairs(Slot& S) {
+// neighbour pairs of one finished sub-batch (its keys were sorted on the device behind the kernel: ascending i,
+// then ascending j): start the copy of the n valid keys; rerun with a larger buffer first if it overflowed
+int collect_pairs_begin(Slot& S, size_t n_i_dispatch) {
     unsigned int n = *S.h_cursor;
     while ((size_t)n > S.cap_pairs) {
         int rc = grow_pairs(S, (size_t)n + n / 4);
         if (rc != PB_OK) return rc;
         CU(cudaMemsetAsync(S.d_cursor, 0, sizeof(unsigned int), S.stream));
+        CU(cudaMemsetAsync(S.d_pairs, 0xff, sizeof(unsigned long long) * S.cap_pairs, S.stream));
         CU(launch_plan(S.stream, S.plan, S.d_arena, false, S.d_part4, S.d_partn, S.d_out, true, &S));
+        CU(sort_pairs(S, n_i_dispatch));
         CU(cudaMemcpyAsync(S.h_cursor, S.d_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
         CU(cudaStreamSynchronize(S.stream));
-        E.prof.n_kernel_launch += 1;
+        E.prof.n_kernel_launch += 2;
         n = *S.h_cursor;
     }
-    if (n == 0) return PB_OK;
-    size_t tmp = 0;
-    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, S.d_pairs, S.d_pairs_sorted, (int)n, 0, 64, S.stream));
-    if (tmp > S.cap_cubtmp) {
-        if (S.d_cubtmp) CU(cudaFree(S.d_cubtmp));
-        S.d_cubtmp = nullptr; S.cap_cubtmp = 0;
-        CU(cudaMalloc(&S.d_cubtmp, tmp + tmp / 2));
-        S.cap_cubtmp = tmp + tmp / 2;
-    }
-    CU(cub::DeviceRadixSort::SortKeys(S.d_cubtmp, tmp, S.d_pairs, S.d_pairs_sorted, (int)n, 0, 64, S.stream));
-    CU(cudaMemcpyAsync(S.h_pairs, S.d_pairs_sorted, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, S.stream));
-    CU(cudaStreamSynchronize(S.stream));
-    E.prof.n_kernel_launch += 1;
+    if (n) CU(cudaMemcpyAsync(S.h_pairs, S.d_pairs_sorted, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, S.stream));
     E.prof.d2h_bytes += (long long)(sizeof(unsigned long long) * n);
+    return PB_OK;
+}
+int collect_pairs_end(Slot& S) {
+    const unsigned int n = *S.h_cursor;
+    if (n == 0) return PB_OK;
+    CU(cudaStreamSynchronize(S.stream));
     E.nb_keys.insert(E.nb_keys.end(), S.h_pairs, S.h_pairs + n);
     return PB_OK;
 }
@@ -634,12 +647,17 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
             S.i_base = i_base_next;
             if ((rc = grow_pairs(S, 12 * S.plan.n_i + 65536)) != PB_OK) return rc;
             CU(cudaMemsetAsync(S.d_cursor, 0, sizeof(unsigned int), S.stream));
+            CU(cudaMemsetAsync(S.d_pairs, 0xff, sizeof(unsigned long long) * S.cap_pairs, S.stream));
         }
         i_base_next += (int)S.plan.n_i;
         CU(launch_plan(S.stream, S.plan, S.d_arena, direct, S.d_part4, S.d_partn, S.d_out, false, S.emit ? &S : nullptr));
         CU(cudaEventRecord(S.ev[2], S.stream));
         if (s == last_active) CU(cudaEventRecord(E.ev_end[E.end_cur], S.stream));
-        if (S.emit) CU(cudaMemcpyAsync(S.h_cursor, S.d_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
+        if (S.emit) {
+            CU(sort_pairs(S, (size_t)n_i));
+            CU(cudaMemcpyAsync(S.h_cursor, S.d_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
+            E.prof.n_kernel_launch += 1;
+        }
         CU(cudaMemcpyAsync(S.h_out, S.d_out, sizeof(ForceOut) * S.plan.n_i, cudaMemcpyDeviceToHost, S.stream));
         CU(cudaEventRecord(S.ev[3], S.stream));
         E.prof.h2d_bytes += (long long)S.plan.bytes;
@@ -927,6 +945,8 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
     if (n_walk && (!ni || !force || !L)) return fail(PB_ERR_ARG, "pb_retrieve: null argument");
     for (int w = 0; w < n_walk; w++)
         if (ni[w] != E.out_ni[w]) return fail(PB_ERR_ARG, "pb_retrieve: ni[%d]=%d != dispatched %d", w, ni[w], E.out_ni[w]);
+    size_t n_i_dispatch = 0;
+    for (int w = 0; w < n_walk; w++) n_i_dispatch += (size_t)ni[w];
     const bool plain = !E.out_count_only && L && L->stride == sizeof(ForceOut) && L->off_acc == 0 && L->off_pot == 24 && L->off_nngb == 32;
     for (int s = 0; s < E.out_n_slots; s++) {
         Slot& S = E.slots[s];
@@ -936,6 +956,10 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
         CU(cudaEventElapsedTime(&ms, S.ev[0], S.ev[1])); E.prof.t_send += 1e-3 * ms;
         CU(cudaEventElapsedTime(&ms, S.ev[1], S.ev[2])); E.prof.t_calc += 1e-3 * ms;
         CU(cudaEventElapsedTime(&ms, S.ev[2], S.ev[3])); E.prof.t_recv += 1e-3 * ms;
+        if (S.emit) {                                     // the sorted pairs travel while the counts are scattered
+            int rc = collect_pairs_begin(S, n_i_dispatch);
+            if (rc != PB_OK) return rc;
+        }
         const double t0 = now_s();
         const int nw = S.w_end - S.w_begin;
         std::vector<size_t> first(nw + 1, 0);
@@ -961,7 +985,7 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
         E.prof.t_copy += now_s() - t0;
         E.prof.t_unpack += now_s() - t0;
         if (S.emit) {
-            int rc = collect_pairs(S);
+            int rc = collect_pairs_end(S);
             if (rc != PB_OK) return rc;
             E.nb_n_i += (long long)S.plan.n_i;
         }
@@ -991,9 +1015,11 @@ int pb_retrieve_neighbors(long long* n_pairs, int* nb_off, int* nb_idx, long lon
     const long long n = (long long)E.nb_keys.size();
     if (n_pairs) *n_pairs = n;
     if (nb_off) {
-        for (long long i = 0; i <= E.nb_n_i; i++) nb_off[i] = 0;
-        for (long long k = 0; k < n; k++) nb_off[(E.nb_keys[k] >> 32) + 1]++;
-        for (long long i = 0; i < E.nb_n_i; i++) nb_off[i + 1] += nb_off[i];
+        // keys are sorted by i: list i ends where the first key of a larger i starts
+        const unsigned long long* k0 = E.nb_keys.data();
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i <= E.nb_n_i; i++)
+            nb_off[i] = (int)(std::lower_bound(k0, k0 + n, (unsigned long long)i << 32) - k0);
     }
     if (nb_idx) {
         if (cap < n) return fail(PB_ERR_ARG, "pb_retrieve_neighbors: %lld pairs do not fit in %lld entries", n, cap);

@@ -248,7 +248,7 @@ def retrieve_neighbors(n_i):
     return off, idx
 
 
-def tree_neighbor_search(batch, n_walk_limit=200, force=None, lists=False):
+def tree_neighbor_search(batch, n_walk_limit=200, force=None, lists=False, tables=None):
     """What ``PeTar::treeNeighborSearch`` (reference src/petar.hpp:767-788) would do with the extension
     functor: count neighbours over every walk's EP list; only ``n_ngb`` of ``force`` is assigned.
     lists=True also returns the neighbour lists themselves, (f, nb_off, nb_idx): CSR over the i-particles in
@@ -269,8 +269,9 @@ def tree_neighbor_search(batch, n_walk_limit=200, force=None, lists=False):
     try:
         assert disp(0, 0, none_u64, none_i32, none_u64, none_i32, batch.epj, len(batch.epj), True) == 0
         prev = None
-        for w0 in range(0, batch.n_walk, n_walk_limit):
-            t = batch.pointer_tables(f, slice(w0, min(w0 + n_walk_limit, batch.n_walk)))
+        if tables is None:                               # FDPS holds these ready; pass make_dispatch_tables(batch, force) to reuse them
+            tables = (batch.pointer_tables(f, slice(w0, min(w0 + n_walk_limit, batch.n_walk))) for w0 in range(0, batch.n_walk, n_walk_limit))
+        for t in tables:
             if prev is not None:
                 collect(prev)
             assert disp(0, t.n_walk, t.epi_ptrs, t.n_epi, t.id_epj_ptrs, t.n_epj, batch.epj, len(batch.epj), False) == 0
