@@ -403,6 +403,11 @@ def main():
                          "flop_convention": "38 per EP-EP, 65 per EP-SP interaction (north star)",
                          "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz={f_mhz:.0f} from {peak_src} (non-tensor FP32; "
                                         "MEASURED_PEAKS has no FP32-pipe figure)",
+                         # the two rooflines the contract names, for the record: neither binds this kernel
+                         "hbm": {"algorithmic_bytes_per_step": h2d, "achieved": h2d / (ms_force * 1e-3) / 1e9,
+                                 "peak": float(peaks.get("hbm_gbs", 6536.4)) * world, "unit": "GB/s",
+                                 "frac": h2d / (ms_force * 1e-3) / 1e9 / (float(peaks.get("hbm_gbs", 6536.4)) * world),
+                                 "note": "every byte the step's kernels must read once (tables, i-particles, index lists, j store = the H2D bytes)"},
                          "note": "bound is the non-tensor FP32/issue pipe, not HBM or tensor: ~300-500 flop per HBM byte"},
             "clocks": clocks,
         }
