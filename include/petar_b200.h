@@ -125,6 +125,8 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "lead"       the first of a dispatch's per-stream sub-batches is 1/(1+lead) the size of the others
  *                (the GPU idles until its copy lands): 0 = equal sizes, 1 (default), up to 15.
  *   "tree_batch" groups per force launch of pb_tree_force (default 1024).
+ *   "tree_fill"  pb_tree_force writes the lists with 0 (default): one step-wide launch, 1: one launch per batch on
+ *                the batch's stream (measured: no gain, the force kernels own the SMs).
  *   "nb_lists"   1: pb_dispatch_count_index also collects the neighbour PAIRS (see pb_retrieve_neighbors);
  *                0 (default): counts only.
  * Returns PB_ERR_ARG for an unknown key or value. */

@@ -136,6 +136,7 @@ struct Engine {
     int2* h_counts_p = nullptr; size_t cap_counts_p = 0; int* h_over_p = nullptr;   // pinned landing zone of the count pass
     cudaEvent_t ev_count = nullptr; bool count_pending = false;
     int opt_tree_batch = 1024; int tree_last_batches = 0;
+    int opt_tree_fill = 0;                                 // pb_tree_force: 0 one step-wide list-fill launch, 1 one per batch on the batch's stream
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
     long long nb_n_i = 0;
@@ -781,6 +782,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "streams must be 1..%d", kMaxStreams); E.opt_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "jchunk"))  { if (v < 0 || v > (1 << 20)) return fail(PB_ERR_ARG, "jchunk out of range"); E.opt_jchunk = (int)v; return PB_OK; }
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
+    if (!strcmp(key, "tree_fill")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_fill must be 0 or 1"); E.opt_tree_fill = (int)v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
     if (!strcmp(key, "lead"))    { if (v < 0 || v > 15) return fail(PB_ERR_ARG, "lead must be in [0, 15]"); E.opt_lead = (int)v; return PB_OK; }
@@ -1328,10 +1330,15 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
     if (tot_s > E.cap_tree_ids) { if (E.d_tree_ids) CU(cudaFree(E.d_tree_ids)); E.cap_tree_ids = tot_s + tot_s / 8 + 4096; CU(cudaMalloc(&E.d_tree_ids, sizeof(int) * E.cap_tree_ids)); }
     if (!E.d_tree_off) CU(cudaMalloc(&E.d_tree_off, sizeof(int2) * E.cap_counts));   // freed whenever d_counts is re-sized
     CU(cudaMemcpyAsync(E.d_tree_off, E.h_tree_off.data(), sizeof(int2) * (size_t)E.n_groups, cudaMemcpyHostToDevice, s0));
-    CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, E.n_groups, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
-                        E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow));
-    CU(cudaEventRecord(E.ev_fill, s0));
-    E.prof.n_kernel_launch += 1;
+    const bool split_fill = E.opt_tree_fill == 1;          // fill each batch's lists on the batch's own stream, just ahead of its force launch
+    if (!split_fill) {
+        CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, E.n_groups, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
+                            E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow));
+        E.prof.n_kernel_launch += 1;
+    } else {
+        for (int s = 0; s < n_slots; s++) if ((rc = ensure_walk_scratch(s)) != PB_OK) return rc;
+    }
+    CU(cudaEventRecord(E.ev_fill, s0));                    // offsets (and, unless split, the lists) are in place
     // pass 3: per batch of groups — plan tasks from the counts, force, reduce
     const char* ebase = (const char*)epi;
     const double tp0 = now_s();
@@ -1375,6 +1382,11 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
         // only tables + i-particles cross PCIe; the index sections of the arena are filled in place
         const size_t h2d = S.plan.off_ide;
         CU(cudaStreamWaitEvent(S.stream, E.ev_fill, 0));
+        if (split_fill) {
+            CU(launch_walk_fill(S.stream, E.d_cells, E.d_groups, g0, nb, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
+                                E.d_walk_scratch[s], kWalkCap, std::min(kWalkCtas, (nb + 3) / 4), E.d_overflow));
+            E.prof.n_kernel_launch += 1;
+        }
         CU(cudaEventRecord(S.ev[0], S.stream));
         CU(cudaMemcpyAsync(S.d_arena, S.h_arena, h2d, cudaMemcpyHostToDevice, S.stream));
         CU(cudaEventRecord(S.ev[1], S.stream));
