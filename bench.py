@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work per step of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-device-walk", action="store_true", help="skip the informational device-side list building leg")
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--nr", type=int, default=0)
     ap.add_argument("--cull", type=int, default=1)
     ap.add_argument("--jchunk", type=int, default=0)

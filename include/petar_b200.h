@@ -115,7 +115,7 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *                1: absolute coordinates cast to fp32 — dx = float(xj) - float(xi), the exact
  *                   arithmetic the reference kernel and the CPU changeover correction replay use
  *                   (src/force_gpu_cuda.cu:58-60, src/hard.hpp:1346-1351).
- *   "streams"    number of CUDA streams one dispatch is split across (default 4, 1..8).
+ *   "streams"    number of CUDA streams one dispatch is split across (default 8, 1..8).
  *   "jchunk"     target EP j-chunk per warp-task (default 0 = automatic).
  *   "nr"         Newton-Raphson steps after MUFU.RSQ (0 default, or 1).
  *   "cull"       1 (default): skip the neighbour test for j-tile segments that cannot reach any
@@ -123,7 +123,7 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "occupancy"  resident CTAs per SM the force kernel is compiled for: 2 (default, 122 registers)
  *                or 3 (80 registers).
  *   "lead"       the first of a dispatch's per-stream sub-batches is 1/(1+lead) the size of the others
- *                (the GPU idles until its copy lands): 0 = equal sizes, 1 (default), up to 15.
+ *                (the GPU idles until its copy lands): 0 = equal sizes, 3 (default), up to 15.
  *   "tree_batch" groups per force launch of pb_tree_force (default 1024).
  *   "tree_fill"  pb_tree_force writes the lists with 0 (default): one step-wide launch, 1: one launch per batch on
  *                the batch's stream (measured: no gain, the force kernels own the SMs).

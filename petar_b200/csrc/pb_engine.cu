@@ -102,7 +102,7 @@ struct Engine {
     bool inited = false;
     int  rank = 0, device = 0;
     double eps2 = 0.0, rcut2 = 0.0, G = 1.0;
-    int opt_coords = 0, opt_streams = 4, opt_jchunk = 0, opt_nr = 0, opt_cull = 1, opt_occ = 2, opt_lead = 1;
+    int opt_coords = 0, opt_streams = 8, opt_jchunk = 0, opt_nr = 0, opt_cull = 1, opt_occ = 2, opt_lead = 3;
 
     // j store
     float4* d_epj = nullptr; size_t cap_epj = 0; int n_epj = 0;

@@ -30,7 +30,7 @@ def test_finalize_and_reinit_and_growth():
     f3 = engine.calc_force_all_and_write_back(small, prm_s["eps"], prm_s["r_out"], prm_s["G"])    # lazy re-init
     assert np.array_equal(f1["n_ngb"], f3["n_ngb"]) and np.allclose(f1["acc"], f3["acc"], rtol=1e-12, atol=0)
     _tol(f2["acc"], f2["pot"], ob.walks_index(big, prm_b["eps"], prm_b["r_out"], prm_b["G"]))
-    engine.set_option("streams", 4)
+    engine.set_option("streams", 8)
 
 
 def test_foreign_struct_layouts():

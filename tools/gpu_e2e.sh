@@ -1,19 +1,17 @@
 #!/bin/bash
-# e2e sweeps: sub-batch lead and stream count (the kernels-only value is unaffected)
+# e2e A/B on one box, interleaved repeats: sub-batch lead and stream count (the kernels-only value is unaffected)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out
 mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -x -q > $O/y_pytest.log 2>&1
-tail -3 $O/y_pytest.log
-B="timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-device-walk"
-$B > $O/y_s4_l1.log 2>&1
-$B --opt lead=3 > $O/y_s4_l3.log 2>&1
-$B --opt lead=7 > $O/y_s4_l7.log 2>&1
-$B --streams 6 --opt lead=3 > $O/y_s6_l3.log 2>&1
-$B --streams 8 --opt lead=3 > $O/y_s8_l3.log 2>&1
-$B --streams 8 --opt lead=7 > $O/y_s8_l7.log 2>&1
-$B --streams 3 --opt lead=3 > $O/y_s3_l3.log 2>&1
-for f in $O/y_s*.log; do python - "$f" <<'PY'
+nproc > $O/y_nproc.log
+B="timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-device-walk"
+for rep in 1 2 3; do
+  $B > $O/y_s4_l1_$rep.log 2>&1
+  $B --streams 8 --opt lead=3 > $O/y_s8_l3_$rep.log 2>&1
+  $B --streams 8 --opt lead=1 > $O/y_s8_l1_$rep.log 2>&1
+  $B --streams 6 --opt lead=2 > $O/y_s6_l2_$rep.log 2>&1
+done
+for f in $O/y_s*_[123].log; do python - "$f" <<'PY'
 import json,sys
 for line in open(sys.argv[1]):
     if line.startswith('{"metric"'):
