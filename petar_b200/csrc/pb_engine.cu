@@ -14,6 +14,8 @@
 #include "petar_b200.h"
 #include "pb_device.h"
 #include <cub/cub.cuh>
+#include <atomic>
+#include <emmintrin.h>
 
 #include <algorithm>
 #include <chrono>
@@ -446,73 +448,74 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     p.bytes = o;
 }
 
-// fill the pinned arena of one sub-batch
-void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
-                const pb_layout_epj* Lj, const pb_layout_spj* Ls, HostPlan& hp, char* arena) {
+// one walk of a sub-batch into its pinned arena: i-particles relative to the walk origin, index lists
+void pack_walk(const WalkIn* win, bool direct, const pb_layout_epi& Li, HostPlan& hp, char* arena, int w) {
     const Plan& p = hp.p;
     float4* epi = (float4*)(arena + p.off_epi);
     int* ide = (int*)(arena + p.off_ide);
     int* ids = (int*)(arena + p.off_ids);
-    float4* lepj = (float4*)(arena + p.off_lepj);
-    float4* lspj = (float4*)(arena + p.off_lspj);
     const bool rel = (E.opt_coords == 0);
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int w = 0; w < p.n_walk; w++) {
-        Walk& W = hp.walks[w];
-        const char* base = (const char*)win[w].epi;
-        // Walk origin = mean position of the i-particles (robust against outliers, unlike the box
-        // centre), as a hi/lo fp32 pair.  i and j positions are shifted to it by the SAME fp32
-        // operation sequence — (x_hi - o_hi) + (x_lo - o_lo) — here for i, in the kernel for j, so
-        // that a particle meeting itself (or an exact copy) gives dx == 0 exactly, as in the
-        // reference kernel; absolute mode is the same code with a zero origin (then x_rel == x_hi).
-        float oh[3] = {0.f, 0.f, 0.f}, ol[3] = {0.f, 0.f, 0.f};
-        if (rel && W.ni > 0) {
-            double sum[3] = {0.0, 0.0, 0.0};
-            for (int i = 0; i < W.ni; i++) {
-                const char* q = base + (size_t)i * Li.stride;
-                for (int k = 0; k < 3; k++) sum[k] += ld(q, Li.off_pos, k);
-            }
-            for (int k = 0; k < 3; k++) split(sum[k] / W.ni, oh[k], ol[k]);
-        }
-        W.ohx = oh[0]; W.ohy = oh[1]; W.ohz = oh[2];
-        W.olx = ol[0]; W.oly = ol[1]; W.olz = ol[2];
-        float4* e = epi + 2 * (size_t)W.i_off;           // two float4 per i: {x,y,z,rs}, {xl,yl,zl,0}
-        float hmax[3] = {0.f, 0.f, 0.f}, rsmax = 0.f;
+    Walk& W = hp.walks[w];
+    const char* base = (const char*)win[w].epi;
+    // Walk origin = mean position of the i-particles (robust against outliers, unlike the box
+    // centre), as a hi/lo fp32 pair.  i and j positions are shifted to it by the SAME fp32
+    // operation sequence — (x_hi - o_hi) + (x_lo - o_lo) — here for i, in the kernel for j, so
+    // that a particle meeting itself (or an exact copy) gives dx == 0 exactly, as in the
+    // reference kernel; absolute mode is the same code with a zero origin (then x_rel == x_hi).
+    float oh[3] = {0.f, 0.f, 0.f}, ol[3] = {0.f, 0.f, 0.f};
+    if (rel && W.ni > 0) {
+        double sum[3] = {0.0, 0.0, 0.0};
         for (int i = 0; i < W.ni; i++) {
             const char* q = base + (size_t)i * Li.stride;
-            float r[3], rl[3];
-            for (int k = 0; k < 3; k++) {
-                float xh, xl;
-                split(ld(q, Li.off_pos, k), xh, xl);
-                rel_hilo(xh, xl, oh[k], ol[k], r[k], rl[k]);
-                if (!rel) rl[k] = 0.f;
-            }
-            const float4 v = make_float4(r[0], r[1], r[2], (float)ld(q, Li.off_rsearch));
-            e[2 * i] = v;
-            e[2 * i + 1] = make_float4(rl[0], rl[1], rl[2], 0.f);
-            hmax[0] = std::max(hmax[0], std::fabs(v.x)); hmax[1] = std::max(hmax[1], std::fabs(v.y));
-            hmax[2] = std::max(hmax[2], std::fabs(v.z)); rsmax = std::max(rsmax, v.w);
+            for (int k = 0; k < 3; k++) sum[k] += ld(q, Li.off_pos, k);
         }
-        // bounding box of the packed fp32 i-positions about the origin: lets the kernel skip the
-        // neighbour test for j segments that are provably out of reach of every i of the walk
-        if (rel && E.opt_cull) { W.hx = hmax[0]; W.hy = hmax[1]; W.hz = hmax[2]; }
-        else                   { W.hx = W.hy = W.hz = INFINITY; }
-        // "near" radius: max r_search of the i-particles, and at least kPrecFactor ulps of the box
-        // half-size — inside it a single-float relative coordinate is not accurate enough against
-        // the pair separation, so those segments take the exact-dx loop
-        const float hbox = std::max(hmax[0], std::max(hmax[1], hmax[2]));
-        const float rprec = rel ? 4.0e4f * (std::nextafter(hbox, INFINITY) - hbox) : 0.f;
-        const float rnear = std::max(rsmax, rprec);
-        W.rsi2max = rnear * rnear;
-        if (!direct) {
-            if (W.nej && W.ej_off >= 0 && win[w].ide != &g_devlist_marker) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
-            if (W.nsj && win[w].ids != &g_devlist_marker) memcpy(ids + W.sj_off, win[w].ids, sizeof(int) * (size_t)W.nsj);
-        } else {
-            const size_t e0 = hp.lepj_off[w], s0 = hp.lspj_off[w];
-            for (int j = 0; j < W.nej; j++) ide[W.ej_off + j] = (int)(e0 + j);
-            for (int j = 0; j < W.nsj; j++) ids[W.sj_off + j] = (int)(s0 + j);
-        }
+        for (int k = 0; k < 3; k++) split(sum[k] / W.ni, oh[k], ol[k]);
     }
+    W.ohx = oh[0]; W.ohy = oh[1]; W.ohz = oh[2];
+    W.olx = ol[0]; W.oly = ol[1]; W.olz = ol[2];
+    float4* e = epi + 2 * (size_t)W.i_off;           // two float4 per i: {x,y,z,rs}, {xl,yl,zl,0}
+    float hmax[3] = {0.f, 0.f, 0.f}, rsmax = 0.f;
+    for (int i = 0; i < W.ni; i++) {
+        const char* q = base + (size_t)i * Li.stride;
+        float r[3], rl[3];
+        for (int k = 0; k < 3; k++) {
+            float xh, xl;
+            split(ld(q, Li.off_pos, k), xh, xl);
+            rel_hilo(xh, xl, oh[k], ol[k], r[k], rl[k]);
+            if (!rel) rl[k] = 0.f;
+        }
+        const float4 v = make_float4(r[0], r[1], r[2], (float)ld(q, Li.off_rsearch));
+        e[2 * i] = v;
+        e[2 * i + 1] = make_float4(rl[0], rl[1], rl[2], 0.f);
+        hmax[0] = std::max(hmax[0], std::fabs(v.x)); hmax[1] = std::max(hmax[1], std::fabs(v.y));
+        hmax[2] = std::max(hmax[2], std::fabs(v.z)); rsmax = std::max(rsmax, v.w);
+    }
+    // bounding box of the packed fp32 i-positions about the origin: lets the kernel skip the
+    // neighbour test for j segments that are provably out of reach of every i of the walk
+    if (rel && E.opt_cull) { W.hx = hmax[0]; W.hy = hmax[1]; W.hz = hmax[2]; }
+    else                   { W.hx = W.hy = W.hz = INFINITY; }
+    // "near" radius: max r_search of the i-particles, and at least kPrecFactor ulps of the box
+    // half-size — inside it a single-float relative coordinate is not accurate enough against
+    // the pair separation, so those segments take the exact-dx loop
+    const float hbox = std::max(hmax[0], std::max(hmax[1], hmax[2]));
+    const float rprec = rel ? 4.0e4f * (std::nextafter(hbox, INFINITY) - hbox) : 0.f;
+    const float rnear = std::max(rsmax, rprec);
+    W.rsi2max = rnear * rnear;
+    if (!direct) {
+        if (W.nej && W.ej_off >= 0 && win[w].ide != &g_devlist_marker) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
+        if (W.nsj && win[w].ids != &g_devlist_marker) memcpy(ids + W.sj_off, win[w].ids, sizeof(int) * (size_t)W.nsj);
+    } else {
+        const size_t e0 = hp.lepj_off[w], s0 = hp.lspj_off[w];
+        for (int j = 0; j < W.nej; j++) ide[W.ej_off + j] = (int)(e0 + j);
+        for (int j = 0; j < W.nsj; j++) ids[W.sj_off + j] = (int)(s0 + j);
+    }
+}
+
+// what follows once every walk of the sub-batch is packed: direct-mode j arrays, the tables
+void pack_tail(const WalkIn* win, bool direct, const pb_layout_epj* Lj, const pb_layout_spj* Ls, HostPlan& hp, char* arena) {
+    const Plan& p = hp.p;
+    float4* lepj = (float4*)(arena + p.off_lepj);
+    float4* lspj = (float4*)(arena + p.off_lspj);
     if (direct) {
         // per-walk j arrays -> dispatch-local j store (pack_* parallelise internally)
         for (int w = 0; w < p.n_walk; w++) {
@@ -523,6 +526,14 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
     memcpy(arena + p.off_walks, hp.walks.data(), sizeof(Walk) * hp.walks.size());
     memcpy(arena + p.off_tasks, hp.tasks.data(), sizeof(Task) * hp.tasks.size());
     memcpy(arena + p.off_iblocks, hp.iblocks.data(), sizeof(IBlock) * hp.iblocks.size());
+}
+
+// fill the pinned arena of one sub-batch
+void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
+                const pb_layout_epj* Lj, const pb_layout_spj* Ls, HostPlan& hp, char* arena) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int w = 0; w < hp.p.n_walk; w++) pack_walk(win, direct, Li, hp, arena, w);
+    pack_tail(win, direct, Lj, Ls, hp, arena);
 }
 
 cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, bool direct,
@@ -633,20 +644,22 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         if ((rc = grow_arena(S, hp[s].p.bytes)) != PB_OK) return rc;
         if ((rc = grow_out(S, hp[s].p.n_i)) != PB_OK) return rc;
         if ((rc = grow_part(S, hp[s].p.n_part)) != PB_OK) return rc;
-        const double tp2 = now_s();
-        pack_batch(win + S.w_begin, direct, Li, Lj, Ls, hp[s], S.h_arena);
-        S.plan = hp[s].p;
+        S.emit = E.count_only && E.opt_nb_lists;
+        if (S.emit && (rc = grow_pairs(S, 12 * hp[s].p.n_i + 65536)) != PB_OK) return rc;
+    }
+
+    // enqueue of one packed sub-batch: its whole input travels in one copy
+    double t_enq = 0.0;
+    auto enqueue_slot = [&](int s) -> int {
+        Slot& S = E.slots[s];
         const double t1 = now_s();
-        E.prof.t_pack += t1 - tp2;
-        // enqueue: the sub-batch's whole input travels in one copy
+        S.plan = hp[s].p;
         if (!direct) CU(cudaStreamWaitEvent(S.stream, E.ev_j_ready, 0));
         CU(cudaEventRecord(S.ev[0], S.stream));
         CU(cudaMemcpyAsync(S.d_arena, S.h_arena, S.plan.bytes, cudaMemcpyHostToDevice, S.stream));
         CU(cudaEventRecord(S.ev[1], S.stream));
-        S.emit = E.count_only && E.opt_nb_lists;
         if (S.emit) {
             S.i_base = i_base_next;
-            if ((rc = grow_pairs(S, 12 * S.plan.n_i + 65536)) != PB_OK) return rc;
             CU(cudaMemsetAsync(S.d_cursor, 0, sizeof(unsigned int), S.stream));
             CU(cudaMemsetAsync(S.d_pairs, 0xff, sizeof(unsigned long long) * S.cap_pairs, S.stream));
         }
@@ -664,12 +677,6 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         E.prof.h2d_bytes += (long long)S.plan.bytes;
         E.prof.d2h_bytes += (long long)(sizeof(ForceOut) * S.plan.n_i);
         E.prof.n_kernel_launch += (S.plan.n_tasks > 0) + (S.plan.n_iblocks > 0);
-        {
-            const double te = now_s() - t1;   // enqueue time is not packing time
-            E.prof.t_copy -= te;
-            E.prof.t_enqueue += te;
-        }
-
         if (E.recording) {
             Recorded r;
             r.plan = S.plan; r.direct = direct; r.slot = s;
@@ -677,6 +684,67 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
             CU(cudaMemcpyAsync(r.d_arena, S.d_arena, S.plan.bytes, cudaMemcpyDeviceToDevice, S.stream));
             E.recs.push_back(r);
         }
+        t_enq += now_s() - t1;
+        return PB_OK;
+    };
+
+    const double tp2 = now_s();
+    int rc_enq = PB_OK;
+    if (direct || omp_get_max_threads() < 2) {
+        // pack and enqueue the sub-batches in turn (the direct mode's j packing parallelises internally)
+        for (int s = 0; s < n_slots && rc_enq == PB_OK; s++) {
+            Slot& S = E.slots[s];
+            if (!S.active) continue;
+            pack_batch(win + S.w_begin, direct, Li, Lj, Ls, hp[s], S.h_arena);
+            rc_enq = enqueue_slot(s);
+        }
+    } else {
+        // ONE parallel region per dispatch: walks are handed out in order, so the sub-batches complete in order;
+        // the calling thread enqueues a sub-batch (copy + kernels) as soon as its last walk is packed and packs
+        // walks itself in between, so that enqueueing overlaps the other threads' packing
+        std::atomic<int> next_walk{0};
+        std::atomic<int> done[kMaxStreams];
+        int slot_of_walk_begin[kMaxStreams + 1];
+        for (int s = 0; s < n_slots; s++) { done[s].store(0); slot_of_walk_begin[s] = cut[s]; }
+        slot_of_walk_begin[n_slots] = n_walk;
+        auto pack_one = [&]() -> bool {
+            const int w = next_walk.fetch_add(1, std::memory_order_relaxed);
+            if (w >= n_walk) return false;
+            int s = 0;
+            while (w >= slot_of_walk_begin[s + 1]) s++;
+            Slot& S = E.slots[s];
+            pack_walk(win + S.w_begin, direct, Li, hp[s], S.h_arena, w - S.w_begin);
+            done[s].fetch_add(1, std::memory_order_release);
+            return true;
+        };
+#pragma omp parallel
+        {
+            if (omp_get_thread_num() == 0) {
+                int s = 0;
+                while (s < n_slots) {
+                    Slot& S = E.slots[s];
+                    if (!S.active) { s++; continue; }
+                    if (done[s].load(std::memory_order_acquire) == S.w_end - S.w_begin) {
+                        if (rc_enq == PB_OK) {
+                            pack_tail(win + S.w_begin, direct, Lj, Ls, hp[s], S.h_arena);
+                            rc_enq = enqueue_slot(s);
+                        }
+                        s++;
+                    } else if (!pack_one()) {
+                        _mm_pause();
+                    }
+                }
+            } else {
+                while (pack_one()) {}
+            }
+        }
+    }
+    if (rc_enq != PB_OK) return rc_enq;
+    {
+        const double tt = now_s() - tp2;
+        E.prof.t_pack += tt - t_enq;
+        E.prof.t_enqueue += t_enq;
+        E.prof.t_copy -= t_enq;              // enqueue time is not packing time
     }
     for (int s = n_slots; s < kMaxStreams; s++) E.slots[s].active = false;
 
