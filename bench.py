@@ -65,7 +65,11 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  Started before the warm-up (the
+    tool needs a few hundred ms to deliver its first sample) at 20 ms intervals; every sample carries the host
+    time it arrived at, and only those inside [t_begin, t_end] of the timed region are used.  A timed region
+    too short to catch 3 samples (multi-GPU runs last tens of ms) falls back to the samples of warm-up + timed
+    region together — the same kernels, back to back — and says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -76,8 +80,8 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -85,9 +89,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,20 +99,31 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except (ValueError, IndexError):
-                continue
-        # under load = samples in the upper half of the observed clock range
-        load = [s for s in sm if s >= 0.5 * max(sm)] if sm else []
-        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+        def stats(rows):
+            sm, mx, reasons, power = [], [], set(), []
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                    for k, nm in enumerate(names):
+                        if r[5 + k].lower().startswith("active"):
+                            reasons.add(nm)
+                except (ValueError, IndexError):
+                    continue
+            # under load = samples in the upper half of the observed clock range
+            load = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+            return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                    "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+        inside = [x for x in self.rows if t_begin is None or (t_begin <= x[0] <= (t_end or 1e300))]
+        out = stats(inside)
+        out["window"] = "timed region"
+        if out["samples"] < 3:
+            out = stats(self.rows)
+            out["window"] = ("warm-up + timed region (the timed region, %.0f ms, is shorter than 3 sampling intervals)"
+                             % (1e3 * ((t_end or 0) - (t_begin or 0))))
+        return out
 
 
 def build_workload(n, rank, world, args):
@@ -308,18 +323,19 @@ def main():
     engine.check(L.pb_record_end(), "pb_record_end")
     launches_per_step = L.pb_replay_launches()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
     # ---- warm-up ----
     ms_t, ms_f = C.c_float(0), C.c_float(0)
     for _ in range(args.warmup):
         engine.check(L.pb_replay(1, C.byref(ms_t), C.byref(ms_f)), "pb_replay")
         e2e_step()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-
     # ---- timed: K steps, device resident ----
     barrier()
+    t_timed_begin = time.time()
     engine.check(L.pb_replay(args.steps, C.byref(ms_t), C.byref(ms_f)), "pb_replay")
     barrier()
     ms_step, ms_force = float(ms_t.value), float(ms_f.value)
@@ -332,7 +348,18 @@ def main():
         e2e_step()
     barrier()
     sec_e2e = (time.perf_counter() - t0) / args.steps
+    t_timed_end = time.time()
     prof = engine.get_profile()
+    clock_probe_s = 0.0
+    if t_timed_end - t_timed_begin < 0.5:
+        # too short for nvidia-smi to sample (multi-GPU runs): keep the same recorded steps running, untimed,
+        # for one more second so that the clocks are read under the very same load
+        tp = time.time()
+        pm, pf = C.c_float(0), C.c_float(0)
+        while time.time() - tp < 1.0:
+            engine.check(L.pb_replay(1, C.byref(pm), C.byref(pf)), "pb_replay")
+        clock_probe_s = time.time() - tp
+        t_timed_end = time.time()
 
     # ---- informational: the same step with the interaction lists built on the GPU from the tree
     # (not the drop-in path — FDPS would have to hand over its tree) ----
@@ -357,7 +384,9 @@ def main():
                                    "host_walk_ms = the harness's OpenMP walk that produced the lists the e2e leg is given for free"}
         except Exception as ex:  # noqa: BLE001
             device_walk = {"unavailable": repr(ex)}
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_timed_begin, t_timed_end) if rank == 0 else None
+    if clocks is not None and clock_probe_s > 0:
+        clocks["window"] += " + %.1f s of the same recorded steps replayed right after it (untimed)" % clock_probe_s
 
     # ---- max over ranks, totals over ranks ----
     vals = torch.tensor([ms_step, ms_force, sec_e2e], dtype=torch.float64, device="cuda")
