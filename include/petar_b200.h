@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 2
+#define PB_ABI_VERSION 3
 
 typedef enum pb_status {
     PB_OK = 0,
@@ -183,17 +183,22 @@ int  pb_field_at_points(const double* x, const double* y, const double* z, int n
  *                    or group search box touches cell particle box, or vice versa,
  * evaluated in fp64 without FMA contraction (decisions identical to the host walk), then runs the
  * same force kernels on the lists without them ever crossing PCIe.
- * Requirements: pb_upload_j published the j of this step with EP store order == the tree's sorted
- * particle order and SP store slot c == multipole of cell c (single domain; LET superparticles
- * inside leaves are not supported yet). */
+ * Requirements: pb_upload_j (or pb_reserve_j / pb_upload_j_range / pb_publish_j) published the j of this
+ * step with SP store slot c == multipole of cell c.  Single domain (pb_tree_upload): the EP store order
+ * is the tree's sorted particle order.  With a local essential tree (pb_tree_upload_let): the tree's
+ * leaves also hold the EP and SP received from other domains, and `elem_map` says where each sorted
+ * tree element lives — elem_map[k] >= 0: EP store index; < 0: the LET superparticle in SP store slot
+ * n_cells + ~elem_map[k] — so the store may be in any order (e.g. local particles first, LET entries
+ * behind them as they arrive over NCCL). */
 typedef struct pb_tree_cell {          /* 176 B */
     double cm[3];                      /* centre of mass = expansion centre of the cell's superparticle */
     double len;                        /* geometric cell length */
     double in_lo[3], in_hi[3];         /* box of the particles inside */
     double out_lo[3], out_hi[3];       /* box of their search spheres (pos +- 0.99 r_search) */
     int    child[8];                   /* cell ids, -1 = none */
-    int    first, n;                   /* particle range in the sorted j array */
-    int    leaf, pad;
+    int    first, n;                   /* element range in the tree's sorted order */
+    int    leaf;
+    int    n_let_sp;                   /* leaves: how many of the n elements are LET superparticles (0 without LET) */
 } pb_tree_cell;
 
 typedef struct pb_tree_group {         /* 104 B: one i-group ("walk") */
@@ -205,6 +210,8 @@ typedef struct pb_tree_group {         /* 104 B: one i-group ("walk") */
  * returns as soon as the copy and the walk's counting pass are queued, so calling it FIRST lets the
  * GPU count list lengths while the host packs the j-particles. */
 int  pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta);
+int  pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta,
+                        const int* elem_map, int n_elem);
 /* Forces on all i-particles, given in group order (group 0's particles first, ...); ASSIGNS
  * force[k].{acc,pot,n_ngb}.  Synchronous.  Both arrays are contiguous with the given layouts. */
 int  pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const pb_layout_force* lforce);

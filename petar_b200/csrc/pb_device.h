@@ -102,9 +102,11 @@ cudaError_t launch_reduce(cudaStream_t s, int n_iblocks, const IBlock* iblocks,
 
 // device-side list building (pb_walk.cu); cells / groups are pb_tree_cell / pb_tree_group arrays
 cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
-                              int2* counts, int* scratch, int cap, int n_ctas, int* overflow);
+                              int2* counts, int* scratch, int cap, int n_ctas, int* overflow,
+                              const int* elem_map = nullptr, int n_cells = 0);
 cudaError_t launch_walk_fill(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
-                             const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow);
+                             const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow,
+                             const int* elem_map = nullptr, int n_cells = 0);
 
 // changeover correction (pb_corr.cu): the fields of one neighbour / one corrected particle, fp64
 struct CorrJ { double x, y, z, mass, r_in, r_out, mass_bk, status; long long id; };       // 72 B

@@ -133,6 +133,7 @@ struct Engine {
     int* d_tree_ide = nullptr; int* d_tree_ids = nullptr; size_t cap_tree_ide = 0, cap_tree_ids = 0;
     int2* d_tree_off = nullptr; std::vector<int2> h_tree_off; cudaEvent_t ev_fill = nullptr;
     char* h_corr = nullptr; char* d_corr = nullptr; size_t cap_corr = 0;   // changeover correction: pinned staging + device mirror
+    int* d_elem_map = nullptr; int* h_elem_map = nullptr; size_t cap_elem_map = 0; bool has_elem_map = false;   // device walk over a tree with LET elements
     // end of the last kernel of the two most recent dispatches (gap timer, pb_profile.t_gap)
     cudaEvent_t ev_end[2] = {nullptr, nullptr}; int end_cur = 0; bool end_prev_valid = false; int out_first_slot = -1;
     int2* h_counts_p = nullptr; size_t cap_counts_p = 0; int* h_over_p = nullptr;   // pinned landing zone of the count pass
@@ -819,6 +820,8 @@ void pb_finalize(void) {
         S = Slot();
     }
     cudaFree(E.d_epj); cudaFree(E.d_spj); cudaFreeHost(E.h_jstage);
+    if (E.d_elem_map) cudaFree(E.d_elem_map);
+    if (E.h_elem_map) cudaFreeHost(E.h_elem_map);
     if (E.h_corr) cudaFreeHost(E.h_corr);
     if (E.d_corr) cudaFree(E.d_corr);
     E.h_corr = nullptr; E.d_corr = nullptr; E.cap_corr = 0;
@@ -1288,10 +1291,17 @@ int tree_finish_slot(Slot& S, char* force, const pb_layout_force& L, size_t i_fi
 } // namespace
 
 int pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta) {
+    return pb_tree_upload_let(cells, n_cells, groups, n_groups, theta, nullptr, 0);
+}
+
+int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta,
+                       const int* elem_map, int n_elem) {
     int rc = ensure_init();
     if (rc != PB_OK) return rc;
-    if (n_cells < 0 || n_groups < 0 || (n_cells && !cells) || (n_groups && !groups) || !(theta >= 0.0))
+    if (n_cells < 0 || n_groups < 0 || n_elem < 0 || (n_cells && !cells) || (n_groups && !groups) || !(theta >= 0.0) || (n_elem && !elem_map))
         return fail(PB_ERR_ARG, "pb_tree_upload: bad argument");
+    if (elem_map && n_cells && (long long)cells[0].first + cells[0].n > n_elem)
+        return fail(PB_ERR_ARG, "pb_tree_upload_let: the root cell spans %lld elements, elem_map has %d", (long long)cells[0].first + cells[0].n, n_elem);
     if (E.outstanding) return fail(PB_ERR_PROTOCOL, "pb_tree_upload while a dispatch is outstanding");
     CU(cudaDeviceSynchronize());
     if ((size_t)n_cells > E.cap_cells) {
@@ -1328,6 +1338,19 @@ int pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* 
     }
     CU(cudaMemcpyAsync(E.d_cells, E.h_tstage, bc, cudaMemcpyHostToDevice, E.s_upload));
     CU(cudaMemcpyAsync(E.d_groups, E.h_tstage + bc, bg, cudaMemcpyHostToDevice, E.s_upload));
+    E.has_elem_map = elem_map != nullptr && n_elem > 0;
+    if (E.has_elem_map) {
+        if ((size_t)n_elem > E.cap_elem_map) {
+            if (E.d_elem_map) CU(cudaFree(E.d_elem_map));
+            if (E.h_elem_map) CU(cudaFreeHost(E.h_elem_map));
+            E.cap_elem_map = (size_t)n_elem + n_elem / 4 + 1024;
+            CU(cudaMalloc(&E.d_elem_map, sizeof(int) * E.cap_elem_map));
+            CU(cudaMallocHost(&E.h_elem_map, sizeof(int) * E.cap_elem_map));
+        }
+        memcpy(E.h_elem_map, elem_map, sizeof(int) * (size_t)n_elem);
+        CU(cudaMemcpyAsync(E.d_elem_map, E.h_elem_map, sizeof(int) * (size_t)n_elem, cudaMemcpyHostToDevice, E.s_upload));
+        E.prof.h2d_bytes += (long long)(sizeof(int) * (size_t)n_elem);
+    }
     CU(cudaEventRecord(E.ev_j_ready, E.s_upload));        // dispatch streams wait for j AND tree
     E.prof.h2d_bytes += (long long)(sizeof(pb_tree_cell) * (size_t)n_cells + sizeof(pb_tree_group) * (size_t)n_groups);
     E.n_cells = n_cells; E.n_groups = n_groups; E.theta = theta;
@@ -1349,7 +1372,8 @@ int pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* 
         const double theta_inv2 = theta > 0.0 ? 1.0 / (theta * theta) : 1e300;
         cudaStream_t s0 = E.slots[0].stream;
         CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));
-        CU(launch_walk_count(s0, E.d_cells, E.d_groups, 0, n_groups, theta_inv2, E.d_counts, E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow));
+        CU(launch_walk_count(s0, E.d_cells, E.d_groups, 0, n_groups, theta_inv2, E.d_counts, E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow,
+                             E.has_elem_map ? E.d_elem_map : nullptr, n_cells));
         CU(cudaMemcpyAsync(E.h_counts_p, E.d_counts, sizeof(int2) * (size_t)n_groups, cudaMemcpyDeviceToHost, s0));
         CU(cudaMemcpyAsync(E.h_over_p, E.d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s0));
         CU(cudaEventRecord(E.ev_count, s0));
@@ -1401,7 +1425,7 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
     const bool split_fill = E.opt_tree_fill == 1;          // fill each batch's lists on the batch's own stream, just ahead of its force launch
     if (!split_fill) {
         CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, E.n_groups, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
-                            E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow));
+                            E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells));
         E.prof.n_kernel_launch += 1;
     } else {
         for (int s = 0; s < n_slots; s++) if ((rc = ensure_walk_scratch(s)) != PB_OK) return rc;
@@ -1452,7 +1476,8 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
         CU(cudaStreamWaitEvent(S.stream, E.ev_fill, 0));
         if (split_fill) {
             CU(launch_walk_fill(S.stream, E.d_cells, E.d_groups, g0, nb, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
-                                E.d_walk_scratch[s], kWalkCap, std::min(kWalkCtas, (nb + 3) / 4), E.d_overflow));
+                                E.d_walk_scratch[s], kWalkCap, std::min(kWalkCtas, (nb + 3) / 4), E.d_overflow,
+                                E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells));
             E.prof.n_kernel_launch += 1;
         }
         CU(cudaEventRecord(S.ev[0], S.stream));

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(128)
 walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restrict__ groups,
             int g0, int n_groups, double theta_inv2,
             int2* __restrict__ counts, const int2* __restrict__ offs, int* __restrict__ id_e, int* __restrict__ id_s,
-            int* __restrict__ scratch, int cap, int* __restrict__ overflow)
+            int* __restrict__ scratch, int cap, int* __restrict__ overflow,
+            const int* __restrict__ elem_map, int n_cells)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -74,7 +75,7 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
             int nnext = 0;
             for (int base = 0; base < ncur; base += 32) {
                 const int idx = base + lane;
-                int cls = 0, first = 0, n = 0, cell = -1;
+                int cls = 0, first = 0, n = 0, nls = 0, cell = -1;
                 int child[8];
                 if (idx < ncur) {
                     cell = cur[idx];
@@ -86,7 +87,7 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
                         const bool touch = box_overlap(grp.out_lo, grp.out_hi, c.in_lo, c.in_hi) ||
                                            box_overlap(c.out_lo, c.out_hi, grp.in_lo, grp.in_hi);
                         if (far_enough && !touch) cls = 1;
-                        else if (c.leaf) { cls = 2; first = c.first; }
+                        else if (c.leaf) { cls = 2; first = c.first; nls = elem_map ? c.n_let_sp : 0; }
                         else {
                             cls = 3;
 #pragma unroll
@@ -98,11 +99,26 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
                 const unsigned m1 = __ballot_sync(0xffffffffu, cls == 1);
                 if (FILL && cls == 1) os[nsp + __popc(m1 & ((1u << lane) - 1u))] = cell;
                 nsp += __popc(m1);
-                // opened leaves: particle ranges -> EP list
+                // opened leaves: element ranges -> EP list (and, with a local essential tree, the superparticles
+                // received from other domains -> SP list; elem_map says where each sorted element is stored)
                 int tot;
-                const int off_e = warp_excl_scan(cls == 2 ? n : 0, lane, tot);
-                if (FILL && cls == 2)
-                    for (int k = 0; k < n; k++) oe[nep + off_e + k] = first + k;
+                const int off_e = warp_excl_scan(cls == 2 ? n - nls : 0, lane, tot);
+                if (elem_map == nullptr) {
+                    if (FILL && cls == 2)
+                        for (int k = 0; k < n; k++) oe[nep + off_e + k] = first + k;
+                } else {
+                    int tot_s;
+                    const int off_s = warp_excl_scan(cls == 2 ? nls : 0, lane, tot_s);
+                    if (FILL && cls == 2) {
+                        int ke = nep + off_e, ks = nsp + off_s;
+                        for (int k = 0; k < n; k++) {
+                            const int m = elem_map[first + k];
+                            if (m >= 0) oe[ke++] = m;
+                            else        os[ks++] = n_cells + ~m;
+                        }
+                    }
+                    nsp += tot_s;
+                }
                 nep += tot;
                 // opened cells: children -> next frontier
                 int nch = 0;
@@ -129,18 +145,19 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
 }
 
 cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
-                              int2* counts, int* scratch, int cap, int n_ctas, int* overflow) {
+                              int2* counts, int* scratch, int cap, int n_ctas, int* overflow, const int* elem_map, int n_cells) {
     if (n_groups <= 0) return cudaSuccess;
     walk_kernel<false><<<n_ctas, 128, 0, s>>>((const pb_tree_cell*)cells, (const pb_tree_group*)groups, g0, n_groups, theta_inv2,
-                                              counts, nullptr, nullptr, nullptr, scratch, cap, overflow);
+                                              counts, nullptr, nullptr, nullptr, scratch, cap, overflow, elem_map, n_cells);
     return cudaGetLastError();
 }
 
 cudaError_t launch_walk_fill(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
-                             const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow) {
+                             const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow,
+                             const int* elem_map, int n_cells) {
     if (n_groups <= 0) return cudaSuccess;
     walk_kernel<true><<<n_ctas, 128, 0, s>>>((const pb_tree_cell*)cells, (const pb_tree_group*)groups, g0, n_groups, theta_inv2,
-                                             nullptr, offs, id_e, id_s, scratch, cap, overflow);
+                                             nullptr, offs, id_e, id_s, scratch, cap, overflow, elem_map, n_cells);
     return cudaGetLastError();
 }
 

@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
     "pb_field_at_points", "pb_dispatch_count_index", "pb_tree_upload", "pb_tree_force", "pb_tree_lists",
-    "pb_correct_changeover", "pb_retrieve_neighbors",
+    "pb_correct_changeover", "pb_retrieve_neighbors", "pb_tree_upload_let",
 ]
 
 _lib = None
@@ -128,6 +128,7 @@ def load():
     L.pb_pack_epj_host_indexed.argtypes = [_vp, _vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_spj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutSpj), _vp]
     L.pb_tree_upload.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double]
+    L.pb_tree_upload_let.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double, _vp, C.c_int]
     L.pb_tree_force.argtypes = [_vp, C.POINTER(LayoutEpi), _vp, C.POINTER(LayoutForce)]
     L.pb_tree_lists.argtypes = [_vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong]
     L.pb_correct_changeover.argtypes = [C.c_int, _vp, C.POINTER(LayoutCorr), C.c_int, _vp, C.POINTER(LayoutCorr), _vp, _vp, C.POINTER(CorrParams)]
@@ -294,7 +295,7 @@ def tree_neighbor_search(batch, n_walk_limit=200, force=None, lists=False, table
     return f, nb_off.astype(np.int32), nb_idx
 
 
-def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, upload=True):
+def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, upload=True, elem_map=None):
     """Device-side list building: publish j, upload the tree, let the GPU build every
     group's id_epj / id_spj and run the force kernels on them.  `batch` only supplies epj / spj / epi
     (its host index lists are NOT used).  Returns ForceSoft[n_epi_total] in group order."""
@@ -304,7 +305,12 @@ def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, uploa
     if upload:
         # tree first: its upload also starts the walk's counting pass, which then runs on the GPU
         # while the host packs the j-particles
-        check(L.pb_tree_upload(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta)), "pb_tree_upload")
+        if elem_map is None:
+            check(L.pb_tree_upload(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta)), "pb_tree_upload")
+        else:                                            # tree over local + LET elements, store in any order
+            em = np.ascontiguousarray(elem_map, dtype=np.int32)
+            check(L.pb_tree_upload_let(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta),
+                                       em.ctypes.data, len(em)), "pb_tree_upload_let")
         check(L.pb_upload_j(batch.epj.ctypes.data, len(batch.epj), C.byref(LAYOUT_EPJ),
                             batch.spj.ctypes.data, len(batch.spj), C.byref(LAYOUT_SPJ)), "pb_upload_j")
     check(L.pb_tree_force(batch.epi.ctypes.data, C.byref(LAYOUT_EPI), f.ctypes.data, C.byref(LAYOUT_FORCE)), "pb_tree_force")

@@ -160,13 +160,19 @@ class TreeHandle:
 
     def export_tree(self):
         """(cells, groups) in the layout of pb_tree_cell / pb_tree_group, for the device-side list
-        builder (single-domain builds only)."""
+        builder.  A tree with LET elements also needs :meth:`export_elem_map`."""
         from .types import TreeCell, TreeGroup
-        assert self._let[1] is None or len(self._let[1]) == 0, "device walk: single-domain trees only"
         cells = np.zeros(self.n_nodes, dtype=TreeCell)
         groups = np.zeros(self.n_walk, dtype=TreeGroup)
         lib().hz_export_tree(self.h, cells.ctypes.data, groups.ctypes.data)
         return cells, groups
+
+    def export_elem_map(self):
+        """For the k-th Morton-sorted element of the (global) tree: its index in epj_sorted (>= 0) or
+        ~(its index in the LET part of spj) (< 0) — pb_tree_upload_let's `elem_map`."""
+        out = np.zeros(self.n_epj + self.n_let_sp, dtype=np.int32)
+        lib().hz_export_elem_map(self.h, out.ctypes.data)
+        return out
 
     def timing(self):
         """(seconds building the tree, seconds walking it for all groups) on the host, OpenMP."""

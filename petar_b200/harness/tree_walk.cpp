@@ -389,8 +389,8 @@ void hz_export_let_sp_src(void* h, int* out) {
 }
 
 // The tree itself, in the layout of pb_tree_cell / pb_tree_group (include/petar_b200.h), for the
-// device-side list builder.  Only meaningful for a single-domain build (no LET elements): cell c's
-// superparticle is spj[c], element range [first, first+n) indexes epj_sorted.
+// device-side list builder.  Cell c's superparticle is spj[c]; its element range [first, first+n) indexes the
+// Morton-sorted elements (= epj_sorted for a single-domain build; with LET elements see hz_export_elem_map).
 struct ExportCell  { double cm[3], len, in_lo[3], in_hi[3], out_lo[3], out_hi[3]; int child[8]; int first, n, leaf, pad; };
 struct ExportGroup { int first, n; double in_lo[3], in_hi[3], out_lo[3], out_hi[3]; };
 
@@ -407,7 +407,10 @@ void hz_export_tree(void* h, void* cells_out, void* groups_out) {
         }
         c[i].len = 2.0 * nd.half;
         for (int k = 0; k < 8; k++) c[i].child[k] = nd.child[k];
-        c[i].first = nd.first; c[i].n = nd.n; c[i].leaf = nd.leaf ? 1 : 0; c[i].pad = 0;
+        c[i].first = nd.first; c[i].n = nd.n; c[i].leaf = nd.leaf ? 1 : 0;
+        int nls = 0;                                   // LET superparticles among a leaf's elements
+        if (nd.leaf) for (int e = nd.first; e < nd.first + nd.n; e++) nls += (G.sp_index[e] >= 0);
+        c[i].pad = nls;
     }
     ExportGroup* g = (ExportGroup*)groups_out;
     for (size_t i = 0; i < R->groups.size(); i++) {
@@ -418,6 +421,14 @@ void hz_export_tree(void* h, void* cells_out, void* groups_out) {
             g[i].out_lo[k] = gr.outer.lo[k]; g[i].out_hi[k] = gr.outer.hi[k];
         }
     }
+}
+
+// Element map of the (global) tree for the device walk: out[k] for the k-th Morton-sorted element is its
+// index in epj_sorted (>= 0) or ~(index in the LET part of spj) (< 0).  Single-domain builds: the identity.
+void hz_export_elem_map(void* h, int* out) {
+    Result* R = (Result*)h;
+    const Tree& G = R->gt();
+    for (size_t i = 0; i < G.el.size(); i++) out[i] = G.ep_index[i] >= 0 ? G.ep_index[i] : ~G.sp_index[i];
 }
 
 // Local boxes of this domain: out[0..5] = particle box lo/hi, out[6..11] = search box lo/hi

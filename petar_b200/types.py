@@ -33,7 +33,7 @@ ForceSoft = np.dtype([("acc", "<f8", (3,)), ("pot", "<f8"), ("n_ngb", "<i8")], a
 # device-side list building (include/petar_b200.h: pb_tree_cell, pb_tree_group)
 TreeCell = np.dtype(
     [("cm", "<f8", (3,)), ("len", "<f8"), ("in_lo", "<f8", (3,)), ("in_hi", "<f8", (3,)), ("out_lo", "<f8", (3,)), ("out_hi", "<f8", (3,)),
-     ("child", "<i4", (8,)), ("first", "<i4"), ("n", "<i4"), ("leaf", "<i4"), ("pad", "<i4")],
+     ("child", "<i4", (8,)), ("first", "<i4"), ("n", "<i4"), ("leaf", "<i4"), ("n_let_sp", "<i4")],
     align=True,
 )
 TreeGroup = np.dtype(

@@ -83,3 +83,56 @@ def test_device_walk_fullsize_report():
     assert np.array_equal(f["n_ngb"], force["n_ngb"])
     assert np.abs(f["acc"] - force["acc"]).max() <= 2e-6 * np.abs(force["acc"]).max()
     assert prof["n_interaction_ep"] == batch.interactions()[0] and prof["n_interaction_sp"] == batch.interactions()[1]
+
+
+def _two_domain_case(n=40000):
+    """Domain A (x < median) of a Plummer model with the local essential tree it receives from domain B."""
+    mass, pos, vel = hz.make_plummer(n)
+    prm = hz.petar_auto_params(mass, vel)
+    r_in, r_out, rs = hz.particle_rout_rsearch(mass, vel, prm)
+    a = pos[:, 0] < np.median(pos[:, 0])
+    b = ~a
+    ta = hz.TreeHandle(pos[a], mass[a], rs[a])
+    tb = hz.TreeHandle(pos[b], mass[b], rs[b])
+    ep_idx, sp = tb.make_let(ta.local_boxes())                    # what B owes A: particles near the border, multipoles beyond
+    let = dict(pos=pos[b][ep_idx], mass=mass[b][ep_idx], rsearch=rs[b][ep_idx], spj=sp)
+    batch, _ = hz.build_walk_batch(pos[a], mass[a], rs[a], vel=vel[a], r_in=r_in[a], r_out=r_out[a], let=let)
+    assert len(ep_idx) > 100 and len(sp) > 100 and len(batch.epj) == a.sum() + len(ep_idx)
+    return batch, prm
+
+
+def test_device_walk_with_local_essential_tree():
+    """Multi-domain trees: leaves hold EP *and* SP received from other domains; elem_map tells the walk where
+    each sorted element is stored.  Lists must still be the host walk's sets; forces meet the tolerance."""
+    batch, prm = _two_domain_case()
+    cells, groups = batch.tree.export_tree()
+    emap = batch.tree.export_elem_map()
+    n_let_sp = int((emap < 0).sum())
+    assert n_let_sp > 0 and cells["n_let_sp"].sum() == n_let_sp and len(batch.spj) == len(cells) + n_let_sp
+    engine.set_option("tree_batch", 1 << 20)
+    f = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], elem_map=emap)
+    ne, ns, ide, ids = engine.tree_lists(len(groups))
+    engine.set_option("tree_batch", 1024)
+    assert np.array_equal(ne, batch.n_epj) and np.array_equal(ns, batch.n_spj)
+    eo, so = np.concatenate([[0], np.cumsum(ne)]), np.concatenate([[0], np.cumsum(ns)])
+    saw_let_sp = False
+    for g in range(len(groups)):
+        assert np.array_equal(np.sort(ide[eo[g]:eo[g + 1]]), np.sort(batch.id_epj[batch.ej_off[g]:batch.ej_off[g + 1]])), f"EP list of group {g}"
+        sp_g = np.sort(ids[so[g]:so[g + 1]])
+        assert np.array_equal(sp_g, np.sort(batch.id_spj[batch.sj_off[g]:batch.sj_off[g + 1]])), f"SP list of group {g}"
+        saw_let_sp |= bool(len(sp_g) and sp_g[-1] >= len(cells))
+    assert saw_let_sp
+    ref = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"])
+    ea = np.linalg.norm(f["acc"] - ref["acc"], axis=1) / np.linalg.norm(ref["acc"], axis=1)
+    assert np.median(ea) <= 1e-6 and ea.max() <= 1e-4 and np.array_equal(f["n_ngb"], ref["n_ngb"])
+
+    # the j store in another order (as in the multi-GPU step: local particles first, LET entries as they arrive)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(len(batch.epj)).astype(np.int32)        # sorted index k lives in store slot perm[k]
+    epj_store = np.zeros_like(batch.epj)
+    epj_store[perm] = batch.epj
+    shuffled = type(batch)(epj_store, batch.spj, batch.epi, batch.i_off, perm[batch.id_epj], batch.ej_off, batch.id_spj, batch.sj_off)
+    emap_store = np.where(emap >= 0, perm[np.maximum(emap, 0)], emap).astype(np.int32)
+    f2 = engine.tree_force(shuffled, cells, groups, prm["eps"], prm["r_out"], prm["G"], elem_map=emap_store)
+    assert np.array_equal(f2["n_ngb"], f["n_ngb"])
+    assert np.abs(f2["acc"] - f["acc"]).max() <= 2e-6 * np.abs(f["acc"]).max()
