@@ -364,15 +364,20 @@ def main():
     # ---- informational: the same step with the interaction lists built on the GPU from the tree
     # (not the drop-in path — FDPS would have to hand over its tree) ----
     device_walk = None
-    if world == 1 and not args.no_device_walk:
+    if not args.no_device_walk:
         try:
-            cells, groups = batch.tree.export_tree()
-            engine.tree_force(batch, cells, groups, eps, r_out, G, force=force)              # warm-up / allocations
+            if stepper is None:
+                cells, groups = batch.tree.export_tree()
+                dw_step = lambda: engine.tree_force(batch, cells, groups, eps, r_out, G, force=force)
+            else:
+                cells, groups = wl["tree_cells"], wl["tree_groups"]
+                dw_step = lambda: stepper.step_device_walk(force)
+            dw_step()                                                                        # warm-up / allocations
             engine.get_profile(reset=True)
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                engine.tree_force(batch, cells, groups, eps, r_out, G, force=force)
+                dw_step()
             barrier()
             sec_dw = (time.perf_counter() - t0) / args.steps
             pdw = engine.get_profile()
@@ -389,13 +394,14 @@ def main():
         clocks["window"] += " + %.1f s of the same recorded steps replayed right after it (untimed)" % clock_probe_s
 
     # ---- max over ranks, totals over ranks ----
-    vals = torch.tensor([ms_step, ms_force, sec_e2e], dtype=torch.float64, device="cuda")
+    sec_dw_loc = device_walk["ms_per_step"] * 1e-3 if device_walk and "ms_per_step" in device_walk else 0.0
+    vals = torch.tensor([ms_step, ms_force, sec_e2e, sec_dw_loc], dtype=torch.float64, device="cuda")
     tot = torch.tensor([I_ep, I_sp, prof["h2d_bytes"] / args.steps, prof["d2h_bytes"] / args.steps,
                         stepper.nccl_bytes_per_step if stepper else 0], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_step, ms_force, sec_e2e = (float(x) for x in vals.tolist())
+    ms_step, ms_force, sec_e2e, sec_dw_max = (float(x) for x in vals.tolist())
     I_ep_t, I_sp_t, h2d, d2h, nccl_b = (float(x) for x in tot.tolist())
 
     if rank == 0:
@@ -441,6 +447,9 @@ def main():
             "clocks": clocks,
         }
         if device_walk is not None:
+            if "ms_per_step" in device_walk and sec_dw_max > 0:                  # whole job: max time over ranks, all ranks' interactions
+                device_walk["ms_per_step"] = sec_dw_max * 1e3
+                device_walk["value"] = inter / sec_dw_max * 1e-9
             line["device_walk"] = device_walk
         if stepper is not None and stepper.n_steps:
             line["e2e"]["rank0_step_phases_ms"] = {k: v * 1e3 / stepper.n_steps for k, v in stepper.host_s.items()}

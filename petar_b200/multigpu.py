@@ -135,8 +135,13 @@ def build_domain_workload(pos, mass, vel, rs, r_in, r_out, rank, world, dist=Non
     epi["type"] = 1 if ptype is None else np.asarray(ptype)[my[epi_src]]
     batch = WalkBatch(epj, spj, epi, i_off, id_epj_store, ej_off, id_spj_store, sj_off)
     batch.tree = t
+    # for the device-side walk (pb_tree_upload_let): the global tree and where each of its sorted elements is stored
+    cells, groups = t.export_tree()
+    em = t.export_elem_map()
+    elem_map = np.where(em >= 0, epj_src[np.maximum(em, 0)], ~sp_src[np.maximum(~em, 0)] if n_let_sp else em).astype(np.int32)
     return dict(batch=batch, my=my, epi_src=epi_src, n_loc=n_loc, n_nodes=n_nodes, n_let_ep=n_let_ep, n_let_sp=n_let_sp,
-                send_ep_idx=send_ep_idx, send_sp=send_sp, recv_ep_cnt=recv_ep_cnt, recv_sp_cnt=recv_sp_cnt, let=let, local_tree=tloc)
+                send_ep_idx=send_ep_idx, send_sp=send_sp, recv_ep_cnt=recv_ep_cnt, recv_sp_cnt=recv_sp_cnt, let=let, local_tree=tloc,
+                tree_cells=cells, tree_groups=groups, elem_map=elem_map)
 
 
 class DomainStepper:
@@ -201,6 +206,25 @@ class DomainStepper:
             se, ss = self.h_send_ep, self.h_send_sp
         dist.all_to_all_single(self.store_ep[self.n_loc:], se, self.out_ep, self.in_ep)
         dist.all_to_all_single(self.store_sp[self.n_nodes:], ss, self.out_sp, self.in_sp)
+
+    def step_device_walk(self, force, theta=0.3):
+        """The same tree step with the interaction lists built on the GPU: the global tree
+        (local + LET elements) is uploaded instead of per-walk index lists; j travels as in :meth:`step`."""
+        b, L, wl = self.batch, self.L, self.wl
+        cells, groups, em = wl["tree_cells"], wl["tree_groups"], wl["elem_map"]
+        engine.check(L.pb_set_params(self.prm["eps"] ** 2, self.prm["r_out"] ** 2, self.prm["G"]), "pb_set_params")
+        engine.check(L.pb_tree_upload_let(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta),
+                                          em.ctypes.data, len(em)), "pb_tree_upload_let")       # starts the walk's counting pass
+        pe, ps = C.c_void_p(0), C.c_void_p(0)
+        engine.check(L.pb_reserve_j(len(b.epj), len(b.spj), C.byref(pe), C.byref(ps)), "pb_reserve_j")
+        assert (pe.value, ps.value) == self._ptrs, "j store moved"
+        engine.check(L.pb_upload_j_range(b.epj.ctypes.data, 0, self.n_loc, C.byref(engine.LAYOUT_EPJ),
+                                         b.spj.ctypes.data, 0, self.n_nodes, C.byref(engine.LAYOUT_SPJ)), "pb_upload_j_range")
+        self.pack_sends()
+        self.exchange()
+        engine.check(L.pb_publish_j(C.c_void_p(self.torch.cuda.current_stream().cuda_stream)), "pb_publish_j")
+        engine.check(L.pb_tree_force(b.epi.ctypes.data, C.byref(engine.LAYOUT_EPI), force.ctypes.data, C.byref(engine.LAYOUT_FORCE)), "pb_tree_force")
+        return force
 
     def step(self, force):
         import time

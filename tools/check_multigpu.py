@@ -33,6 +33,14 @@ ep = np.abs((f["pot"] - ref["pot"]) / ref["pot"])
 ok = np.median(ea) <= 1e-6 and ea.max() <= 1e-4 and np.median(ep) <= 1e-6 and ep.max() <= 1e-4 and np.array_equal(f["n_ngb"], ref["n_ngb"])
 print(f"rank {rank}/{world} n_loc={wl['n_loc']} let_ep={wl['n_let_ep']} let_sp={wl['n_let_sp']} nccl_bytes={st.nccl_bytes_per_step} "
       f"acc med {np.median(ea):.2e} max {ea.max():.2e} pot max {ep.max():.2e} nngb_equal {np.array_equal(f['n_ngb'], ref['n_ngb'])} -> {'OK' if ok else 'FAIL'}", flush=True)
+# the same step with the lists built on the GPU from the global (local + LET) tree
+f2 = np.zeros_like(f)
+for _ in range(2):
+    st.step_device_walk(f2)
+ea2 = np.linalg.norm(f2["acc"] - ref["acc"], axis=1) / np.linalg.norm(ref["acc"], axis=1)
+ok2 = np.median(ea2) <= 1e-6 and ea2.max() <= 1e-4 and np.array_equal(f2["n_ngb"], ref["n_ngb"])
+print(f"rank {rank}/{world} device walk over the LET tree: acc med {np.median(ea2):.2e} max {ea2.max():.2e} nngb_equal {np.array_equal(f2['n_ngb'], ref['n_ngb'])} -> {'OK' if ok2 else 'FAIL'}", flush=True)
+ok = ok and ok2
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
