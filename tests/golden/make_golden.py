@@ -4,7 +4,8 @@ The reference keeps no golden vectors for this path (src/simd_test.cxx stores no
 fails), so the fixtures are produced here from the reference's OWN kernels: the AVX2 / AVX-512
 PhantomGrapeQuad code compiled verbatim from /root/reference/src/phantomquad_for_p3t_x86.hpp
 (oracle/_ref, recipe in oracle/Makefile) on the input set of src/simd_test.cxx, next to the fp64
-restatement's output on the same inputs.  The GPU box has no /root/reference: its tests read
+restatement's output on the same inputs; and, for the changeover correction, from the reference's
+ChangeOver class and pair function compiled in oracle/_ref.  The GPU box has no /root/reference: its tests read
 only the committed .npz files.
 
     python tests/golden/make_golden.py
@@ -62,7 +63,37 @@ def main():
     for isa in ("avx2", "avx512"):
         out2[f"ref_{isa}"], _ = ob.ref_walks_index(batch, prm["eps"], prm["r_out"], prm["G"], isa=isa)
     np.savez_compressed(os.path.join(OUT, "plummer1k_walks.npz"), **out2)
-    for f in ("simdtest.npz", "plummer1k_walks.npz"):
+
+    # changeover correction: random pairs of every neighbour kind through the REFERENCE's own
+    # calcAccPotShortWithLinearCutoff (src/hard.hpp:1408-1476, compiled in oracle/_ref from the reference
+    # sources together with src/changeover.hpp), both the USE_GPU (float replay) and the all-double branch
+    from petar_b200.types import PtclCorr
+    rng = np.random.default_rng(2024)
+    n, r_out_g, G = 1000, 2e-3, 0.7
+    pi, pj = np.zeros(n, PtclCorr), np.zeros(n, PtclCorr)
+    pi["pos"] = rng.uniform(-1, 1, (n, 3))
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+    pj["pos"] = pi["pos"] + (10 ** rng.uniform(-5, -2, n))[:, None] * d
+    for q in (pi, pj):
+        f = rng.uniform(1, 3, n)
+        q["mass"], q["r_in"], q["r_out"], q["id"] = 10 ** rng.uniform(-7, -4, n), r_out_g / 10 * f, r_out_g * f, rng.integers(1, 1 << 40, n)
+    kind = np.arange(n) % 3
+    pj["status"][kind == 1] = -5.0; pj["mass_backup"][kind == 1] = pj["mass"][kind == 1]; pj["mass"][kind == 1] = 0.0
+    pj["status"][kind == 2] = 3.0
+    pi["acc"], pi["pot_tot"], pi["pot_soft"] = rng.normal(size=(n, 3)), rng.normal(size=n), rng.normal(size=n)
+    pi["status"] = 1.0          # the pair function does not read it; keeps the one-particle loop's self-potential term out
+    eps = np.where(np.arange(n) % 2 == 0, 0.0, 1e-4)
+    out3 = dict(pi=pi, pj=pj, eps=eps, r_out=np.array(r_out_g), G=np.array(G))
+    for replay in (0, 1):
+        res = pi.copy()
+        for k in range(n):
+            ob.ref_changeover_pair(res[k:k + 1], pj[k:k + 1], float(eps[k]), r_out_g, G, replay)
+        out3["ref_replay_fp32" if replay else "ref_fp64"] = res
+    w = np.array([[ri, ro, dr, *ob.ref_changeover_w(ri, ro, dr)] for ri, ro, dr in
+                  zip(10 ** rng.uniform(-5, -2, 500), 10 ** rng.uniform(-1.9, -1, 500), 10 ** rng.uniform(-6, -1, 500))])
+    out3["w_table"] = w                                   # r_in, r_out, dr, calcAcc0W, calcPotW
+    np.savez_compressed(os.path.join(OUT, "changeover_pairs.npz"), **out3)
+    for f in ("simdtest.npz", "plummer1k_walks.npz", "changeover_pairs.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 

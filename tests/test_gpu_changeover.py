@@ -107,3 +107,18 @@ def test_soft_force_plus_correction_is_the_changeover_force():
         want[i] = -(w[:, None] * dr).sum(axis=0)
     err = np.linalg.norm(got["acc"] - want, axis=1) / np.linalg.norm(want, axis=1)
     assert np.median(err) < 1e-6 and err.max() < 1e-4, (np.median(err), err.max())
+
+
+def test_kernel_vs_committed_reference_vectors():
+    """The device kernel against outputs of the REFERENCE's own pair function (tests/golden/changeover_pairs.npz,
+    generated where /root/reference exists): one neighbour per particle, both branches, eps = 0 and 1e-4."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "changeover_pairs.npz"))
+    pi, pj, eps = g["pi"], g["pj"], g["eps"]
+    for replay, key in ((False, "ref_fp64"), (True, "ref_replay_fp32")):
+        for e in np.unique(eps):
+            sel = np.nonzero(eps == e)[0]
+            off = np.arange(len(sel) + 1, dtype=np.int32)
+            got = engine.correct_force_with_cutoff_tree_neighbor(np.ascontiguousarray(pi[sel]), off, sel.astype(np.int32), pj,
+                                                                 float(e), float(g["r_out"]), float(g["G"]), replay)
+            assert got.tobytes() == np.ascontiguousarray(g[key][sel]).tobytes()

@@ -275,3 +275,17 @@ def test_changeover_neighbor_loop_matches_pairwise_application():
             if p["id"][j] != q["id"][0]:
                 ob.changeover_pair(q, p[j:j + 1].copy(), 0.0, P["prm"]["r_out"], 1.0, False)
         assert q.tobytes() == out[i:i + 1].tobytes()
+
+
+def test_changeover_oracle_vs_committed_reference_vectors():
+    """tests/golden/changeover_pairs.npz: outputs of the reference's own pair function and ChangeOver class
+    (generated by tests/golden/make_golden.py where /root/reference exists) — bit for bit, no oracle/_ref needed."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "changeover_pairs.npz"))
+    pi, pj, eps = g["pi"], g["pj"], g["eps"]
+    for replay, key in ((0, "ref_fp64"), (1, "ref_replay_fp32")):
+        out = pi.copy()
+        for k in range(len(pi)):
+            ob.changeover_pair(out[k:k + 1], pj[k:k + 1], float(eps[k]), float(g["r_out"]), float(g["G"]), replay)
+        assert out.tobytes() == g[key].tobytes()
+    for r_in, r_out, dr, a, p in g["w_table"]:
+        assert ob.changeover_w(r_in, r_out, dr) == (a, p)
