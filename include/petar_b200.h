@@ -127,6 +127,9 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "tree_batch" groups per force launch of pb_tree_force (default 1024).
  *   "tree_fill"  pb_tree_force writes the lists with 0 (default): one step-wide launch, 1: one launch per batch on
  *                the batch's stream (measured: no gain, the force kernels own the SMs).
+ *   "min_slot_work"  a dispatch is not cut into per-stream sub-batches smaller than this many EP-equivalent
+ *                interactions (n_epi * (n_epj + 2 n_spj)); default 0 = always "streams" (measured: 4e7 saves enqueue time
+ *                at 8 ranks per node but costs more pipelining than it saves at 4).
  *   "nb_lists"   1: pb_dispatch_count_index also collects the neighbour PAIRS (see pb_retrieve_neighbors);
  *                0 (default): counts only.
  * Returns PB_ERR_ARG for an unknown key or value. */

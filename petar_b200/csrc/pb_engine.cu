@@ -140,6 +140,7 @@ struct Engine {
     cudaEvent_t ev_count = nullptr; bool count_pending = false;
     int opt_tree_batch = 1024; int tree_last_batches = 0;
     int opt_tree_fill = 0;                                 // pb_tree_force: 0 one step-wide list-fill launch, 1 one per batch on the batch's stream
+    long long opt_min_slot_work = 0;                       // > 0: a dispatch is not cut into sub-batches smaller than this many EP-equivalent interactions
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
     long long nb_n_i = 0;
@@ -593,11 +594,16 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
     if (!direct && !E.j_published) return fail(PB_ERR_PROTOCOL, "pb_dispatch_index before pb_upload_j");
     const double t0 = now_s();
 
-    // contiguous sub-batches of ~equal work, one per stream
-    int n_slots = std::max(1, std::min(E.opt_streams, n_walk));
+    // contiguous sub-batches of ~equal work, one per stream; a dispatch with little work (many ranks sharing
+    // the particles) is not cut finer than ~50 us of GPU time per sub-batch — every sub-batch costs ~13 us of
+    // enqueueing on the calling thread
     std::vector<double> cum(n_walk + 1, 0.0);
     for (int w = 0; w < n_walk; w++)
         cum[w + 1] = cum[w] + (double)win[w].ni * ((double)win[w].nej + 2.0 * (double)win[w].nsj) + 1.0;
+    const double min_work = (double)E.opt_min_slot_work;   // EP-equivalent interactions (option "min_slot_work")
+    int n_slots = std::min(E.opt_streams, n_walk);
+    if (min_work > 0.0) n_slots = std::min(n_slots, (int)(cum[n_walk] / min_work));
+    n_slots = std::max(1, n_slots);
     std::vector<int> cut(n_slots + 1, 0);
     cut[n_slots] = n_walk;
     // the first sub-batch is 1/(1+lead) the size of the others: the GPU is idle until its copy lands
@@ -854,6 +860,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "jchunk"))  { if (v < 0 || v > (1 << 20)) return fail(PB_ERR_ARG, "jchunk out of range"); E.opt_jchunk = (int)v; return PB_OK; }
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_fill")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_fill must be 0 or 1"); E.opt_tree_fill = (int)v; return PB_OK; }
+    if (!strcmp(key, "min_slot_work")) { if (v < 0) return fail(PB_ERR_ARG, "min_slot_work must be >= 0"); E.opt_min_slot_work = v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
     if (!strcmp(key, "lead"))    { if (v < 0 || v > 15) return fail(PB_ERR_ARG, "lead must be in [0, 15]"); E.opt_lead = (int)v; return PB_OK; }

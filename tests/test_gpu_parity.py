@@ -58,7 +58,7 @@ def count_mismatch_report(batch, f, ref, what):
 
 @pytest.fixture(autouse=True)
 def _defaults():
-    for k, v in (("coords", 0), ("streams", 2), ("jchunk", 0), ("nr", 0), ("cull", 1)):
+    for k, v in (("coords", 0), ("streams", 2), ("jchunk", 0), ("nr", 0), ("cull", 1), ("min_slot_work", 0)):
         engine.set_option(k, v)
     yield
 
