@@ -79,6 +79,8 @@ LAYOUT_EPJ = LayoutEpj(EPJSoft.itemsize, _off(EPJSoft, "pos"), _off(EPJSoft, "ma
 LAYOUT_SPJ = LayoutSpj(SPJQuad.itemsize, _off(SPJQuad, "pos"), _off(SPJQuad, "mass"), _off(SPJQuad, "quad"), 1)
 LAYOUT_FORCE = LayoutForce(ForceSoft.itemsize, _off(ForceSoft, "acc"), _off(ForceSoft, "pot"), _off(ForceSoft, "n_ngb"))
 
+ABI_VERSION = 3   # PB_ABI_VERSION of include/petar_b200.h this module binds
+
 # every symbol include/petar_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "pb_init", "pb_finalize", "pb_abi_version", "pb_last_error", "pb_set_params", "pb_set_option",

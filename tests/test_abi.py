@@ -27,7 +27,7 @@ def test_header_symbols_all_exported():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/petar_b200.h but not exported"
     assert sorted(engine.ABI_SYMBOLS) == names
-    assert L.pb_abi_version() == 3
+    assert L.pb_abi_version() == engine.ABI_VERSION == 3
 
 
 def test_shim_defines_petar_symbols():
@@ -128,3 +128,15 @@ def test_layouts_match_petar_structs():
     assert (engine.LAYOUT_EPJ.stride, engine.LAYOUT_EPJ.off_pos, engine.LAYOUT_EPJ.off_mass, engine.LAYOUT_EPJ.off_rsearch) == (120, 16, 8, 80)
     assert (engine.LAYOUT_SPJ.stride, engine.LAYOUT_SPJ.off_pos, engine.LAYOUT_SPJ.off_mass, engine.LAYOUT_SPJ.off_quad) == (80, 8, 0, 32)
     assert (engine.LAYOUT_FORCE.stride, engine.LAYOUT_FORCE.off_acc, engine.LAYOUT_FORCE.off_pot, engine.LAYOUT_FORCE.off_nngb) == (40, 0, 24, 32)
+
+
+def test_header_abi_version_matches_binding():
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "petar_b200.h")).read()
+    assert int(re.search(r"#define\s+PB_ABI_VERSION\s+(\d+)", hdr).group(1)) == engine.ABI_VERSION
+
+
+def test_graft_entry_build():
+    """The driver's "does it build" check: compiles every native library (and the checker) and loads them."""
+    import __graft_entry__ as g
+    g.build()
