@@ -91,6 +91,7 @@ struct Slot {
     unsigned int* d_cursor = nullptr; unsigned int* h_cursor = nullptr;
     void* d_cubtmp = nullptr; size_t cap_cubtmp = 0;
     bool emit = false; int i_base = 0;
+    long long j_epoch = -1;            // the j publication this stream has already been ordered after
 };
 
 struct Recorded {
@@ -140,6 +141,7 @@ struct Engine {
     cudaEvent_t ev_count = nullptr; bool count_pending = false;
     int opt_tree_batch = 1024; int tree_last_batches = 0;
     int opt_tree_fill = 0;                                 // pb_tree_force: 0 one step-wide list-fill launch, 1 one per batch on the batch's stream
+    long long j_epoch = 0;                                 // bumped whenever ev_j_ready is re-recorded
     long long opt_min_slot_work = 0;                       // > 0: a dispatch is not cut into sub-batches smaller than this many EP-equivalent interactions
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
@@ -661,7 +663,10 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         Slot& S = E.slots[s];
         const double t1 = now_s();
         S.plan = hp[s].p;
-        if (!direct) CU(cudaStreamWaitEvent(S.stream, E.ev_j_ready, 0));
+        if (!direct && S.j_epoch != E.j_epoch) {          // once per stream and j publication
+            CU(cudaStreamWaitEvent(S.stream, E.ev_j_ready, 0));
+            S.j_epoch = E.j_epoch;
+        }
         CU(cudaEventRecord(S.ev[0], S.stream));
         CU(cudaMemcpyAsync(S.d_arena, S.h_arena, S.plan.bytes, cudaMemcpyHostToDevice, S.stream));
         CU(cudaEventRecord(S.ev[1], S.stream));
@@ -896,13 +901,23 @@ int pb_upload_j_range(const void* epj, int epj_first, int n_epj, const pb_layout
     CU(cudaStreamSynchronize(E.s_upload));               // staging buffer free again
     float4* he = E.h_jstage;
     float4* hs = E.h_jstage + 2 * (size_t)n_epj;
-    if (n_epj) pack_epj(epj, n_epj, *lepj, he);
-    if (n_spj) pack_spj(spj, n_spj, *lspj, hs);
-    E.prof.t_copy += now_s() - t0;
     E.end_prev_valid = false;                             // a new tree step: no gap to the previous dispatch
     CU(cudaEventRecord(E.ev_send0, E.s_upload));
-    if (n_epj) CU(cudaMemcpyAsync(E.d_epj + 2 * (size_t)epj_first, he, (size_t)PB_EPJ_DEV_BYTES * n_epj, cudaMemcpyHostToDevice, E.s_upload));
-    if (n_spj) CU(cudaMemcpyAsync(E.d_spj + 4 * (size_t)spj_first, hs, (size_t)PB_SPJ_DEV_BYTES * n_spj, cudaMemcpyHostToDevice, E.s_upload));
+    // packed and copied in pieces: the DMA of one piece runs while the host packs the next
+    constexpr int kPiece = 1 << 18;
+    const char* be = (const char*)epj;
+    for (int o = 0; o < n_epj; o += kPiece) {
+        const int m = std::min(kPiece, n_epj - o);
+        pack_epj(be + (size_t)o * lepj->stride, m, *lepj, he + 2 * (size_t)o);
+        CU(cudaMemcpyAsync(E.d_epj + 2 * ((size_t)epj_first + o), he + 2 * (size_t)o, (size_t)PB_EPJ_DEV_BYTES * m, cudaMemcpyHostToDevice, E.s_upload));
+    }
+    const char* bs = (const char*)spj;
+    for (int o = 0; o < n_spj; o += kPiece) {
+        const int m = std::min(kPiece, n_spj - o);
+        pack_spj(bs + (size_t)o * lspj->stride, m, *lspj, hs + 4 * (size_t)o);
+        CU(cudaMemcpyAsync(E.d_spj + 4 * ((size_t)spj_first + o), hs + 4 * (size_t)o, (size_t)PB_SPJ_DEV_BYTES * m, cudaMemcpyHostToDevice, E.s_upload));
+    }
+    E.prof.t_copy += now_s() - t0;
     CU(cudaEventRecord(E.ev_send1, E.s_upload));
     E.send_timed = true;
     E.prof.h2d_bytes += (long long)(nf4 * sizeof(float4));
@@ -921,7 +936,7 @@ int pb_publish_j(void* cuda_stream) {
         CU(cudaStreamWaitEvent(E.s_upload, ev, 0));
         CU(cudaEventDestroy(ev));
     }
-    CU(cudaEventRecord(E.ev_j_ready, E.s_upload));
+    CU(cudaEventRecord(E.ev_j_ready, E.s_upload)); E.j_epoch++;
     E.j_published = true;
     return PB_OK;
 }
@@ -931,7 +946,7 @@ int pb_upload_j(const void* epj, int n_epj, const pb_layout_epj* lepj,
     int rc = pb_reserve_j(n_epj, n_spj, nullptr, nullptr);
     if (rc != PB_OK) return rc;
     if ((rc = pb_upload_j_range(epj, 0, n_epj, lepj, spj, 0, n_spj, lspj)) != PB_OK) return rc;
-    CU(cudaEventRecord(E.ev_j_ready, E.s_upload));
+    CU(cudaEventRecord(E.ev_j_ready, E.s_upload)); E.j_epoch++;
     E.j_published = true;
     return PB_OK;
 }
@@ -1358,7 +1373,7 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
         CU(cudaMemcpyAsync(E.d_elem_map, E.h_elem_map, sizeof(int) * (size_t)n_elem, cudaMemcpyHostToDevice, E.s_upload));
         E.prof.h2d_bytes += (long long)(sizeof(int) * (size_t)n_elem);
     }
-    CU(cudaEventRecord(E.ev_j_ready, E.s_upload));        // dispatch streams wait for j AND tree
+    CU(cudaEventRecord(E.ev_j_ready, E.s_upload)); E.j_epoch++;        // dispatch streams wait for j AND tree
     E.prof.h2d_bytes += (long long)(sizeof(pb_tree_cell) * (size_t)n_cells + sizeof(pb_tree_group) * (size_t)n_groups);
     E.n_cells = n_cells; E.n_groups = n_groups; E.theta = theta;
     E.grp_n.resize(n_groups);
@@ -1437,7 +1452,8 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
     } else {
         for (int s = 0; s < n_slots; s++) if ((rc = ensure_walk_scratch(s)) != PB_OK) return rc;
     }
-    CU(cudaEventRecord(E.ev_fill, s0));                    // offsets (and, unless split, the lists) are in place
+    CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));          // j may have been published after the tree (the recommended order)
+    CU(cudaEventRecord(E.ev_fill, s0));                    // offsets (and, unless split, the lists) and this step's j are in place
     // pass 3: per batch of groups — plan tasks from the counts, force, reduce
     const char* ebase = (const char*)epi;
     const double tp0 = now_s();
