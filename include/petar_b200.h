@@ -127,6 +127,8 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "tree_batch" groups per force launch of pb_tree_force (default 1024).
  *   "tree_fill"  pb_tree_force writes the lists with 0 (default): one step-wide launch, 1: one launch per batch on
  *                the batch's stream (measured: no gain, the force kernels own the SMs).
+ *   "walk_ctas"  CTAs (4 warps each) of the tree-walk launches of pb_tree_upload / pb_tree_force, 1..2368 (default
+ *                2368 = every warp slot of the GPU: the walk is latency-bound; 592 costs 2.3 ms per step at N = 1e6).
  *   "min_slot_work"  a dispatch is not cut into per-stream sub-batches smaller than this many EP-equivalent
  *                interactions (n_epi * (n_epj + 2 n_spj)); default 0 = always "streams" (measured: 4e7 saves enqueue time
  *                at 8 ranks per node but costs more pipelining than it saves at 4).

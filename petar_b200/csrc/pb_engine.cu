@@ -143,6 +143,7 @@ struct Engine {
     int opt_tree_fill = 0;                                 // pb_tree_force: 0 one step-wide list-fill launch, 1 one per batch on the batch's stream
     long long j_epoch = 0;                                 // bumped whenever ev_j_ready is re-recorded
     long long opt_min_slot_work = 0;                       // > 0: a dispatch is not cut into sub-batches smaller than this many EP-equivalent interactions
+    int opt_walk_ctas = 148 * 16;                          // CTAs (4 warps each, one warp per i-group at a time) of the tree-walk launches
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
     long long nb_n_i = 0;
@@ -866,6 +867,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_fill")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_fill must be 0 or 1"); E.opt_tree_fill = (int)v; return PB_OK; }
     if (!strcmp(key, "min_slot_work")) { if (v < 0) return fail(PB_ERR_ARG, "min_slot_work must be >= 0"); E.opt_min_slot_work = v; return PB_OK; }
+    if (!strcmp(key, "walk_ctas")) { if (v < 1 || v > 148 * 16) return fail(PB_ERR_ARG, "walk_ctas must be in [1, 2368]"); E.opt_walk_ctas = (int)v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
     if (!strcmp(key, "lead"))    { if (v < 0 || v > 15) return fail(PB_ERR_ARG, "lead must be in [0, 15]"); E.opt_lead = (int)v; return PB_OK; }
@@ -1275,11 +1277,12 @@ int pb_correct_changeover(int n_i, void* ptcl_i, const pb_layout_corr* li,
 // ---- device-side interaction lists --------------------------------------------
 namespace {
 constexpr int kWalkCap  = 32768;       // frontier capacity per warp (cells of one tree level an i-group touches)
-constexpr int kWalkCtas = 148 * 4;     // 4 CTAs of 4 warps per SM (the walk is latency-bound); warps stride over the groups
+constexpr int kWalkCtasMax = 148 * 16; // scratch is sized for this many CTAs of 4 warps; option "walk_ctas" picks how many run
+#define kWalkCtas (E.opt_walk_ctas)
 
 int ensure_walk_scratch(int slot) {
     if (!E.d_walk_scratch[slot])
-        CU(cudaMalloc(&E.d_walk_scratch[slot], sizeof(int) * (size_t)kWalkCtas * 4 * 2 * kWalkCap));
+        CU(cudaMalloc(&E.d_walk_scratch[slot], sizeof(int) * (size_t)kWalkCtasMax * 4 * 2 * kWalkCap));
     if (!E.d_overflow) { CU(cudaMalloc(&E.d_overflow, sizeof(int))); CU(cudaMemset(E.d_overflow, 0, sizeof(int))); }
     return PB_OK;
 }
