@@ -214,13 +214,21 @@ __device__ __forceinline__ void ep_count_pairs(const EpTile& t, int p0, int p1,
         r2 = __ffma2_rn(dz, dz, r2);
         const bool h0 = r2.x < fmaxf(C.x, rsi2), h1 = r2.y < fmaxf(C.y, rsi2);
         cf = __fadd2_rn(cf, make_float2(h0 ? 1.f : 0.f, h1 ? 1.f : 0.f));
-        if (EMIT && (h0 || h1) && i_global != 0xffffffffu) {
-            // rare (well under 1 % of the tested pairs): one slot per hit from the launch-wide cursor
-            const unsigned int n = (unsigned int)h0 + (unsigned int)h1;
-            const unsigned int at = atomicAdd(prm.pair_cursor, n);
-            const unsigned long long hi = (unsigned long long)i_global << 32;
-            if (h0 && at < prm.pair_cap) prm.pairs[at] = hi | (unsigned int)jid[2 * p];
-            if (h1 && at + (unsigned int)h0 < prm.pair_cap) prm.pairs[at + (unsigned int)h0] = hi | (unsigned int)jid[2 * p + 1];
+        if (EMIT) {
+            // hits are rare (well under 1 % of the tested pairs); the warp is converged here, so one atomic per
+            // warp and pair step reserves the slots of all its hits
+            const bool e0 = h0 && i_global != 0xffffffffu, e1 = h1 && i_global != 0xffffffffu;
+            const unsigned m0 = __ballot_sync(0xffffffffu, e0), m1 = __ballot_sync(0xffffffffu, e1);
+            if (m0 | m1) {
+                const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(prm.pair_cursor, (unsigned int)(__popc(m0) + __popc(m1)));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned long long hi = (unsigned long long)i_global << 32;
+                const unsigned int at0 = base + __popc(m0 & below), at1 = base + __popc(m0) + __popc(m1 & below);
+                if (e0 && at0 < prm.pair_cap) prm.pairs[at0] = hi | (unsigned int)jid[2 * p];
+                if (e1 && at1 < prm.pair_cap) prm.pairs[at1] = hi | (unsigned int)jid[2 * p + 1];
+            }
         }
     }
 }

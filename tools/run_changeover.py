@@ -11,6 +11,8 @@ from petar_b200.types import PtclCorr
 from oracle import binding as ob
 
 n_star = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1000000
+for kv in sys.argv[2:]:                                      # library options, key=value
+    engine.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 batch, epi_src, prm, P = harness.kroupa_binary_case(n_star)
 out = {"n_particles": int(batch.n_epi_total), "candidate_pairs": float(batch.interactions()[0])}
 
