@@ -1112,6 +1112,35 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
 }
 
 // ---- direct-sum field query ---------------------------------------------------
+int pb_debug_plan(int n_walk, const int* n_epi, const int* n_epj, const int* n_spj, int n_streams_active,
+                  int* walks_out, int* tasks_out, int cap_tasks, int* iblocks_out, int cap_iblocks,
+                  int* n_iblocks, long long* n_part) {
+    if (n_walk < 0 || (n_walk && (!n_epi || !n_epj || !n_spj))) return fail(PB_ERR_ARG, "pb_debug_plan: bad argument");
+    static const int dummy = 0;
+    std::vector<WalkIn> win(n_walk);
+    for (int w = 0; w < n_walk; w++) win[w] = {&dummy, n_epi[w], &dummy, n_epj[w], &dummy, n_spj[w], nullptr, nullptr};
+    HostPlan hp;
+    plan_batch(win.data(), n_walk, false, std::max(1, n_streams_active), hp);
+    for (int w = 0; w < n_walk && walks_out; w++) {
+        const Walk& W = hp.walks[w];
+        int* o = walks_out + 6 * w;
+        o[0] = W.i_off; o[1] = W.ni; o[2] = W.ej_off; o[3] = W.nej; o[4] = W.sj_off; o[5] = W.nsj;
+    }
+    for (int t = 0; t < (int)hp.tasks.size() && t < cap_tasks && tasks_out; t++) {
+        const Task& T = hp.tasks[t];
+        int* o = tasks_out + 8 * t;
+        o[0] = T.walk; o[1] = T.i_first; o[2] = T.nib; o[3] = T.jsplit; o[4] = T.kind; o[5] = T.j_begin; o[6] = T.j_count; o[7] = T.part_base;
+    }
+    for (int b = 0; b < (int)hp.iblocks.size() && b < cap_iblocks && iblocks_out; b++) {
+        const IBlock& B = hp.iblocks[b];
+        int* o = iblocks_out + 5 * b;
+        o[0] = B.part_base; o[1] = B.n_chunks; o[2] = B.stride; o[3] = B.out_off; o[4] = B.n_valid;
+    }
+    if (n_iblocks) *n_iblocks = (int)hp.iblocks.size();
+    if (n_part) *n_part = (long long)hp.p.n_part;
+    return (int)hp.tasks.size();
+}
+
 int pb_retrieve_neighbors(long long* n_pairs, int* nb_off, int* nb_idx, long long cap) {
     if (!E.inited) return fail(PB_ERR_PROTOCOL, "pb_retrieve_neighbors before any dispatch");
     if (E.outstanding) return fail(PB_ERR_PROTOCOL, "pb_retrieve_neighbors while a dispatch is outstanding");

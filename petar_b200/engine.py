@@ -88,7 +88,7 @@ ABI_SYMBOLS = [
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
     "pb_field_at_points", "pb_dispatch_count_index", "pb_tree_upload", "pb_tree_force", "pb_tree_lists",
-    "pb_correct_changeover", "pb_retrieve_neighbors", "pb_tree_upload_let",
+    "pb_correct_changeover", "pb_retrieve_neighbors", "pb_tree_upload_let", "pb_debug_plan",
 ]
 
 _lib = None
@@ -134,6 +134,7 @@ def load():
     L.pb_tree_force.argtypes = [_vp, C.POINTER(LayoutEpi), _vp, C.POINTER(LayoutForce)]
     L.pb_tree_lists.argtypes = [_vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong]
     L.pb_correct_changeover.argtypes = [C.c_int, _vp, C.POINTER(LayoutCorr), C.c_int, _vp, C.POINTER(LayoutCorr), _vp, _vp, C.POINTER(CorrParams)]
+    L.pb_debug_plan.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     L.pb_retrieve_neighbors.argtypes = [C.POINTER(C.c_longlong), _vp, _vp, C.c_longlong]
     L.pb_field_at_points.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]
     _lib = L
@@ -237,6 +238,25 @@ class SearchNeighborCUDAMultiWalk:
         S = load_shim()
         return S.pb_shim_dispatch_count(self.my_rank, int(tag), int(n_walk), _ptr(epi), _ptr(n_epi), _ptr(id_epj), _ptr(n_epj),
                                         _ptr(epj), int(n_epj_tot), int(bool(send_flag)))
+
+
+def debug_plan(n_epi, n_epj, n_spj, n_streams_active=1):
+    """Host-only test hook: (walks[n_walk, 6], tasks[n_tasks, 8], iblocks[n_iblocks, 5], n_part) of the task
+    plan for one sub-batch with these list lengths (see pb_debug_plan in include/petar_b200.h)."""
+    L = load()
+    a = [np.ascontiguousarray(x, dtype=np.int32) for x in (n_epi, n_epj, n_spj)]
+    nw = len(a[0])
+    walks = np.zeros((nw, 6), dtype=np.int32)
+    nib, npart = C.c_int(0), C.c_longlong(0)
+    nt = L.pb_debug_plan(nw, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, int(n_streams_active),
+                         walks.ctypes.data, None, 0, None, 0, C.byref(nib), C.byref(npart))
+    if nt < 0:
+        check(nt, "pb_debug_plan")
+    tasks = np.zeros((max(nt, 1), 8), dtype=np.int32)
+    ibl = np.zeros((max(nib.value, 1), 5), dtype=np.int32)
+    L.pb_debug_plan(nw, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, int(n_streams_active),
+                    walks.ctypes.data, tasks.ctypes.data, nt, ibl.ctypes.data, nib.value, C.byref(nib), C.byref(npart))
+    return walks, tasks[:nt], ibl[:nib.value], npart.value
 
 
 def retrieve_neighbors(n_i):
