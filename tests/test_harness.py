@@ -113,3 +113,67 @@ def test_let_two_domains_reproduce_single_domain_lists():
         assert np.array_equal(f["n_ngb"], ref["n_ngb"])
         err = np.linalg.norm(f["acc"] - ref["acc"], axis=1) / np.linalg.norm(ref["acc"], axis=1)
         assert np.median(err) < 5e-4 and err.max() < 5e-2
+
+
+# ---- the exported tree (pb_tree_cell / pb_tree_group / elem_map) reproduces the host walk's lists ----------
+def _python_walk(cells, grp, theta, elem_map, n_cells):
+    """The opening rule of include/petar_b200.h ("device-side interaction lists"), breadth-first, in fp64."""
+    inv2 = 1.0 / (theta * theta)
+    ep, sp, frontier = [], [], [0]
+    while frontier:
+        nxt = []
+        for c in frontier:
+            cell = cells[c]
+            if cell["n"] == 0:
+                continue
+            d = np.maximum(np.maximum(grp["in_lo"] - cell["cm"], cell["cm"] - grp["in_hi"]), 0.0)
+            far = (d * d).sum() > cell["len"] * cell["len"] * inv2
+            touch = (np.all(grp["out_lo"] <= cell["in_hi"]) and np.all(grp["out_hi"] >= cell["in_lo"])) or \
+                    (np.all(cell["out_lo"] <= grp["in_hi"]) and np.all(cell["out_hi"] >= grp["in_lo"]))
+            if far and not touch:
+                sp.append(c)
+            elif cell["leaf"]:
+                for k in range(cell["first"], cell["first"] + cell["n"]):
+                    m = k if elem_map is None else int(elem_map[k])
+                    if m >= 0:
+                        ep.append(m)
+                    else:
+                        sp.append(n_cells + ~m)
+            else:
+                nxt.extend(int(x) for x in cell["child"] if x >= 0)
+        frontier = nxt
+    return np.sort(ep), np.sort(sp)
+
+
+def _check_exported_tree(batch, elem_map):
+    cells, groups = batch.tree.export_tree()
+    assert len(groups) == batch.n_walk
+    rng = np.random.default_rng(0)
+    for g in rng.choice(batch.n_walk, min(12, batch.n_walk), replace=False):
+        ep, sp = _python_walk(cells, groups[g], 0.3, elem_map, len(cells))
+        assert np.array_equal(ep, np.sort(batch.id_epj[batch.ej_off[g]:batch.ej_off[g + 1]])), f"EP list of group {g}"
+        assert np.array_equal(sp, np.sort(batch.id_spj[batch.sj_off[g]:batch.sj_off[g + 1]])), f"SP list of group {g}"
+    return cells
+
+
+def test_exported_tree_single_domain():
+    batch, _, prm, _ = hz.plummer_case(6000)
+    cells = _check_exported_tree(batch, None)
+    assert cells["n_let_sp"].sum() == 0
+    assert np.array_equal(batch.tree.export_elem_map(), np.arange(len(batch.epj)))       # identity without LET
+
+
+def test_exported_tree_with_local_essential_tree():
+    mass, pos, vel = hz.make_plummer(8000)
+    prm = hz.petar_auto_params(mass, vel)
+    _, _, rs = hz.particle_rout_rsearch(mass, vel, prm)
+    a = pos[:, 0] < np.median(pos[:, 0])
+    ta, tb = hz.TreeHandle(pos[a], mass[a], rs[a]), hz.TreeHandle(pos[~a], mass[~a], rs[~a])
+    ep_idx, sp = tb.make_let(ta.local_boxes())
+    let = dict(pos=pos[~a][ep_idx], mass=mass[~a][ep_idx], rsearch=rs[~a][ep_idx], spj=sp)
+    batch, _ = hz.build_walk_batch(pos[a], mass[a], rs[a], let=let)
+    em = batch.tree.export_elem_map()
+    cells = _check_exported_tree(batch, em)
+    assert (em < 0).sum() == len(sp) == cells["n_let_sp"].sum() and len(batch.spj) == len(cells) + len(sp)
+    assert np.array_equal(np.sort(em[em >= 0]), np.arange(len(batch.epj)))                # every EP exactly once
+    assert np.array_equal(np.sort(~em[em < 0]), np.arange(len(sp)))                       # every LET SP exactly once
