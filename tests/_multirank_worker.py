@@ -53,6 +53,16 @@ def main():
         s = b.id_spj[b.sj_off[w]:b.sj_off[w + 1]]
         assert abs(b.epj["mass"][e].sum() + b.spj["mass"][s].sum() - mtot) < 1e-12
 
+    # the tree handed to the device-side walk (pb_tree_upload_let): walking it in Python with the element map must
+    # give this rank's lists in STORE order (local particles first, LET entries where the all-to-all put them)
+    from test_harness import _python_walk
+    cells, groups, em = wl["tree_cells"], wl["tree_groups"], wl["elem_map"]
+    assert (em < 0).sum() == wl["n_let_sp"] and np.array_equal(np.sort(em[em >= 0]), np.arange(len(b.epj)))
+    for g in np.random.default_rng(rank).choice(b.n_walk, min(6, b.n_walk), replace=False):
+        ep, sp = _python_walk(cells, groups[g], 0.3, em, len(cells))
+        assert np.array_equal(ep, np.sort(b.id_epj[b.ej_off[g]:b.ej_off[g + 1]])), f"EP list of group {g}"
+        assert np.array_equal(sp, np.sort(b.id_spj[b.sj_off[g]:b.sj_off[g + 1]])), f"SP list of group {g}"
+
     f = ob.walks_index(b, prm["eps"], prm["r_out"], prm["G"])
     one, src = hz.build_walk_batch(pos, mass, rs)
     fo = ob.walks_index(one, prm["eps"], prm["r_out"], prm["G"])
