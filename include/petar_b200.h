@@ -127,6 +127,10 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "tree_batch" groups per force launch of pb_tree_force (default 1024).
  *   "tree_fill"  pb_tree_force writes the lists with 0 (default): one step-wide launch, 1: one launch per batch on
  *                the batch's stream (measured: no gain, the force kernels own the SMs).
+ *   "tree_spec"  1 (default): from the second tree step on, pb_tree_upload reserves list space from the previous
+ *                step's list lengths (+12.5 % + 64 entries) and fills the lists in ONE walk pass, while the host still
+ *                packs j; a list that outgrows its reservation is detected and pb_tree_force redoes the exact
+ *                two-pass fill.  0: always count, then fill.
  *   "walk_ctas"  CTAs (4 warps each) of the tree-walk launches of pb_tree_upload / pb_tree_force, 1..2368 (default
  *                2368 = every warp slot of the GPU: the walk is latency-bound; 592 costs 2.3 ms per step at N = 1e6).
  *   "min_slot_work"  a dispatch is not cut into per-stream sub-batches smaller than this many EP-equivalent

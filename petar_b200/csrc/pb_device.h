@@ -106,7 +106,7 @@ cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* gro
                               const int* elem_map = nullptr, int n_cells = 0);
 cudaError_t launch_walk_fill(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
                              const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow,
-                             const int* elem_map = nullptr, int n_cells = 0);
+                             const int* elem_map = nullptr, int n_cells = 0, const int2* caps = nullptr, int2* counts = nullptr);
 
 // changeover correction (pb_corr.cu): the fields of one neighbour / one corrected particle, fp64
 struct CorrJ { double x, y, z, mass, r_in, r_out, mass_bk, status; long long id; };       // 72 B

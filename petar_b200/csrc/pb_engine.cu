@@ -144,6 +144,9 @@ struct Engine {
     int opt_tree_fill = 0;                                 // pb_tree_force: 0 one step-wide list-fill launch, 1 one per batch on the batch's stream
     long long j_epoch = 0;                                 // bumped whenever ev_j_ready is re-recorded
     long long opt_min_slot_work = 0;                       // > 0: a dispatch is not cut into sub-batches smaller than this many EP-equivalent interactions
+    int opt_tree_spec = 1;                                 // reserve list space from the previous step's lengths and fill in ONE walk pass
+    std::vector<int2> prev_counts;                         // list lengths of the previous pb_tree_force
+    bool spec_pending = false; int2* d_tree_caps = nullptr; size_t cap_tree_caps = 0;
     int opt_walk_ctas = 148 * 16;                          // CTAs (4 warps each, one warp per i-group at a time) of the tree-walk launches
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
@@ -873,6 +876,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_fill")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_fill must be 0 or 1"); E.opt_tree_fill = (int)v; return PB_OK; }
     if (!strcmp(key, "min_slot_work")) { if (v < 0) return fail(PB_ERR_ARG, "min_slot_work must be >= 0"); E.opt_min_slot_work = v; return PB_OK; }
+    if (!strcmp(key, "tree_spec")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_spec must be 0 or 1"); E.opt_tree_spec = (int)v; return PB_OK; }
     if (!strcmp(key, "walk_ctas")) { if (v < 1 || v > 148 * 16) return fail(PB_ERR_ARG, "walk_ctas must be in [1, 2368]"); E.opt_walk_ctas = (int)v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
@@ -1318,7 +1322,7 @@ constexpr int kWalkCtasMax = 148 * 16; // scratch is sized for this many CTAs of
 int ensure_walk_scratch(int slot) {
     if (!E.d_walk_scratch[slot])
         CU(cudaMalloc(&E.d_walk_scratch[slot], sizeof(int) * (size_t)kWalkCtasMax * 4 * 2 * kWalkCap));
-    if (!E.d_overflow) { CU(cudaMalloc(&E.d_overflow, sizeof(int))); CU(cudaMemset(E.d_overflow, 0, sizeof(int))); }
+    if (!E.d_overflow) { CU(cudaMalloc(&E.d_overflow, 2 * sizeof(int))); CU(cudaMemset(E.d_overflow, 0, 2 * sizeof(int))); }   // [0] frontier, [1] list reservation
     return PB_OK;
 }
 
@@ -1428,14 +1432,49 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
             E.cap_counts_p = E.cap_counts;
             CU(cudaMallocHost(&E.h_counts_p, sizeof(int2) * E.cap_counts_p));
         }
-        if (!E.h_over_p) CU(cudaMallocHost(&E.h_over_p, sizeof(int)));
+        if (!E.h_over_p) CU(cudaMallocHost(&E.h_over_p, 2 * sizeof(int)));
         const double theta_inv2 = theta > 0.0 ? 1.0 / (theta * theta) : 1e300;
         cudaStream_t s0 = E.slots[0].stream;
         CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));
-        CU(launch_walk_count(s0, E.d_cells, E.d_groups, 0, n_groups, theta_inv2, E.d_counts, E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow,
-                             E.has_elem_map ? E.d_elem_map : nullptr, n_cells));
+        E.spec_pending = false;
+        if (E.opt_tree_spec && (int)E.prev_counts.size() == n_groups) {
+            // Speculative single pass: the lists of consecutive tree steps have nearly the same lengths, so space is
+            // reserved from the previous step's (+12.5 % + 64) and the walk fills the lists right away — while the host
+            // is still packing j.  The true lengths come back with it; a list that outgrew its reservation is detected
+            // (nothing is written past it) and pb_tree_force then falls back to the exact two-pass fill.
+            E.h_tree_off.resize(n_groups);
+            std::vector<int2> caps(n_groups);
+            size_t tot_e = 0, tot_s = 0;
+            for (int g = 0; g < n_groups; g++) {
+                const size_t ce = align_up((size_t)E.prev_counts[g].x + E.prev_counts[g].x / 8 + 64, 4);
+                const size_t cs = align_up((size_t)E.prev_counts[g].y + E.prev_counts[g].y / 8 + 64, 4);
+                E.h_tree_off[g] = make_int2((int)tot_e, (int)tot_s);
+                caps[g] = make_int2((int)ce, (int)cs);
+                tot_e += ce; tot_s += cs;
+            }
+            if (tot_e < (1ull << 31) && tot_s < (1ull << 31)) {
+                if (tot_e > E.cap_tree_ide) { if (E.d_tree_ide) CU(cudaFree(E.d_tree_ide)); E.cap_tree_ide = tot_e + tot_e / 8 + 4096; CU(cudaMalloc(&E.d_tree_ide, sizeof(int) * E.cap_tree_ide)); }
+                if (tot_s > E.cap_tree_ids) { if (E.d_tree_ids) CU(cudaFree(E.d_tree_ids)); E.cap_tree_ids = tot_s + tot_s / 8 + 4096; CU(cudaMalloc(&E.d_tree_ids, sizeof(int) * E.cap_tree_ids)); }
+                if (!E.d_tree_off) CU(cudaMalloc(&E.d_tree_off, sizeof(int2) * E.cap_counts));
+                if ((size_t)n_groups > E.cap_tree_caps) {
+                    if (E.d_tree_caps) CU(cudaFree(E.d_tree_caps));
+                    E.cap_tree_caps = E.cap_counts;
+                    CU(cudaMalloc(&E.d_tree_caps, sizeof(int2) * E.cap_tree_caps));
+                }
+                CU(cudaMemcpyAsync(E.d_tree_off, E.h_tree_off.data(), sizeof(int2) * (size_t)n_groups, cudaMemcpyHostToDevice, s0));
+                CU(cudaMemcpyAsync(E.d_tree_caps, caps.data(), sizeof(int2) * (size_t)n_groups, cudaMemcpyHostToDevice, s0));
+                CU(cudaMemsetAsync(E.d_overflow + 1, 0, sizeof(int), s0));
+                CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, n_groups, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
+                                    E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, n_cells,
+                                    E.d_tree_caps, E.d_counts));
+                E.spec_pending = true;
+            }
+        }
+        if (!E.spec_pending)
+            CU(launch_walk_count(s0, E.d_cells, E.d_groups, 0, n_groups, theta_inv2, E.d_counts, E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow,
+                                 E.has_elem_map ? E.d_elem_map : nullptr, n_cells));
         CU(cudaMemcpyAsync(E.h_counts_p, E.d_counts, sizeof(int2) * (size_t)n_groups, cudaMemcpyDeviceToHost, s0));
-        CU(cudaMemcpyAsync(E.h_over_p, E.d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s0));
+        CU(cudaMemcpyAsync(E.h_over_p, E.d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, s0));
         CU(cudaEventRecord(E.ev_count, s0));
         E.count_pending = true;
         E.prof.n_kernel_launch += 1;
@@ -1471,29 +1510,38 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
         return fail(PB_ERR_PROTOCOL, "pb_tree_force: call pb_tree_upload for this step first");
     }
 
+    const bool lists_ready = E.spec_pending && E.h_over_p[1] == 0;     // the speculative pass already wrote them
+    E.spec_pending = false;
+    E.prev_counts = E.h_counts;
+    if (lists_ready) {
+        CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));
+        CU(cudaEventRecord(E.ev_fill, s0));
+    }
     // pass 2: one launch writes every group's lists into a step-wide device buffer
-    E.h_tree_off.resize(E.n_groups);
-    size_t tot_e = 0, tot_s = 0;
-    for (int g = 0; g < E.n_groups; g++) {
-        E.h_tree_off[g] = make_int2((int)tot_e, (int)tot_s);
-        tot_e += align_up((size_t)E.h_counts[g].x, 4);
-        tot_s += align_up((size_t)E.h_counts[g].y, 4);
+    const bool split_fill = !lists_ready && E.opt_tree_fill == 1;   // fill each batch's lists on the batch's own stream, just ahead of its force launch
+    if (!lists_ready) {
+        E.h_tree_off.resize(E.n_groups);
+        size_t tot_e = 0, tot_s = 0;
+        for (int g = 0; g < E.n_groups; g++) {
+            E.h_tree_off[g] = make_int2((int)tot_e, (int)tot_s);
+            tot_e += align_up((size_t)E.h_counts[g].x, 4);
+            tot_s += align_up((size_t)E.h_counts[g].y, 4);
+        }
+        if (tot_e >= (1ull << 31) || tot_s >= (1ull << 31)) return fail(PB_ERR_ARG, "pb_tree_force: more than 2^31 list entries in one step");
+        if (tot_e > E.cap_tree_ide) { if (E.d_tree_ide) CU(cudaFree(E.d_tree_ide)); E.cap_tree_ide = tot_e + tot_e / 8 + 4096; CU(cudaMalloc(&E.d_tree_ide, sizeof(int) * E.cap_tree_ide)); }
+        if (tot_s > E.cap_tree_ids) { if (E.d_tree_ids) CU(cudaFree(E.d_tree_ids)); E.cap_tree_ids = tot_s + tot_s / 8 + 4096; CU(cudaMalloc(&E.d_tree_ids, sizeof(int) * E.cap_tree_ids)); }
+        if (!E.d_tree_off) CU(cudaMalloc(&E.d_tree_off, sizeof(int2) * E.cap_counts));   // freed whenever d_counts is re-sized
+        CU(cudaMemcpyAsync(E.d_tree_off, E.h_tree_off.data(), sizeof(int2) * (size_t)E.n_groups, cudaMemcpyHostToDevice, s0));
+        if (!split_fill) {
+            CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, E.n_groups, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
+                                E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells));
+            E.prof.n_kernel_launch += 1;
+        } else {
+            for (int s = 0; s < n_slots; s++) if ((rc = ensure_walk_scratch(s)) != PB_OK) return rc;
+        }
+        CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));          // j may have been published after the tree (the recommended order)
+        CU(cudaEventRecord(E.ev_fill, s0));                    // offsets (and, unless split, the lists) and this step's j are in place
     }
-    if (tot_e >= (1ull << 31) || tot_s >= (1ull << 31)) return fail(PB_ERR_ARG, "pb_tree_force: more than 2^31 list entries in one step");
-    if (tot_e > E.cap_tree_ide) { if (E.d_tree_ide) CU(cudaFree(E.d_tree_ide)); E.cap_tree_ide = tot_e + tot_e / 8 + 4096; CU(cudaMalloc(&E.d_tree_ide, sizeof(int) * E.cap_tree_ide)); }
-    if (tot_s > E.cap_tree_ids) { if (E.d_tree_ids) CU(cudaFree(E.d_tree_ids)); E.cap_tree_ids = tot_s + tot_s / 8 + 4096; CU(cudaMalloc(&E.d_tree_ids, sizeof(int) * E.cap_tree_ids)); }
-    if (!E.d_tree_off) CU(cudaMalloc(&E.d_tree_off, sizeof(int2) * E.cap_counts));   // freed whenever d_counts is re-sized
-    CU(cudaMemcpyAsync(E.d_tree_off, E.h_tree_off.data(), sizeof(int2) * (size_t)E.n_groups, cudaMemcpyHostToDevice, s0));
-    const bool split_fill = E.opt_tree_fill == 1;          // fill each batch's lists on the batch's own stream, just ahead of its force launch
-    if (!split_fill) {
-        CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, E.n_groups, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
-                            E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells));
-        E.prof.n_kernel_launch += 1;
-    } else {
-        for (int s = 0; s < n_slots; s++) if ((rc = ensure_walk_scratch(s)) != PB_OK) return rc;
-    }
-    CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));          // j may have been published after the tree (the recommended order)
-    CU(cudaEventRecord(E.ev_fill, s0));                    // offsets (and, unless split, the lists) and this step's j are in place
     // pass 3: per batch of groups — plan tasks from the counts, force, reduce
     const char* ebase = (const char*)epi;
     const double tp0 = now_s();

@@ -48,14 +48,16 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 
 } // namespace
 
-// FILL = false: counts[g] = {n_ep, n_sp}.  FILL = true: ids written at id_e + offs[g].x / id_s + offs[g].y.
+// FILL = false: counts[g] = {n_ep, n_sp}.  FILL = true: ids written at id_e + offs[g].x / id_s + offs[g].y; with `caps`
+// (speculative fill: offsets reserved from the previous step's list lengths) nothing is written past a group's
+// reservation, the true lengths still go to counts[g], and overflow[1] is raised if any list did not fit.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restrict__ groups,
             int g0, int n_groups, double theta_inv2,
             int2* __restrict__ counts, const int2* __restrict__ offs, int* __restrict__ id_e, int* __restrict__ id_s,
             int* __restrict__ scratch, int cap, int* __restrict__ overflow,
-            const int* __restrict__ elem_map, int n_cells)
+            const int* __restrict__ elem_map, int n_cells, const int2* __restrict__ caps)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -70,7 +72,9 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
         __syncwarp();
         int ncur = 1, nep = 0, nsp = 0;
         int* oe = nullptr; int* os = nullptr;
+        int cap_e = 0x7fffffff, cap_s = 0x7fffffff;   // speculative fill: room reserved from the previous step's lengths
         if (FILL) { const int2 o = offs[g0 + g]; oe = id_e + o.x; os = id_s + o.y; }
+        if (FILL && caps) { const int2 c = caps[g0 + g]; cap_e = c.x; cap_s = c.y; }
         while (ncur > 0) {
             int nnext = 0;
             for (int base = 0; base < ncur; base += 32) {
@@ -97,7 +101,10 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
                 }
                 // superparticles
                 const unsigned m1 = __ballot_sync(0xffffffffu, cls == 1);
-                if (FILL && cls == 1) os[nsp + __popc(m1 & ((1u << lane) - 1u))] = cell;
+                if (FILL && cls == 1) {
+                    const int at = nsp + __popc(m1 & ((1u << lane) - 1u));
+                    if (at < cap_s) os[at] = cell;
+                }
                 nsp += __popc(m1);
                 // opened leaves: element ranges -> EP list (and, with a local essential tree, the superparticles
                 // received from other domains -> SP list; elem_map says where each sorted element is stored)
@@ -105,7 +112,7 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
                 const int off_e = warp_excl_scan(cls == 2 ? n - nls : 0, lane, tot);
                 if (elem_map == nullptr) {
                     if (FILL && cls == 2)
-                        for (int k = 0; k < n; k++) oe[nep + off_e + k] = first + k;
+                        for (int k = 0; k < n; k++) if (nep + off_e + k < cap_e) oe[nep + off_e + k] = first + k;
                 } else {
                     int tot_s;
                     const int off_s = warp_excl_scan(cls == 2 ? nls : 0, lane, tot_s);
@@ -113,8 +120,8 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
                         int ke = nep + off_e, ks = nsp + off_s;
                         for (int k = 0; k < n; k++) {
                             const int m = elem_map[first + k];
-                            if (m >= 0) oe[ke++] = m;
-                            else        os[ks++] = n_cells + ~m;
+                            if (m >= 0) { if (ke < cap_e) oe[ke] = m; ke++; }
+                            else        { if (ks < cap_s) os[ks] = n_cells + ~m; ks++; }
                         }
                     }
                     nsp += tot_s;
@@ -139,7 +146,10 @@ walk_kernel(const pb_tree_cell* __restrict__ cells, const pb_tree_group* __restr
             int* t = cur; cur = nxt; nxt = t;
             ncur = nnext;
         }
-        if (!FILL && lane == 0) counts[g0 + g] = make_int2(nep, nsp);
+        if (lane == 0) {
+            if (counts) counts[g0 + g] = make_int2(nep, nsp);
+            if (FILL && caps && (nep > cap_e || nsp > cap_s)) atomicExch(overflow + 1, 1);   // a list outgrew its reservation
+        }
         __syncwarp();
     }
 }
@@ -148,16 +158,16 @@ cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* gro
                               int2* counts, int* scratch, int cap, int n_ctas, int* overflow, const int* elem_map, int n_cells) {
     if (n_groups <= 0) return cudaSuccess;
     walk_kernel<false><<<n_ctas, 128, 0, s>>>((const pb_tree_cell*)cells, (const pb_tree_group*)groups, g0, n_groups, theta_inv2,
-                                              counts, nullptr, nullptr, nullptr, scratch, cap, overflow, elem_map, n_cells);
+                                              counts, nullptr, nullptr, nullptr, scratch, cap, overflow, elem_map, n_cells, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_walk_fill(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
                              const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow,
-                             const int* elem_map, int n_cells) {
+                             const int* elem_map, int n_cells, const int2* caps, int2* counts) {
     if (n_groups <= 0) return cudaSuccess;
     walk_kernel<true><<<n_ctas, 128, 0, s>>>((const pb_tree_cell*)cells, (const pb_tree_group*)groups, g0, n_groups, theta_inv2,
-                                             nullptr, offs, id_e, id_s, scratch, cap, overflow, elem_map, n_cells);
+                                             counts, offs, id_e, id_s, scratch, cap, overflow, elem_map, n_cells, caps);
     return cudaGetLastError();
 }
 

@@ -136,3 +136,23 @@ def test_device_walk_with_local_essential_tree():
     f2 = engine.tree_force(shuffled, cells, groups, prm["eps"], prm["r_out"], prm["G"], elem_map=emap_store)
     assert np.array_equal(f2["n_ngb"], f["n_ngb"])
     assert np.abs(f2["acc"] - f["acc"]).max() <= 2e-6 * np.abs(f["acc"]).max()
+
+
+def test_speculative_single_pass_fill_and_its_fallback():
+    """From the second tree step on, list space is reserved from the previous step's lengths and the walk fills the
+    lists in ONE pass; a list that outgrows its reservation must be caught and redone exactly."""
+    batch, prm, cells, groups = _case("kroupa_binaries", 20000)
+    engine.set_option("tree_spec", 0)
+    ref = {th: engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=th).copy() for th in (0.5, 0.3)}
+    engine.set_option("tree_spec", 1)
+    f1 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.5).copy()     # no history yet or stale: exact path
+    f2 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.5).copy()     # speculative, fits
+    ne2, ns2, ide2, ids2 = engine.tree_lists(len(groups))
+    assert f1.tobytes() == ref[0.5].tobytes() and f2.tobytes() == ref[0.5].tobytes()
+    f3 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.3).copy()     # lists ~2x longer: reservation overflows
+    ne3, ns3, ide3, ids3 = engine.tree_lists(len(groups))
+    assert ns3.sum() > 1.3 * ns2.sum()
+    assert f3.tobytes() == ref[0.3].tobytes()
+    f4 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.3).copy()     # speculative again
+    ne4, ns4, ide4, ids4 = engine.tree_lists(len(groups))
+    assert f4.tobytes() == ref[0.3].tobytes() and np.array_equal(ne4, ne3) and np.array_equal(ide4, ide3) and np.array_equal(ids4, ids3)
