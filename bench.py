@@ -367,7 +367,9 @@ def main():
     if not args.no_device_walk:
         try:
             if stepper is None:
-                cells, groups = batch.tree.export_tree()
+                # the tree is written straight into the library's pinned staging buffers, as a converter from FDPS's
+                # cells would do it
+                cells, groups = batch.tree.export_tree(out=engine.tree_stage(batch.tree.n_nodes, batch.n_walk))
                 dw_step = lambda: engine.tree_force(batch, cells, groups, eps, r_out, G, force=force)
             else:
                 cells, groups = wl["tree_cells"], wl["tree_groups"]

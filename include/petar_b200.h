@@ -221,6 +221,10 @@ typedef struct pb_tree_group {         /* 104 B: one i-group ("walk") */
 int  pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta);
 int  pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta,
                         const int* elem_map, int n_elem);
+/* Optional: pinned staging for the tree.  Returns buffers for n_cells cells and n_groups groups that stay valid until
+ * the next pb_tree_stage / pb_finalize; write the tree into them (e.g. while converting FDPS's cells) and pass these
+ * very pointers to pb_tree_upload / pb_tree_upload_let, which then skip their own 176 B-per-cell staging copy. */
+int  pb_tree_stage(int n_cells, int n_groups, pb_tree_cell** cells, pb_tree_group** groups);
 /* Forces on all i-particles, given in group order (group 0's particles first, ...); ASSIGNS
  * force[k].{acc,pot,n_ngb}.  Synchronous.  Both arrays are contiguous with the given layouts. */
 int  pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const pb_layout_force* lforce);

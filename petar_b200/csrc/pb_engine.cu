@@ -1354,6 +1354,24 @@ int tree_finish_slot(Slot& S, char* force, const pb_layout_force& L, size_t i_fi
 }
 } // namespace
 
+int pb_tree_stage(int n_cells, int n_groups, pb_tree_cell** cells, pb_tree_group** groups) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    if (n_cells < 0 || n_groups < 0 || !cells || !groups) return fail(PB_ERR_ARG, "pb_tree_stage: bad argument");
+    const size_t bc = sizeof(pb_tree_cell) * (size_t)n_cells, bg = sizeof(pb_tree_group) * (size_t)n_groups;
+    if (bc + bg > E.cap_tstage) {
+        CU(cudaStreamSynchronize(E.s_upload));             // a previous tree may still be travelling from the old buffer
+        if (E.h_tstage) CU(cudaFreeHost(E.h_tstage));
+        E.h_tstage = nullptr; E.cap_tstage = 0;
+        const size_t cap = bc + bg + (bc + bg) / 4 + 4096;
+        CU(cudaMallocHost(&E.h_tstage, cap));
+        E.cap_tstage = cap;
+    }
+    *cells = (pb_tree_cell*)E.h_tstage;
+    *groups = (pb_tree_group*)(E.h_tstage + bc);
+    return PB_OK;
+}
+
 int pb_tree_upload(const pb_tree_cell* cells, int n_cells, const pb_tree_group* groups, int n_groups, double theta) {
     return pb_tree_upload_let(cells, n_cells, groups, n_groups, theta, nullptr, 0);
 }
@@ -1392,7 +1410,8 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
         E.cap_tstage = bc + bg + (bc + bg) / 4;
         CU(cudaMallocHost(&E.h_tstage, E.cap_tstage));
     }
-    {
+    const bool staged = E.h_tstage && (const char*)cells == E.h_tstage && (const char*)groups == E.h_tstage + bc;   // pb_tree_stage buffers
+    if (!staged) {
         const size_t chunk = 1 << 20;
         const long long nchunk = (long long)((bc + chunk - 1) / chunk);
 #pragma omp parallel for schedule(static)

@@ -88,7 +88,7 @@ ABI_SYMBOLS = [
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
     "pb_field_at_points", "pb_dispatch_count_index", "pb_tree_upload", "pb_tree_force", "pb_tree_lists",
-    "pb_correct_changeover", "pb_retrieve_neighbors", "pb_tree_upload_let", "pb_debug_plan",
+    "pb_correct_changeover", "pb_retrieve_neighbors", "pb_tree_upload_let", "pb_debug_plan", "pb_tree_stage",
 ]
 
 _lib = None
@@ -130,6 +130,7 @@ def load():
     L.pb_pack_epj_host_indexed.argtypes = [_vp, _vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_spj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutSpj), _vp]
     L.pb_tree_upload.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double]
+    L.pb_tree_stage.argtypes = [C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]
     L.pb_tree_upload_let.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double, _vp, C.c_int]
     L.pb_tree_force.argtypes = [_vp, C.POINTER(LayoutEpi), _vp, C.POINTER(LayoutForce)]
     L.pb_tree_lists.argtypes = [_vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong]
@@ -337,6 +338,17 @@ def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, uploa
                             batch.spj.ctypes.data, len(batch.spj), C.byref(LAYOUT_SPJ)), "pb_upload_j")
     check(L.pb_tree_force(batch.epi.ctypes.data, C.byref(LAYOUT_EPI), f.ctypes.data, C.byref(LAYOUT_FORCE)), "pb_tree_force")
     return f
+
+
+def tree_stage(n_cells, n_groups):
+    """(cells, groups) numpy views of the library's pinned tree staging buffers (pb_tree_stage): write the tree into
+    them and hand them to tree_force / pb_tree_upload, which then skips its own staging copy."""
+    from .types import TreeCell, TreeGroup
+    pc, pg = _vp(0), _vp(0)
+    check(load().pb_tree_stage(int(n_cells), int(n_groups), C.byref(pc), C.byref(pg)), "pb_tree_stage")
+    cells = np.frombuffer((C.c_char * (TreeCell.itemsize * n_cells)).from_address(pc.value), dtype=TreeCell) if n_cells else np.zeros(0, TreeCell)
+    groups = np.frombuffer((C.c_char * (TreeGroup.itemsize * n_groups)).from_address(pg.value), dtype=TreeGroup) if n_groups else np.zeros(0, TreeGroup)
+    return cells, groups
 
 
 def tree_lists(n_groups):

@@ -158,12 +158,13 @@ class TreeHandle:
                         ej_off.ctypes.data, sj_off.ctypes.data, id_epj.ctypes.data, id_spj.ctypes.data)
         return epj_src, epi_src, spj, i_off, ej_off, sj_off, id_epj, id_spj
 
-    def export_tree(self):
+    def export_tree(self, out=None):
         """(cells, groups) in the layout of pb_tree_cell / pb_tree_group, for the device-side list
-        builder.  A tree with LET elements also needs :meth:`export_elem_map`."""
+        builder.  A tree with LET elements also needs :meth:`export_elem_map`.  `out` = (cells, groups)
+        arrays to write into (e.g. engine.tree_stage's pinned buffers)."""
         from .types import TreeCell, TreeGroup
-        cells = np.zeros(self.n_nodes, dtype=TreeCell)
-        groups = np.zeros(self.n_walk, dtype=TreeGroup)
+        cells, groups = out if out is not None else (np.zeros(self.n_nodes, dtype=TreeCell), np.zeros(self.n_walk, dtype=TreeGroup))
+        assert len(cells) == self.n_nodes and len(groups) == self.n_walk and cells.dtype == TreeCell and groups.dtype == TreeGroup
         lib().hz_export_tree(self.h, cells.ctypes.data, groups.ctypes.data)
         return cells, groups
 

@@ -156,3 +156,12 @@ def test_speculative_single_pass_fill_and_its_fallback():
     f4 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.3).copy()     # speculative again
     ne4, ns4, ide4, ids4 = engine.tree_lists(len(groups))
     assert f4.tobytes() == ref[0.3].tobytes() and np.array_equal(ne4, ne3) and np.array_equal(ide4, ide3) and np.array_equal(ids4, ids3)
+
+
+def test_tree_from_pinned_staging_buffers():
+    batch, prm, cells, groups = _case("plummer", 20000)
+    f0 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"]).copy()
+    sc, sg = batch.tree.export_tree(out=engine.tree_stage(len(cells), len(groups)))
+    assert sc.tobytes() == cells.tobytes() and sg.tobytes() == groups.tobytes()
+    f1 = engine.tree_force(batch, sc, sg, prm["eps"], prm["r_out"], prm["G"]).copy()
+    assert f1.tobytes() == f0.tobytes()

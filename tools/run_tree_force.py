@@ -8,7 +8,8 @@ from petar_b200 import engine, harness as hz
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 batch, _, prm, _ = hz.kroupa_binary_case(n)
-cells, groups = batch.tree.export_tree()
+cells, groups = batch.tree.export_tree(out=engine.tree_stage(batch.tree.n_nodes, batch.n_walk)) if "--no-stage" not in sys.argv else batch.tree.export_tree()
+sys.argv = [a for a in sys.argv if a != "--no-stage"]
 sweeps = [a for a in sys.argv[3:]] or [""]
 for sw in sweeps:
     for kv in filter(None, sw.split(",")):
