@@ -211,6 +211,10 @@ class DomainStepper:
         """The same tree step with the interaction lists built on the GPU: the global tree
         (local + LET elements) is uploaded instead of per-walk index lists; j travels as in :meth:`step`."""
         b, L, wl = self.batch, self.L, self.wl
+        if not getattr(self, "_tree_staged", False):          # the tree lives in the library's pinned staging buffers
+            sc, sg = engine.tree_stage(len(wl["tree_cells"]), len(wl["tree_groups"]))
+            sc[:] = wl["tree_cells"]; sg[:] = wl["tree_groups"]
+            wl["tree_cells"], wl["tree_groups"], self._tree_staged = sc, sg, True
         cells, groups, em = wl["tree_cells"], wl["tree_groups"], wl["elem_map"]
         engine.check(L.pb_set_params(self.prm["eps"] ** 2, self.prm["r_out"] ** 2, self.prm["G"]), "pb_set_params")
         engine.check(L.pb_tree_upload_let(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta),
