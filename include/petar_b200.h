@@ -124,7 +124,7 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *                or 3 (80 registers).
  *   "lead"       the first of a dispatch's per-stream sub-batches is 1/(1+lead) the size of the others
  *                (the GPU idles until its copy lands): 0 = equal sizes, 3 (default), up to 15.
- *   "tree_batch" groups per force launch of pb_tree_force (default 1024).
+ *   "tree_batch" groups per force launch of pb_tree_force (default 256: 33.7 ms per step at N = 1e6 against 40 ms with 1024).
  *   "tree_fill"  pb_tree_force writes the lists with 0 (default): one step-wide launch, 1: one launch per batch on
  *                the batch's stream (measured: no gain, the force kernels own the SMs).
  *   "tree_spec"  1 (default): from the second tree step on, pb_tree_upload reserves list space from the previous

@@ -140,7 +140,7 @@ struct Engine {
     cudaEvent_t ev_end[2] = {nullptr, nullptr}; int end_cur = 0; bool end_prev_valid = false; int out_first_slot = -1;
     int2* h_counts_p = nullptr; size_t cap_counts_p = 0; int* h_over_p = nullptr;   // pinned landing zone of the count pass
     cudaEvent_t ev_count = nullptr; bool count_pending = false;
-    int opt_tree_batch = 1024; int tree_last_batches = 0;
+    int opt_tree_batch = 256; int tree_last_batches = 0;
     int opt_tree_fill = 0;                                 // pb_tree_force: 0 one step-wide list-fill launch, 1 one per batch on the batch's stream
     long long j_epoch = 0;                                 // bumped whenever ev_j_ready is re-recorded
     long long opt_min_slot_work = 0;                       // > 0: a dispatch is not cut into sub-batches smaller than this many EP-equivalent interactions

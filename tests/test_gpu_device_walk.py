@@ -30,7 +30,7 @@ def test_device_lists_equal_host_lists_as_sets(kind, n):
     engine.set_option("tree_batch", 1 << 20)                      # one batch: lists stay readable
     f = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"])
     ne, ns, ide, ids = engine.tree_lists(len(groups))
-    engine.set_option("tree_batch", 1024)
+    engine.set_option("tree_batch", 256)
     assert np.array_equal(ne, batch.n_epj) and np.array_equal(ns, batch.n_spj), "list lengths differ from the host walk"
     eo = np.concatenate([[0], np.cumsum(ne)])
     so = np.concatenate([[0], np.cumsum(ns)])
@@ -52,7 +52,7 @@ def test_device_walk_batched_equals_single_batch():
     f1 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"])
     engine.set_option("tree_batch", 37)                            # many ragged batches cycling over the streams
     f2 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"])
-    engine.set_option("tree_batch", 1024)
+    engine.set_option("tree_batch", 256)
     assert np.array_equal(f1["n_ngb"], f2["n_ngb"])
     assert np.abs(f1["acc"] - f2["acc"]).max() <= 2e-6 * np.abs(f1["acc"]).max()
     assert np.abs(f1["pot"] - f2["pot"]).max() <= 2e-6 * np.abs(f1["pot"]).max()
@@ -112,7 +112,7 @@ def test_device_walk_with_local_essential_tree():
     engine.set_option("tree_batch", 1 << 20)
     f = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], elem_map=emap)
     ne, ns, ide, ids = engine.tree_lists(len(groups))
-    engine.set_option("tree_batch", 1024)
+    engine.set_option("tree_batch", 256)
     assert np.array_equal(ne, batch.n_epj) and np.array_equal(ns, batch.n_spj)
     eo, so = np.concatenate([[0], np.cumsum(ne)]), np.concatenate([[0], np.cumsum(ns)])
     saw_let_sp = False
