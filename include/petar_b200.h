@@ -127,6 +127,7 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "tree_batch" groups per force launch of pb_tree_force (default 256: 33.7 ms per step at N = 1e6 against 40 ms with 1024).
  *   "tree_fill"  pb_tree_force writes the lists with 0 (default): one step-wide launch, 1: one launch per batch on
  *                the batch's stream (measured: no gain, the force kernels own the SMs).
+ *   "tree_streams"  streams pb_tree_force cycles its force launches over (default 4, measured best with tree_batch 256).
  *   "tree_spec"  1 (default): from the second tree step on, pb_tree_upload reserves list space from the previous
  *                step's list lengths (+12.5 % + 64 entries) and fills the lists in ONE walk pass, while the host still
  *                packs j; a list that outgrows its reservation is detected and pb_tree_force redoes the exact

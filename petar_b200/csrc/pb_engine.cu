@@ -144,6 +144,7 @@ struct Engine {
     int opt_tree_fill = 0;                                 // pb_tree_force: 0 one step-wide list-fill launch, 1 one per batch on the batch's stream
     long long j_epoch = 0;                                 // bumped whenever ev_j_ready is re-recorded
     long long opt_min_slot_work = 0;                       // > 0: a dispatch is not cut into sub-batches smaller than this many EP-equivalent interactions
+    int opt_tree_streams = 4;                              // streams pb_tree_force cycles its batches over
     int opt_tree_spec = 1;                                 // reserve list space from the previous step's lengths and fill in ONE walk pass
     std::vector<int2> prev_counts;                         // list lengths of the previous pb_tree_force
     bool spec_pending = false; int2* d_tree_caps = nullptr; size_t cap_tree_caps = 0;
@@ -876,6 +877,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_fill")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_fill must be 0 or 1"); E.opt_tree_fill = (int)v; return PB_OK; }
     if (!strcmp(key, "min_slot_work")) { if (v < 0) return fail(PB_ERR_ARG, "min_slot_work must be >= 0"); E.opt_min_slot_work = v; return PB_OK; }
+    if (!strcmp(key, "tree_streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "tree_streams must be in [1, %d]", kMaxStreams); E.opt_tree_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_spec")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_spec must be 0 or 1"); E.opt_tree_spec = (int)v; return PB_OK; }
     if (!strcmp(key, "walk_ctas")) { if (v < 1 || v > 148 * 16) return fail(PB_ERR_ARG, "walk_ctas must be in [1, 2368]"); E.opt_walk_ctas = (int)v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
@@ -1514,7 +1516,7 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
     const double theta_inv2 = E.theta > 0.0 ? 1.0 / (E.theta * E.theta) : 1e300;
     // the batches of a whole step are queued at once here, so four streams already keep the GPU full (measured:
     // eight cost 3 ms per step)
-    const int n_slots = std::max(1, std::min(E.opt_streams, 4));
+    const int n_slots = std::max(1, std::min(E.opt_streams, E.opt_tree_streams));
     if ((rc = ensure_walk_scratch(0)) != PB_OK) return rc;
     if (!E.ev_fill) CU(cudaEventCreateWithFlags(&E.ev_fill, cudaEventDisableTiming));
 
