@@ -214,21 +214,14 @@ __device__ __forceinline__ void ep_count_pairs(const EpTile& t, int p0, int p1,
         r2 = __ffma2_rn(dz, dz, r2);
         const bool h0 = r2.x < fmaxf(C.x, rsi2), h1 = r2.y < fmaxf(C.y, rsi2);
         cf = __fadd2_rn(cf, make_float2(h0 ? 1.f : 0.f, h1 ? 1.f : 0.f));
-        if (EMIT) {
-            // hits are rare (well under 1 % of the tested pairs); the warp is converged here, so one atomic per
-            // warp and pair step reserves the slots of all its hits
-            const bool e0 = h0 && i_global != 0xffffffffu, e1 = h1 && i_global != 0xffffffffu;
-            const unsigned m0 = __ballot_sync(0xffffffffu, e0), m1 = __ballot_sync(0xffffffffu, e1);
-            if (m0 | m1) {
-                const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(prm.pair_cursor, (unsigned int)(__popc(m0) + __popc(m1)));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const unsigned long long hi = (unsigned long long)i_global << 32;
-                const unsigned int at0 = base + __popc(m0 & below), at1 = base + __popc(m0) + __popc(m1 & below);
-                if (e0 && at0 < prm.pair_cap) prm.pairs[at0] = hi | (unsigned int)jid[2 * p];
-                if (e1 && at1 < prm.pair_cap) prm.pairs[at1] = hi | (unsigned int)jid[2 * p + 1];
-            }
+        if (EMIT && (h0 || h1) && i_global != 0xffffffffu) {
+            // rare (well under 1 % of the tested pairs): one slot per hit from the launch-wide cursor.  Per lane, not
+            // per warp: lanes that share a particle run different trip counts, so the warp is not converged here
+            const unsigned int n = (unsigned int)h0 + (unsigned int)h1;
+            const unsigned int at = atomicAdd(prm.pair_cursor, n);
+            const unsigned long long hi = (unsigned long long)i_global << 32;
+            if (h0 && at < prm.pair_cap) prm.pairs[at] = hi | (unsigned int)jid[2 * p];
+            if (h1 && at + (unsigned int)h0 < prm.pair_cap) prm.pairs[at + (unsigned int)h0] = hi | (unsigned int)jid[2 * p + 1];
         }
     }
 }
@@ -442,8 +435,16 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
     const int  js   = busy ? warp / task.nib : 0;
     const int  ppw  = kTilePairs / task.jsplit;             // pairs of each tile this warp consumes
 
+    // A block with at most 16 (8) real i-particles — the ragged end of a walk — lets 2 (4) lanes share each particle
+    // and split every j segment between them instead of idling: lane = (sub, il), il = the particle, sub = the lane's
+    // share of the pairs; the shares are added by shuffles after the loops.
+    const int  n_blk  = busy ? min(32, w.ni - (task.i_first + ib * 32)) : 32;
+    const int  ishift = (n_blk <= 8) ? 2 : (n_blk <= 16) ? 1 : 0;     // isplit = 1 << ishift lanes per particle
+    const int  lanes_i = 32 >> ishift;
+    const int  il = lane & (lanes_i - 1), sub = lane >> (5 - ishift);
+
     // i-particle (registers): relative to the walk origin already (host formed x_i - origin in fp64)
-    const int  i_loc  = task.i_first + ib * 32 + lane;
+    const int  i_loc  = task.i_first + ib * 32 + il;
     const bool ivalid = busy && (i_loc < w.ni);
     float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), pil = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ivalid) {
@@ -486,13 +487,15 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 const int p0  = js * ppw, p1 = min(p0 + ppw, npu);
                 float2 ax = bc(0.f), ay = bc(0.f), az = bc(0.f), pt = bc(0.f), cf = bc(0.f);
                 // 16-pair segments = the 32 j one staging warp wrote; count only where flagged
-                for (int seg = p0; seg < p1; seg += 16) {
-                    const int e = min(seg + 16, p1);
+                for (int seg0 = p0; seg0 < p1; seg0 += 16) {
+                    // this lane's contiguous share of the segment (all of it unless lanes share a particle)
+                    const int seg = seg0 + sub * (16 >> ishift);
+                    const int e = min(min(seg0 + 16, p1), seg + (16 >> ishift));
                     if (count_only) {
-                        if (near_flag[k & 1][seg >> 4])
+                        if (near_flag[k & 1][seg0 >> 4])
                             ep_count_pairs<EMIT>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, cf,
                                                  jid[EMIT ? (k & 1) : 0], ivalid ? (unsigned int)(prm.i_base + w.i_off + i_loc) : 0xffffffffu, prm);
-                    } else if (near_flag[k & 1][seg >> 4])
+                    } else if (near_flag[k & 1][seg0 >> 4])
                         ep_pairs<NR, true>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
                     else
                         ep_pairs<NR, false>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
@@ -528,7 +531,9 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 const int npu = ((nv + 1) >> 1);          // pairs with at least one real j (padding pairs are inert anyway)
                 const int p0  = js * ppw, p1 = min(p0 + ppw, npu);
                 float2 ax = bc(0.f), ay = bc(0.f), az = bc(0.f), pt = bc(0.f);
-                sp_pairs<NR>(sm.sp[k & 1], p0, p1, pi.x, pi.y, pi.z, prm.eps2, ax, ay, az, pt);
+                const int plen = (p1 - p0 + (1 << ishift) - 1) >> ishift;   // this lane's contiguous share of the warp's pairs
+                const int q0 = p0 + sub * plen, q1 = min(p1, q0 + plen);
+                sp_pairs<NR>(sm.sp[k & 1], q0, q1, pi.x, pi.y, pi.z, prm.eps2, ax, ay, az, pt);
                 kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
             }
             if (more) sp_store(sm.sp[(k + 1) & 1], tid, id_nxt, jr, w, prm.eps2);
@@ -540,6 +545,11 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
 
     // per-warp totals as exact doubles (hi + lo)
     double dax = kx.value(), day = ky.value(), daz = kz.value(), dpt = kp.value();
+    for (int o = lanes_i; o < 32; o <<= 1) {              // lanes that shared a particle (isplit > 1): fixed-order butterfly
+        dax += __shfl_xor_sync(0xffffffffu, dax, o); day += __shfl_xor_sync(0xffffffffu, day, o);
+        daz += __shfl_xor_sync(0xffffffffu, daz, o); dpt += __shfl_xor_sync(0xffffffffu, dpt, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
 
     if (task.jsplit > 1) {
         // combine the jsplit warps that share an i-block, in fixed order js = 0,1,...
@@ -565,8 +575,8 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             for (int s = 1; s < task.jsplit; ++s) cnt += redn[(s * task.nib + ib) * 32 + lane];
     }
 
-    if (busy && js == 0) {
-        const int slot = task.part_base + ib * 32 + lane;
+    if (busy && js == 0 && sub == 0) {
+        const int slot = task.part_base + ib * 32 + il;
         part4[slot] = make_double4(dax, day, daz, dpt);
         partn[slot] = cnt;
     }

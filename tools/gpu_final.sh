@@ -5,7 +5,7 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out
 mkdir -p $O
 export PATH=$PATH:/usr/local/cuda/bin
-timeout 1200 python -m pytest tests -m gpu -x -q > $O/f_pytest.log 2>&1; tail -3 $O/f_pytest.log
+timeout 300 python -m pytest tests -m gpu -x -q > $O/f_pytest.log 2>&1; tail -3 $O/f_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/f_smoke.log 2>&1; tail -1 $O/f_smoke.log
 timeout 900 python bench.py > $O/f_bench.log 2>&1; tail -1 $O/f_bench.log | cut -c1-400
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/f_bench_ref.log 2>&1; tail -1 $O/f_bench_ref.log | cut -c1-300
