@@ -849,7 +849,7 @@ void pb_finalize(void) {
     E.h_corr = nullptr; E.d_corr = nullptr; E.cap_corr = 0;
     cudaFree(E.d_cells); cudaFree(E.d_groups); cudaFree(E.d_counts); cudaFree(E.d_overflow); cudaFreeHost(E.h_tstage);
     for (int s = 0; s < kMaxStreams; s++) cudaFree(E.d_walk_scratch[s]);
-    cudaFree(E.d_tree_ide); cudaFree(E.d_tree_ids); cudaFree(E.d_tree_off);
+    cudaFree(E.d_tree_ide); cudaFree(E.d_tree_ids); cudaFree(E.d_tree_off); cudaFree(E.d_tree_caps);
     cudaFreeHost(E.h_counts_p); cudaFreeHost(E.h_over_p);
     if (E.ev_count) cudaEventDestroy(E.ev_count);
     if (E.ev_fill) cudaEventDestroy(E.ev_fill);
