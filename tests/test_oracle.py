@@ -289,3 +289,40 @@ def test_changeover_oracle_vs_committed_reference_vectors():
         assert out.tobytes() == g[key].tobytes()
     for r_in, r_out, dr, a, p in g["w_table"]:
         assert ob.changeover_w(r_in, r_out, dr) == (a, p)
+
+
+def test_changeover_correction_properties():
+    """Physics of the pair correction (fp64 branch): nothing changes beyond both the changeover radius and the
+    cutoff radius; inside r_in the pair's soft force is removed entirely, i.e. the correction only takes the
+    kernel's clamped term back out (acc_after = acc_before + G m dr / r_out^3); the corrected pair force obeys
+    Newton's third law; the part of the pair potential left to the hard integrator shrinks with separation."""
+    from petar_b200.types import PtclCorr
+    G, r_out_g = 1.0, 2e-3
+
+    def pair(sep, mi=3e-6, mj=5e-6, fi=1.0, fj=1.5):
+        pi, pj = np.zeros(1, PtclCorr), np.zeros(1, PtclCorr)
+        pi["pos"], pj["pos"] = [0.1, -0.2, 0.3], [0.1 + sep, -0.2, 0.3]
+        pi["mass"], pj["mass"] = mi, mj
+        pi["r_in"], pi["r_out"], pj["r_in"], pj["r_out"] = 0.1 * r_out_g * fi, r_out_g * fi, 0.1 * r_out_g * fj, r_out_g * fj
+        pi["id"], pj["id"] = 1, 2
+        return pi, pj
+
+    # beyond max(r_out_i, r_out_j) = 1.5 r_out and beyond the global cutoff: exactly nothing to correct in acc
+    pi, pj = pair(2.0 * r_out_g)
+    a = pi.copy(); ob.changeover_pair(a, pj, 0.0, r_out_g, G, 0)
+    assert np.array_equal(a["acc"], pi["acc"]) and a["pot_tot"][0] == 0.0
+    # inside r_in of the pair: k = 0, so the correction only takes the clamped (linear-cutoff) term back out
+    sep = 0.05 * r_out_g
+    pi, pj = pair(sep)
+    a = pi.copy(); ob.changeover_pair(a, pj, 0.0, r_out_g, G, 0)
+    assert np.allclose(a["acc"][0], [G * pj["mass"][0] * (-sep) / r_out_g ** 3, 0.0, 0.0], rtol=1e-11, atol=1e-300)
+    # Newton's third law inside the changeover region
+    pi, pj = pair(0.7 * r_out_g)
+    a, b = pi.copy(), pj.copy()
+    ob.changeover_pair(a, pj, 0.0, r_out_g, G, 0)
+    ob.changeover_pair(b, pi, 0.0, r_out_g, G, 0)
+    assert np.allclose(pi["mass"] * a["acc"], -pj["mass"] * b["acc"], rtol=1e-13, atol=0)
+    # potential: tot - soft of the pair is the part the hard integrator owns, positive and shrinking with separation
+    own = [(lambda a: (a["pot_soft"] - a["pot_tot"])[0])((lambda p: (ob.changeover_pair(p[0], p[1], 0.0, r_out_g, G, 0), p[0])[1])((pair(s)[0].copy(), pair(s)[1])))
+           for s in (0.2 * r_out_g, 0.6 * r_out_g, 1.2 * r_out_g)]
+    assert own[0] > own[1] > own[2] >= 0.0
