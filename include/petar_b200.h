@@ -120,7 +120,7 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "nr"         Newton-Raphson steps after MUFU.RSQ (0 default, or 1).
  *   "cull"       1 (default): skip the neighbour test for j-tile segments that cannot reach any
  *                i-particle of the walk (results identical); 0: test every pair.
- *   "occupancy"  resident CTAs per SM the force kernel is compiled for: 2 (default, 122 registers)
+ *   "occupancy"  resident CTAs per SM the force kernel is compiled for: 2 (default, 124 registers)
  *                or 3 (80 registers).
  *   "lead"       the first of a dispatch's per-stream sub-batches is 1/(1+lead) the size of the others
  *                (the GPU idles until its copy lands): 0 = equal sizes, 3 (default), up to 15.
