@@ -186,6 +186,22 @@ def test_plummer100k_default_mode(plummer100k):
     assert prof["t_calc"] > 0 and prof["t_send"] > 0 and prof["t_recv"] > 0
 
 
+def test_maximum_walks_per_dispatch(plummer100k):
+    """The reference asserts n_walk <= 1000 per dispatch (src/force_gpu_cuda.cu:548); the library has no limit.  1000
+    walks per dispatch, and the whole step in one dispatch, with the default 8 sub-batches and the smallest lead."""
+    batch, prm, ref = plummer100k
+    for k, v in (("streams", 8), ("lead", 3)):
+        engine.set_option(k, v)
+    f200 = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"])
+    for limit in (1000, batch.n_walk):
+        engine.get_profile(reset=True)
+        f = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"], n_walk_limit=limit)
+        assert engine.get_profile()["n_call"] == (batch.n_walk + limit - 1) // limit
+        check_tol(f, ref, f"n_walk_limit={limit}")
+        assert np.array_equal(f["n_ngb"], f200["n_ngb"])
+    engine.set_option("lead", 3)
+
+
 def test_plummer100k_option_matrix(plummer100k):
     """cull on/off and stream count must not change results at all; chunking changes only the
     summation order (<< tolerance); one Newton step must stay within tolerance."""
