@@ -315,6 +315,41 @@ def test_ragged_and_tiny_walks():
     assert f_py.tobytes() == f.tobytes()
 
 
+def test_one_huge_walk_and_every_ragged_block_size():
+    """One walk far beyond PeTar's n_group_limit (2069 i-particles: 64 full blocks and a ragged one of 21) with long
+    lists (many chunks per i-block group), then walks whose last block holds 1..32 particles: every lane-sharing
+    configuration of the ragged block (4, 2 and 1 lanes per particle) against the oracle."""
+    rng = np.random.default_rng(11)
+    n = 120000
+    pos = rng.normal(scale=0.3, size=(n, 3))
+    rs = np.full(n, 2e-3)
+    epj = _epj(pos, np.full(n, 1.0 / n), rs)
+    spj = np.zeros(40000, dtype=SPJQuad)
+    spj["pos"] = rng.normal(scale=3.0, size=(len(spj), 3)) + 6.0
+    spj["mass"] = rng.uniform(1e-5, 1e-4, len(spj))
+    spj["quad"] = rng.normal(scale=1e-7, size=(len(spj), 6))
+    sizes = [2069] + list(range(1, 33)) + [33, 40, 48, 49, 63, 64, 65]
+    i_off, ej_off, sj_off, ide, ids, epi_idx = [0], [0], [0], [], [], []
+    for k, ni in enumerate(sizes):
+        c = rng.integers(0, n)
+        near = np.argsort(((pos - pos[c]) ** 2).sum(1))[:max(ni, 64)]
+        epi_idx.append(near[:ni])
+        ne, ns = (100000, 40000) if k == 0 else (int(rng.integers(300, 3000)), int(rng.integers(0, 2000)))
+        ide.append(np.union1d(near, rng.choice(n, ne, replace=False)))            # own neighbourhood + random far j
+        ids.append(rng.choice(len(spj), ns, replace=False))
+        i_off.append(i_off[-1] + ni); ej_off.append(ej_off[-1] + len(ide[-1])); sj_off.append(sj_off[-1] + ns)
+    epi_idx = np.concatenate(epi_idx)
+    epi = _epi(pos[epi_idx], rs[epi_idx])
+    batch = WalkBatch(epj, spj, epi, i_off, np.concatenate(ide), ej_off, np.concatenate(ids), sj_off)
+    ref = ob.walks_index(batch, 0.0, 5e-3, 1.0)
+    for streams in (1, 8):
+        engine.set_option("streams", streams)
+        f = engine.calc_force_all_and_write_back(batch, 0.0, 5e-3, 1.0)
+        ea = np.linalg.norm(f["acc"] - ref["acc"], axis=1) / np.linalg.norm(ref["acc"], axis=1)
+        assert np.median(ea) < 1e-6 and ea.max() < TOL_MAX, (streams, np.median(ea), ea.max())
+        assert count_mismatch_report(batch, f, ref, f"huge+ragged streams={streams}") <= 2
+
+
 def test_protocol_errors():
     L = engine.load()
     epi, epj, spj = ob.simdtest_inputs(64, 128, 16)
