@@ -315,6 +315,20 @@ def test_ragged_and_tiny_walks():
     assert f_py.tobytes() == f.tobytes()
 
 
+def test_config1_standin_star_cluster():
+    """BASELINE configs[0] (sample/star_cluster.sh: N = 1000, Kroupa IMF, 95 % binaries) stand-in: the soft tree sees
+    up to 1000 + 12 * 475 = 6700 particles, most groups dominated by zero-mass artificial particles."""
+    batch, _, prm, P = hz.kroupa_binary_case(1000, f_bin=0.95)
+    assert P["n_bin"] == 475 and len(P["mass"]) == 1000 + 12 * 475
+    ref = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"])
+    f = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"])
+    check_tol(f, ref, "config 1 stand-in")
+    assert count_mismatch_report(batch, f, ref, "config 1 stand-in") <= 2
+    cells, groups = batch.tree.export_tree()
+    f2 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"])         # and with device-built lists
+    assert np.array_equal(f2["n_ngb"], f["n_ngb"]) and np.abs(f2["acc"] - f["acc"]).max() <= 2e-6 * np.abs(f["acc"]).max()
+
+
 def test_one_huge_walk_and_every_ragged_block_size():
     """One walk far beyond PeTar's n_group_limit (2069 i-particles: 64 full blocks and a ragged one of 21) with long
     lists (many chunks per i-block group), then walks whose last block holds 1..32 particles: every lane-sharing
