@@ -213,7 +213,43 @@ def workload_config(args, wl, world):
             "l2_policy": "inputs larger than L2: every step re-reads all dispatches' index lists, i-particles and the j store"}
 
 
-def cpu_baseline_leg(args, wl):
+def parity_report(batch, prm, f_gpu, f_avx):
+    """SURVEY §8(d) "parity report (every run)": the e2e step's forces against the fp64 oracle on a bounded sample of
+    walks (first, middle and last 32), with the reference's AVX path on the same walks for context.  Checker only."""
+    from oracle import binding as ob
+    nw = batch.n_walk
+    starts = sorted({0, max(0, nw // 2 - 16), max(0, nw - 32)})
+    idx, ref_rows = [], []
+    for w0 in starts:
+        sl = slice(w0, min(nw, w0 + 32))
+        ref = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"], walk_slice=sl)
+        i0, i1 = int(batch.i_off[sl.start]), int(batch.i_off[sl.stop])
+        idx.append(np.arange(i0, i1)); ref_rows.append(ref[i0:i1] if len(ref) == batch.n_epi_total else ref)
+    idx, ref = np.concatenate(idx), np.concatenate(ref_rows)
+
+    def stats(f, mask=None):
+        f, r = f[idx], ref
+        if mask is not None:
+            f, r = f[mask], r[mask]
+        ea = np.linalg.norm(f["acc"] - r["acc"], axis=1) / np.maximum(np.linalg.norm(r["acc"], axis=1), 1e-300)
+        ep = np.abs(f["pot"] - r["pot"]) / np.maximum(np.abs(r["pot"]), 1e-300)
+        return {"acc_rel_err": {"median": float(np.median(ea)), "p99": float(np.percentile(ea, 99)), "max": float(ea.max())},
+                "pot_rel_err": {"median": float(np.median(ep)), "p99": float(np.percentile(ep, 99)), "max": float(ep.max())},
+                "n_ngb_mismatches": int((f["n_ngb"] != r["n_ngb"]).sum()), "n": int(len(f))}
+
+    out = {"sample": f"{len(idx)} i-particles of {len(starts) * 32} walks (first, middle, last) against the fp64 oracle",
+           "tolerance": "acc/pot relative error <= 1e-6 median, <= 1e-4 max; counts equal except pairs within fp32 rounding of r_search",
+           "petar_b200": stats(f_gpu)}
+    if f_avx is not None:
+        # the SIMD adapters skip type-0 i-particles and zero-mass j (src/soft_force.hpp:371-400): compared on type-1 i only,
+        # and their neighbour counts differ from the NoSimd oracle's wherever a zero-mass j is inside r_search
+        out["reference_avx"] = stats(f_avx, batch.epi["type"][idx] == 1)
+    out["pass"] = bool(out["petar_b200"]["acc_rel_err"]["median"] <= 1e-6 and out["petar_b200"]["acc_rel_err"]["max"] <= 1e-4 and
+                       out["petar_b200"]["pot_rel_err"]["median"] <= 1e-6 and out["petar_b200"]["pot_rel_err"]["max"] <= 1e-4)
+    return out
+
+
+def cpu_baseline_leg(args, wl, f_gpu=None):
     from oracle import binding as ob
     batch, prm = wl["batch"], wl["prm"]
     isa = "avx512" if ob._cpu_has_avx512() else "avx2"
@@ -237,8 +273,14 @@ def cpu_baseline_leg(args, wl):
     else:
         t0 = time.perf_counter(); ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"], walk_slice=slice(0, nwalks)); sec = time.perf_counter() - t0
     ie, isp = batch.interactions(slice(0, nwalks))
-    return {"value": (ie + isp) / sec * 1e-9, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": kind,
-            "sample": f"first {nwalks} of {nw} walks of one tree step ({ie + isp:.3e} interactions, {sec:.2f} s), {isa}, OpenMP over walks"}
+    out = {"value": (ie + isp) / sec * 1e-9, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": kind,
+           "sample": f"first {nwalks} of {nw} walks of one tree step ({ie + isp:.3e} interactions, {sec:.2f} s), {isa}, OpenMP over walks"}
+    if f_gpu is not None:
+        try:
+            out["parity"] = parity_report(batch, prm, f_gpu, force if (kind == "reference" and nwalks == nw) else None)
+        except Exception as ex:  # noqa: BLE001 — the checker must never take the bench down
+            out["parity"] = {"unavailable": repr(ex)}
+    return out
 
 
 def main():
@@ -349,6 +391,7 @@ def main():
     barrier()
     sec_e2e = (time.perf_counter() - t0) / args.steps
     t_timed_end = time.time()
+    f_e2e = force.copy()                      # the e2e step's result, for the parity report of the cpu_baseline leg
     prof = engine.get_profile()
     clock_probe_s = 0.0
     if t_timed_end - t_timed_begin < 0.5:
@@ -458,7 +501,7 @@ def main():
             line["e2e"]["omp_threads_per_rank"] = int(os.environ.get("OMP_NUM_THREADS", "0"))
         if not args.no_cpu_baseline and world == 1:
             try:
-                line["cpu_baseline"] = cpu_baseline_leg(args, wl)
+                line["cpu_baseline"] = cpu_baseline_leg(args, wl, f_e2e)
             except Exception as ex:  # the checker must never take the bench down
                 line["cpu_baseline"] = {"value": None, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)}
             # informational second baseline: the reference's own CUDA kernels and host
