@@ -198,7 +198,7 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (I_ep + I_sp) / (ie + isp),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, wl, 1),
-        "cpu_baseline": {"value": gint, "unit": "Ginteractions/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": gint, "unit": "Ginteractions/s", "cores": cores, "kind": kind, "cpu_model": cpu_model(), "sample": sample},
         "e2e": {"value": gint, "unit": "Ginteractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sec_per_nbody_time_unit": sec * (I_ep + I_sp) / (ie + isp) / prm["dt_soft"],
     }
@@ -211,6 +211,17 @@ def workload_config(args, wl, world):
             "n_group_limit": 512, "n_walk_limit": args.n_walk_limit, "r_out": prm["r_out"], "dt_soft": prm["dt_soft"], "eps": prm["eps"],
             "multipole": "quadrupole", "parallelism": f"domain_decomposition_x{world}",
             "l2_policy": "inputs larger than L2: every step re-reads all dispatches' index lists, i-particles and the j store"}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def parity_report(batch, prm, f_gpu, f_avx):
@@ -273,7 +284,7 @@ def cpu_baseline_leg(args, wl, f_gpu=None):
     else:
         t0 = time.perf_counter(); ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"], walk_slice=slice(0, nwalks)); sec = time.perf_counter() - t0
     ie, isp = batch.interactions(slice(0, nwalks))
-    out = {"value": (ie + isp) / sec * 1e-9, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": kind,
+    out = {"value": (ie + isp) / sec * 1e-9, "unit": "Ginteractions/s", "cores": os.cpu_count(), "kind": kind, "cpu_model": cpu_model(),
            "sample": f"first {nwalks} of {nw} walks of one tree step ({ie + isp:.3e} interactions, {sec:.2f} s), {isa}, OpenMP over walks"}
     if f_gpu is not None:
         try:
