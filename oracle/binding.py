@@ -105,6 +105,52 @@ def ref_lib(isa=None):
     return _ref[isa]
 
 
+_nosimd = None
+
+
+def ref_nosimd_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libpetar_ref_nosimd.so"))
+
+
+def ref_nosimd_lib():
+    """The reference's own fp64 NoSimd functors (src/soft_force.hpp:10-236) compiled from the reference source
+    (ref_nosimd.cpp): the bit-for-bit pin of the restatement in oracle_soft_force.c."""
+    global _nosimd
+    if _nosimd is None:
+        path = os.path.join(_HERE, "_ref", "libpetar_ref_nosimd.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.ref_nosimd_search.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp]
+        L.ref_nosimd_epep.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double, C.c_double, C.c_double]
+        L.ref_nosimd_epsp_mono.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double, C.c_double]
+        L.ref_nosimd_epsp_quad.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double, C.c_double]
+        L.ref_nosimd_pp.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_double]
+        _nosimd = L
+    return _nosimd
+
+
+def ref_nosimd(kind, epi, j, eps=0.0, r_out=0.0, G=1.0, force=None):
+    """kind in {'search', 'epep', 'epsp_mono', 'epsp_quad', 'pp'}: the reference functor of that name on flat arrays."""
+    f = new_force(len(epi)) if force is None else force
+    L = ref_nosimd_lib()
+    jt = SPJQuad if kind.startswith("epsp") else EPJSoft
+    a = (_chk(epi, EPISoft), len(epi), _chk(j, jt), len(j), _chk(f, ForceSoft))
+    if kind == "search":
+        L.ref_nosimd_search(*a)
+    elif kind == "epep":
+        L.ref_nosimd_epep(*a, eps, r_out, G)
+    elif kind == "epsp_mono":
+        L.ref_nosimd_epsp_mono(*a, eps, G)
+    elif kind == "epsp_quad":
+        L.ref_nosimd_epsp_quad(*a, eps, G)
+    elif kind == "pp":
+        L.ref_nosimd_pp(*a, G)
+    else:
+        raise ValueError(kind)
+    return f
+
+
 def _chk(a, dt):
     assert a.dtype == dt and a.flags["C_CONTIGUOUS"], (a.dtype, dt)
     return a.ctypes.data

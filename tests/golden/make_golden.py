@@ -44,6 +44,17 @@ def main():
         oracle_sp_mono=ob.force_epsp_mono(epi, spj, P["eps"], P["G"]),
         oracle_nb=ob.search_neighbor(epi, epj),
     )
+    # the reference's own fp64 NoSimd functors (src/soft_force.hpp:10-236, compiled from the reference source by
+    # oracle/Makefile into oracle/_ref/libpetar_ref_nosimd.so): the oracle must reproduce these bit for bit
+    out["nosimd_ep"] = ob.ref_nosimd("epep", epi, epj, P["eps"], P["r_out"], P["G"])
+    out["nosimd_sp"] = ob.ref_nosimd("epsp_quad", epi, spj, P["eps"], G=P["G"])
+    out["nosimd_sp_mono"] = ob.ref_nosimd("epsp_mono", epi, spj, P["eps"], G=P["G"])
+    out["nosimd_nb"] = ob.ref_nosimd("search", epi, epj)
+    out["nosimd_pp"] = ob.ref_nosimd("pp", epi, epj, G=P["G"])
+    out["oracle_pp"] = ob.force_pp(epi, epj, P["G"])
+    # a second parameter set with eps > 0 and G != 1 (the simd_test recipe has eps = 1e-4, G = 1)
+    out["nosimd_ep_b"] = ob.ref_nosimd("epep", epi, epj, 3e-3, 2e-2, 0.37)
+    out["nosimd_sp_b"] = ob.ref_nosimd("epsp_quad", epi, spj, 3e-3, G=0.37)
     for isa in ("avx2", "avx512"):
         out[f"ref_{isa}_ep"] = ob.ref_force_epep(epi, epj, P["eps"], P["r_out"], P["G"], isa=isa)
         out[f"ref_{isa}_sp"] = ob.ref_force_epsp_quad(epi, spj, P["eps"], P["G"], isa=isa)

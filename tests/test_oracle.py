@@ -68,10 +68,52 @@ def test_oracle_matches_golden_bitwise():
         assert np.array_equal(sp[k], g["oracle_sp"][k])
 
 
+def test_oracle_equals_reference_nosimd_functors_bitwise():
+    """THE PIN: the fp64 restatement (oracle_soft_force.c) reproduces, bit for bit, the outputs of the reference's own
+    NoSimd functors — SearchNeighborEpEpNoSimd, CalcForceEpEpWithLinearCutoffNoSimd, CalcForceEpSpMonoNoSimd,
+    CalcForceEpSpQuadNoSimd, CalcForcePPNoSimd (src/soft_force.hpp:10-236) — compiled from the reference source
+    (oracle/ref_nosimd.cpp, -O2 -ffp-contract=off) and stored in tests/golden/simdtest.npz on the simd_test.cxx
+    inputs, for the test's own parameters and for a second set with a large eps and G != 1."""
+    g = np.load(os.path.join(GOLDEN, "simdtest.npz"))
+    epi, epj, spj = ob.simdtest_inputs()
+    assert ob.force_epep(epi, epj, P["eps"], P["r_out"], P["G"]).tobytes() == g["nosimd_ep"].tobytes()
+    assert ob.force_epsp_quad(epi, spj, P["eps"], P["G"]).tobytes() == g["nosimd_sp"].tobytes()
+    assert ob.force_epsp_mono(epi, spj, P["eps"], P["G"]).tobytes() == g["nosimd_sp_mono"].tobytes()
+    assert ob.search_neighbor(epi, epj).tobytes() == g["nosimd_nb"].tobytes()
+    assert ob.force_pp(epi, epj, P["G"]).tobytes() == g["nosimd_pp"].tobytes()
+    assert ob.force_epep(epi, epj, 3e-3, 2e-2, 0.37).tobytes() == g["nosimd_ep_b"].tobytes()
+    assert ob.force_epsp_quad(epi, spj, 3e-3, 0.37).tobytes() == g["nosimd_sp_b"].tobytes()
+
+
+@pytest.mark.skipif(not ob.ref_nosimd_available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_reference_nosimd_live_equals_golden_and_walk_driver():
+    """Where the reference is compiled (this container): its live outputs equal the committed vectors, the functors
+    ACCUMULATE into acc / pot as the oracle does, and the oracle's multiwalk driver (index gather + EP functor + SP
+    functor per walk) equals the reference functors applied walk by walk to the gathered arrays, bit for bit."""
+    from petar_b200 import harness as hz
+    g = np.load(os.path.join(GOLDEN, "simdtest.npz"))
+    epi, epj, spj = ob.simdtest_inputs()
+    f = ob.ref_nosimd("epep", epi, epj, P["eps"], P["r_out"], P["G"])
+    assert f.tobytes() == g["nosimd_ep"].tobytes()
+    f2 = ob.ref_nosimd("epsp_quad", epi, spj, P["eps"], G=P["G"], force=f.copy())        # accumulates onto the EP result
+    o2 = ob.force_epsp_quad(epi, spj, P["eps"], P["G"], force=ob.force_epep(epi, epj, P["eps"], P["r_out"], P["G"]))
+    assert f2.tobytes() == o2.tobytes()
+    batch, _, prm, _ = hz.plummer_case(1000)
+    ref = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"])
+    for w in range(batch.n_walk):
+        i0, i1 = batch.i_off[w], batch.i_off[w + 1]
+        je = np.ascontiguousarray(batch.epj[batch.id_epj[batch.ej_off[w]:batch.ej_off[w + 1]]])
+        js = np.ascontiguousarray(batch.spj[batch.id_spj[batch.sj_off[w]:batch.sj_off[w + 1]]])
+        ei = np.ascontiguousarray(batch.epi[i0:i1])
+        fw = ob.ref_nosimd("epep", ei, je, prm["eps"], prm["r_out"], prm["G"])
+        fw = ob.ref_nosimd("epsp_quad", ei, js, prm["eps"], G=prm["G"], force=fw)
+        assert fw.tobytes() == ref[i0:i1].tobytes(), w
+
+
 @pytest.mark.parametrize("isa", ["avx2", "avx512"])
 def test_oracle_vs_reference_simd_golden(isa):
-    """The fp64 restatement agrees with the reference's own fp32 SIMD kernels to the SIMD kernels'
-    precision: EP-EP (rsqrt + one Newton step) ~1e-6, EP-SP (raw rsqrt, no Newton step) within the
+    """CONTEXT ONLY (the pin is the bitwise NoSimd test above): the fp64 restatement agrees with the reference's own
+    fp32 SIMD kernels to the SIMD kernels' precision: EP-EP (rsqrt + one Newton step) ~1e-6, EP-SP (raw rsqrt, no Newton step) within the
     reference test's own 7e-3 print threshold (src/simd_test.cxx:68); neighbour counts identical."""
     g = np.load(os.path.join(GOLDEN, "simdtest.npz"))
     ep, sp = g["oracle_ep"], g["oracle_sp"]
