@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 3
+#define PB_ABI_VERSION 4
 
 typedef enum pb_status {
     PB_OK = 0,
@@ -110,11 +110,19 @@ const char* pb_last_error(void);
 int  pb_set_params(double eps2, double rcut2, double G);
 
 /* Options (key, value):
- *   "coords"     0 (default): positions relative to each walk's origin (centre of its i-particles),
- *                   formed from fp64 on the host (i) and from a hi/lo fp32 split on the device (j);
- *                1: absolute coordinates cast to fp32 — dx = float(xj) - float(xi), the exact
- *                   arithmetic the reference kernel and the CPU changeover correction replay use
- *                   (src/force_gpu_cuda.cu:58-60, src/hard.hpp:1346-1351).
+ *   "coords"     how dx of an EP-EP pair is formed (fp32 in every mode):
+ *                0: positions relative to each walk's origin (centre of its i-particles), formed from fp64 on the
+ *                   host (i) and from a hi/lo fp32 split on the device (j) — the most accurate kernel-level result;
+ *                   pair it with an all-double correction (pb_correct_changeover with replay_fp32 = 0, or PeTar built
+ *                   with the `#else` branch of src/hard.hpp:1443-1453);
+ *                1: absolute coordinates cast to fp32 for EVERY pair — dx = float(xj) - float(xi), the exact
+ *                   arithmetic of the reference kernel (src/force_gpu_cuda.cu:58-60);
+ *                2 (default, the drop-in mode): as 0, except that a pair passing the neighbour test
+ *                   r^2 < max(rs_i, rs_j)^2 is evaluated from dx = float(xj) - float(xi).  Those are the pairs PeTar's
+ *                   CPU changeover correction visits afterwards, and with USE_GPU it removes the kernel's clamped
+ *                   term by re-computing it in float from exactly that dx (`dr_32`, src/hard.hpp:1428-1442); with
+ *                   any other dx a residual G m (dx - dr_32) / r_out^3 per neighbour would stay in the force
+ *                   (tests/test_gpu_replay_gap.py measures it).  Neighbour counts are the same in all modes.
  *   "streams"    number of CUDA streams one dispatch is split across (default 8, 1..8).
  *   "jchunk"     target EP j-chunk per warp-task (default 0 = automatic).
  *   "nr"         Newton-Raphson steps after MUFU.RSQ (0 default, or 1).
@@ -141,6 +149,8 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *                0 (default): counts only.
  * Returns PB_ERR_ARG for an unknown key or value. */
 int  pb_set_option(const char* key, long long value);
+/* Current value of an option (any key of pb_set_option). */
+int  pb_get_option(const char* key, long long* value);
 
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* send_flag == true: publish all j of this tree step.  Replaces any previous j set. */

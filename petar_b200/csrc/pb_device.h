@@ -67,7 +67,9 @@ struct ForceOut {
 struct Params {
     float eps2;
     float rcut2;
-    int   abs_mode;       // 1: absolute-coordinate mode (no lo parts: dx = float(xj) - float(xi))
+    int   abs_mode;       // option "coords": 0 walk-relative two-float dx; 1 absolute float-cast dx for every pair;
+                          // 2 walk-relative, but pairs that pass the neighbour test use the absolute float-cast dx
+    int   i_f4;           // float4 per packed i-particle: 2, or 3 with the absolute float-cast position (coords = 2)
     // neighbour-list emission (count-only launches with option "nb_lists"): every pair that passes the
     // neighbour test appends the key (i_base + i index in the sub-batch) << 32 | j store index
     int   i_base;

@@ -72,6 +72,7 @@ struct Plan {                // layout of one sub-batch inside an arena
     size_t off_walks = 0, off_tasks = 0, off_iblocks = 0, off_epi = 0, off_ide = 0, off_ids = 0;
     size_t off_lepj = 0, off_lspj = 0, bytes = 0;
     int    count_only = 0;                    // neighbour search only: EP lists as kind-2 tasks, no SP, eps2 = 0
+    int    coords = 0, i_f4 = 2;              // option "coords" the sub-batch was packed for; float4 per packed i-particle
     const int* ext_ide = nullptr;             // index lists living outside the arena (built on the device for the whole step)
     const int* ext_ids = nullptr;
 };
@@ -106,7 +107,7 @@ struct Engine {
     bool inited = false;
     int  rank = 0, device = 0;
     double eps2 = 0.0, rcut2 = 0.0, G = 1.0;
-    int opt_coords = 0, opt_streams = 8, opt_jchunk = 0, opt_nr = 0, opt_cull = 1, opt_occ = 2, opt_lead = 3;
+    int opt_coords = 2, opt_streams = 8, opt_jchunk = 0, opt_nr = 0, opt_cull = 1, opt_occ = 2, opt_lead = 3;
 
     // j store
     float4* d_epj = nullptr; size_t cap_epj = 0; int n_epj = 0;
@@ -410,8 +411,9 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
             const int nj = kind == 0 ? W.nej : W.nsj;
             const int nc = kind == 0 ? nce : ncs;
             if (nc == 0) continue;
-            // equal chunks, multiples of 8 (pair unroll) except the last
-            const int len = (int)align_up((size_t)(nj + nc - 1) / nc, 8);
+            // equal chunks of whole j tiles: only the last chunk of a list ends in a ragged tile (which the warps that
+            // share an i-block then split evenly, see force_kernel)
+            const int len = (int)align_up((size_t)(nj + nc - 1) / nc, kTileJ);
             for (int c = 0; c < nc; c++) {
                 const int jb = c * len;
                 if (jb >= nj) break;
@@ -444,13 +446,15 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
 
     Plan& p = hp.p;
     p.count_only = E.count_only ? 1 : 0;
+    p.coords = E.opt_coords;
+    p.i_f4 = (E.opt_coords == 2 && !E.count_only) ? 3 : 2;
     p.n_walk = n_walk; p.n_tasks = (int)hp.tasks.size(); p.n_iblocks = (int)hp.iblocks.size();
     p.n_i = i_off; p.n_ide = ide; p.n_ids = ids; p.n_part = part; p.n_lepj = lepj; p.n_lspj = lspj;
     size_t o = 0;
     p.off_walks = o;   o = align_up(o + sizeof(Walk) * n_walk, 256);
     p.off_tasks = o;   o = align_up(o + sizeof(Task) * p.n_tasks, 256);
     p.off_iblocks = o; o = align_up(o + sizeof(IBlock) * p.n_iblocks, 256);
-    p.off_epi = o;     o = align_up(o + 2 * sizeof(float4) * p.n_i, 256);
+    p.off_epi = o;     o = align_up(o + (size_t)p.i_f4 * sizeof(float4) * p.n_i, 256);
     p.off_ide = o;     o = align_up(o + sizeof(int) * p.n_ide, 256);
     p.off_ids = o;     o = align_up(o + sizeof(int) * p.n_ids, 256);
     p.off_lepj = o;    o = align_up(o + (size_t)PB_EPJ_DEV_BYTES * p.n_lepj, 256);
@@ -464,7 +468,8 @@ void pack_walk(const WalkIn* win, bool direct, const pb_layout_epi& Li, HostPlan
     float4* epi = (float4*)(arena + p.off_epi);
     int* ide = (int*)(arena + p.off_ide);
     int* ids = (int*)(arena + p.off_ids);
-    const bool rel = (E.opt_coords == 0);
+    const bool rel = (p.coords != 1);
+    const int f4 = p.i_f4;
     Walk& W = hp.walks[w];
     const char* base = (const char*)win[w].epi;
     // Walk origin = mean position of the i-particles (robust against outliers, unlike the box
@@ -483,20 +488,22 @@ void pack_walk(const WalkIn* win, bool direct, const pb_layout_epi& Li, HostPlan
     }
     W.ohx = oh[0]; W.ohy = oh[1]; W.ohz = oh[2];
     W.olx = ol[0]; W.oly = ol[1]; W.olz = ol[2];
-    float4* e = epi + 2 * (size_t)W.i_off;           // two float4 per i: {x,y,z,rs}, {xl,yl,zl,0}
+    float4* e = epi + (size_t)f4 * (size_t)W.i_off;  // per i: {x,y,z,rs}, {xl,yl,zl,0} [, {float(x),float(y),float(z),0}: coords = 2]
     float hmax[3] = {0.f, 0.f, 0.f}, rsmax = 0.f;
     for (int i = 0; i < W.ni; i++) {
         const char* q = base + (size_t)i * Li.stride;
-        float r[3], rl[3];
+        float r[3], rl[3], xa[3];
         for (int k = 0; k < 3; k++) {
             float xh, xl;
             split(ld(q, Li.off_pos, k), xh, xl);
             rel_hilo(xh, xl, oh[k], ol[k], r[k], rl[k]);
             if (!rel) rl[k] = 0.f;
+            xa[k] = xh;
         }
         const float4 v = make_float4(r[0], r[1], r[2], (float)ld(q, Li.off_rsearch));
-        e[2 * i] = v;
-        e[2 * i + 1] = make_float4(rl[0], rl[1], rl[2], 0.f);
+        e[f4 * i] = v;
+        e[f4 * i + 1] = make_float4(rl[0], rl[1], rl[2], 0.f);
+        if (f4 == 3) e[f4 * i + 2] = make_float4(xa[0], xa[1], xa[2], 0.f);
         hmax[0] = std::max(hmax[0], std::fabs(v.x)); hmax[1] = std::max(hmax[1], std::fabs(v.y));
         hmax[2] = std::max(hmax[2], std::fabs(v.z)); rsmax = std::max(rsmax, v.w);
     }
@@ -551,7 +558,8 @@ cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, boo
     Params prm;
     prm.eps2 = p.count_only ? 0.f : (float)E.eps2;        // SearchNeighborEpEpNoSimd tests r2 without eps
     prm.rcut2 = (float)E.rcut2;
-    prm.abs_mode = E.opt_coords == 1 ? 1 : 0;
+    prm.abs_mode = p.count_only ? (p.coords == 1 ? 1 : 0) : p.coords;
+    prm.i_f4 = p.i_f4;
     prm.i_base = emit ? emit->i_base : 0;
     prm.pair_cap = emit ? (unsigned int)std::min<size_t>(emit->n_pairs_window, 0xffffffffu) : 0u;
     prm.pairs = emit ? emit->d_pairs : nullptr;
@@ -871,7 +879,7 @@ int pb_set_params(double eps2, double rcut2, double G) {
 
 int pb_set_option(const char* key, long long v) {
     if (!key) return fail(PB_ERR_ARG, "pb_set_option: null key");
-    if (!strcmp(key, "coords"))  { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "coords must be 0 or 1"); E.opt_coords = (int)v; return PB_OK; }
+    if (!strcmp(key, "coords"))  { if (v < 0 || v > 2) return fail(PB_ERR_ARG, "coords must be 0, 1 or 2"); E.opt_coords = (int)v; return PB_OK; }
     if (!strcmp(key, "streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "streams must be 1..%d", kMaxStreams); E.opt_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "jchunk"))  { if (v < 0 || v > (1 << 20)) return fail(PB_ERR_ARG, "jchunk out of range"); E.opt_jchunk = (int)v; return PB_OK; }
     if (!strcmp(key, "cull"))    { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "cull must be 0 or 1"); E.opt_cull = (int)v; return PB_OK; }
@@ -886,6 +894,18 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "occupancy")) { if (v < 2 || v > 3) return fail(PB_ERR_ARG, "occupancy must be 2 or 3"); E.opt_occ = (int)v; return PB_OK; }
     if (!strcmp(key, "nr"))      { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nr must be 0 or 1"); E.opt_nr = (int)v; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_set_option: unknown key '%s'", key);
+}
+
+int pb_get_option(const char* key, long long* v) {
+    if (!key || !v) return fail(PB_ERR_ARG, "pb_get_option: null argument");
+    const struct { const char* k; long long val; } tab[] = {
+        {"coords", E.opt_coords}, {"streams", E.opt_streams}, {"jchunk", E.opt_jchunk}, {"cull", E.opt_cull},
+        {"tree_fill", E.opt_tree_fill}, {"min_slot_work", E.opt_min_slot_work}, {"tree_streams", E.opt_tree_streams},
+        {"tree_spec", E.opt_tree_spec}, {"walk_ctas", E.opt_walk_ctas}, {"nb_lists", E.opt_nb_lists},
+        {"tree_batch", E.opt_tree_batch}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
+    for (const auto& t : tab)
+        if (!strcmp(key, t.k)) { *v = t.val; return PB_OK; }
+    return fail(PB_ERR_ARG, "pb_get_option: unknown key '%s'", key);
 }
 
 int pb_reserve_j(int n_epj, int n_spj, void** d_epj, void** d_spj) {

@@ -71,6 +71,8 @@ struct EpTile {                       // 128 pairs, 64 B per pair
     float2 c[kTilePairs];             // {r_search0^2, r_search1^2}
     float4 al[kTilePairs];            // {xl0, xl1, yl0, yl1} lo part (only read in "near" segments)
     float2 bl[kTilePairs];            // {zl0, zl1}
+    float4 ah[kTilePairs];            // {X0, X1, Y0, Y1}   ABSOLUTE position cast to float (coords = 2, near segments)
+    float2 bh[kTilePairs];            // {Z0, Z1}
 };
 struct SpTile {                       // 128 pairs, 96 B per pair
     float4 q0[kTilePairs];            // {x0, x1, y0, y1}
@@ -122,7 +124,7 @@ __device__ __forceinline__ bool ep_store(EpTile& t, int tid, int id, const EpReg
         rel_hilo(r.a.x, r.b.x, w.ohx, w.olx, x, xl);
         rel_hilo(r.a.y, r.b.y, w.ohy, w.oly, y, yl);
         rel_hilo(r.a.z, r.b.z, w.ohz, w.olz, z, zl);
-        if (abs_mode) { xl = 0.f; yl = 0.f; zl = 0.f; }   // reference arithmetic: dx = float(xj) - float(xi)
+        if (abs_mode == 1) { xl = 0.f; yl = 0.f; zl = 0.f; }   // reference arithmetic: dx = float(xj) - float(xi)
         m = r.a.w;
         rs2 = r.b.w * r.b.w;
         const float ex = fmaxf(fabsf(x) - w.hx, 0.f);
@@ -144,13 +146,24 @@ __device__ __forceinline__ bool ep_store(EpTile& t, int tid, int id, const EpReg
     c[s] = rs2;
     al[s] = xl; al[2 + s] = yl;
     bl[s] = zl;
+    if (abs_mode == 2) {                                   // float(x_j): what the CPU replay subtracts with (src/hard.hpp:1431)
+        float* ah = reinterpret_cast<float*>(&t.ah[p]);
+        float* bh = reinterpret_cast<float*>(&t.bh[p]);
+        ah[s] = r.a.x; ah[2 + s] = r.a.y;
+        bh[s] = r.a.z;
+    }
     return near;
 }
 
-// NEAR = false: fast loop (13 packed FP ops per pair).  NEAR = true: exact dx + neighbour count.
-template <int NR, bool NEAR>
+// NEAR = 0: fast loop (13 packed FP ops per pair).  NEAR = 1: exact dx + neighbour count.
+// NEAR = 2 (coords = 2, the drop-in default): as 1, and a pair that passes the neighbour test is evaluated from
+// dx = float(x_j) - float(x_i), ABSOLUTE coordinates cast to float — the very term PeTar's CPU changeover correction
+// re-computes in float and subtracts afterwards (`dr_32`, reference src/hard.hpp:1428-1442), so that it cancels; every
+// other pair keeps the walk-relative two-float dx.  (xih, yih, zih) = float(x_i).
+template <int NR, int NEAR>
 __device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
                                          float xi, float yi, float zi, float xil, float yil, float zil, float rsi2,
+                                         float xih, float yih, float zih,
                                          float eps2, float rcut2,
                                          float2& ax, float2& ay, float2& az, float2& pt, float2& cf) {
     const float2 nxi = bc(-xi), nyi = bc(-yi), nzi = bc(-zi), e2 = bc(eps2);
@@ -175,9 +188,21 @@ __device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
         if (NEAR) {
             // neighbour flags as 0.0f/1.0f, summed packed; exact (counts per tile are tiny)
             const float2 C = t.c[p];
-            const float2 f = make_float2((r2.x < fmaxf(C.x, rsi2)) ? 1.f : 0.f,
-                                         (r2.y < fmaxf(C.y, rsi2)) ? 1.f : 0.f);
-            cf = __fadd2_rn(cf, f);
+            const bool h0 = r2.x < fmaxf(C.x, rsi2), h1 = r2.y < fmaxf(C.y, rsi2);
+            cf = __fadd2_rn(cf, make_float2(h0 ? 1.f : 0.f, h1 ? 1.f : 0.f));
+            if (NEAR == 2) {
+                const float4 AH = t.ah[p];
+                const float2 BH = t.bh[p];
+                const float2 ex = __fadd2_rn(make_float2(AH.x, AH.y), bc(-xih));
+                const float2 ey = __fadd2_rn(make_float2(AH.z, AH.w), bc(-yih));
+                const float2 ez = __fadd2_rn(BH, bc(-zih));
+                dx = make_float2(h0 ? ex.x : dx.x, h1 ? ex.y : dx.y);
+                dy = make_float2(h0 ? ey.x : dy.x, h1 ? ey.y : dy.y);
+                dz = make_float2(h0 ? ez.x : dz.x, h1 ? ez.y : dz.y);
+                r2 = __ffma2_rn(dx, dx, e2);
+                r2 = __ffma2_rn(dy, dy, r2);
+                r2 = __ffma2_rn(dz, dz, r2);
+            }
         }
         const float2 r2c  = make_float2(fmaxf(r2.x, rcut2), fmaxf(r2.y, rcut2));
         const float2 ri   = rsqrt2<NR>(r2c);
@@ -446,10 +471,12 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
     // i-particle (registers): relative to the walk origin already (host formed x_i - origin in fp64)
     const int  i_loc  = task.i_first + ib * 32 + il;
     const bool ivalid = busy && (i_loc < w.ni);
-    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), pil = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), pil = make_float4(0.f, 0.f, 0.f, 0.f), pih = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ivalid) {
-        pi  = __ldg(epi + 2 * (size_t)(w.i_off + i_loc));        // {x, y, z, r_search}: relative position, hi part
-        pil = __ldg(epi + 2 * (size_t)(w.i_off + i_loc) + 1);    // {xl, yl, zl, -}: lo part
+        const float4* rec = epi + (size_t)prm.i_f4 * (size_t)(w.i_off + i_loc);
+        pi  = __ldg(rec);                                        // {x, y, z, r_search}: relative position, hi part
+        pil = __ldg(rec + 1);                                    // {xl, yl, zl, -}: lo part
+        if (prm.abs_mode == 2) pih = __ldg(rec + 2);             // {float(x), float(y), float(z), -}: absolute, as the CPU replay casts it
     }
     const float rsi2 = ivalid ? pi.w * pi.w : -1.f;
 
@@ -484,7 +511,9 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             if (busy) {
                 const int nv  = min(kTileJ, task.j_count - k * kTileJ);
                 const int npu = (((nv + 1) >> 1) + kPairUnroll - 1) & ~(kPairUnroll - 1);
-                const int p0  = js * ppw, p1 = min(p0 + ppw, npu);
+                // a ragged (last) tile is shared out evenly, in whole 16-pair segments, between the warps of an i-block
+                const int ppk = (nv == kTileJ) ? ppw : max(16, (((npu + task.jsplit - 1) / task.jsplit) + 15) & ~15);
+                const int p0  = js * ppk, p1 = min(p0 + ppk, npu);
                 float2 ax = bc(0.f), ay = bc(0.f), az = bc(0.f), pt = bc(0.f), cf = bc(0.f);
                 // 16-pair segments = the 32 j one staging warp wrote; count only where flagged
                 for (int seg0 = p0; seg0 < p1; seg0 += 16) {
@@ -495,10 +524,13 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                         if (near_flag[k & 1][seg0 >> 4])
                             ep_count_pairs<EMIT>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, cf,
                                                  jid[EMIT ? (k & 1) : 0], ivalid ? (unsigned int)(prm.i_base + w.i_off + i_loc) : 0xffffffffu, prm);
-                    } else if (near_flag[k & 1][seg0 >> 4])
-                        ep_pairs<NR, true>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
-                    else
-                        ep_pairs<NR, false>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                    } else if (near_flag[k & 1][seg0 >> 4]) {
+                        if (prm.abs_mode == 2)
+                            ep_pairs<NR, 2>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, pih.x, pih.y, pih.z, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                        else
+                            ep_pairs<NR, 1>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                    } else
+                        ep_pairs<NR, 0>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
                 }
                 kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
                 cnt += (int)(cf.x + cf.y);
@@ -529,7 +561,8 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             if (busy) {
                 const int nv  = min(kTileJ, task.j_count - k * kTileJ);
                 const int npu = ((nv + 1) >> 1);          // pairs with at least one real j (padding pairs are inert anyway)
-                const int p0  = js * ppw, p1 = min(p0 + ppw, npu);
+                const int ppk = (nv == kTileJ) ? ppw : (npu + task.jsplit - 1) / task.jsplit;   // ragged tile: even shares
+                const int p0  = js * ppk, p1 = min(p0 + ppk, npu);
                 float2 ax = bc(0.f), ay = bc(0.f), az = bc(0.f), pt = bc(0.f);
                 const int plen = (p1 - p0 + (1 << ishift) - 1) >> ishift;   // this lane's contiguous share of the warp's pairs
                 const int q0 = p0 + sub * plen, q1 = min(p1, q0 + plen);

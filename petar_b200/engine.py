@@ -79,11 +79,11 @@ LAYOUT_EPJ = LayoutEpj(EPJSoft.itemsize, _off(EPJSoft, "pos"), _off(EPJSoft, "ma
 LAYOUT_SPJ = LayoutSpj(SPJQuad.itemsize, _off(SPJQuad, "pos"), _off(SPJQuad, "mass"), _off(SPJQuad, "quad"), 1)
 LAYOUT_FORCE = LayoutForce(ForceSoft.itemsize, _off(ForceSoft, "acc"), _off(ForceSoft, "pot"), _off(ForceSoft, "n_ngb"))
 
-ABI_VERSION = 3   # PB_ABI_VERSION of include/petar_b200.h this module binds
+ABI_VERSION = 4   # PB_ABI_VERSION of include/petar_b200.h this module binds
 
 # every symbol include/petar_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "pb_init", "pb_finalize", "pb_abi_version", "pb_last_error", "pb_set_params", "pb_set_option",
+    "pb_init", "pb_finalize", "pb_abi_version", "pb_last_error", "pb_set_params", "pb_set_option", "pb_get_option",
     "pb_upload_j", "pb_dispatch_index", "pb_dispatch_direct", "pb_retrieve", "pb_get_profile",
     "pb_record_begin", "pb_record_end", "pb_replay", "pb_replay_launches",
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
@@ -116,6 +116,7 @@ def load():
     L.pb_last_error.restype = C.c_char_p
     L.pb_set_params.argtypes = [C.c_double, C.c_double, C.c_double]
     L.pb_set_option.argtypes = [C.c_char_p, C.c_longlong]
+    L.pb_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_longlong)]
     L.pb_upload_j.argtypes = [_vp, C.c_int, C.POINTER(LayoutEpj), _vp, C.c_int, C.POINTER(LayoutSpj)]
     L.pb_dispatch_index.argtypes = [C.c_int, _vp, _vp, C.POINTER(LayoutEpi), _vp, _vp, _vp, _vp]
     L.pb_dispatch_direct.argtypes = [C.c_int, _vp, _vp, C.POINTER(LayoutEpi), _vp, _vp, C.POINTER(LayoutEpj), _vp, _vp, C.POINTER(LayoutSpj)]
@@ -175,6 +176,12 @@ def check(rc, where):
 
 def set_option(key, value):
     check(load().pb_set_option(key.encode(), int(value)), f"pb_set_option({key})")
+
+
+def get_option(key):
+    v = C.c_longlong(0)
+    check(load().pb_get_option(key.encode(), C.byref(v)), f"pb_get_option({key})")
+    return int(v.value)
 
 
 def get_profile(reset=False):

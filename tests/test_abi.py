@@ -27,7 +27,7 @@ def test_header_symbols_all_exported():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/petar_b200.h but not exported"
     assert sorted(engine.ABI_SYMBOLS) == names
-    assert L.pb_abi_version() == engine.ABI_VERSION == 3
+    assert L.pb_abi_version() == engine.ABI_VERSION == 4
 
 
 def test_shim_defines_petar_symbols():
@@ -65,8 +65,13 @@ def test_no_gpu_fails_loudly():
 
 def test_options_validate():
     L = engine.load()
+    import ctypes as C
+    v = C.c_longlong(-1)
+    assert L.pb_get_option(b"coords", C.byref(v)) == 0 and v.value == 2           # the drop-in default
     assert L.pb_set_option(b"coords", 1) == 0 and L.pb_set_option(b"coords", 0) == 0
-    assert L.pb_set_option(b"coords", 2) == -3
+    assert L.pb_get_option(b"coords", C.byref(v)) == 0 and v.value == 0
+    assert L.pb_set_option(b"coords", 2) == 0
+    assert L.pb_set_option(b"coords", 3) == -3 and L.pb_get_option(b"nosuchkey", C.byref(v)) == -3
     assert L.pb_set_option(b"streams", 0) == -3
     assert L.pb_set_option(b"nosuchkey", 1) == -3
     assert L.pb_set_params(-1.0, 0.0, 1.0) == -3

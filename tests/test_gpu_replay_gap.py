@@ -1,0 +1,133 @@
+"""The drop-in combination: force kernel + the CPU changeover correction an UNMODIFIED PeTar applies afterwards.
+
+With `USE_GPU` defined PeTar's `calcAccPotShortWithLinearCutoff` (reference src/hard.hpp:1408-1476) removes, for every
+neighbour pair, the clamped term the kernel added by RE-COMPUTING it in float from absolute float-cast positions
+(`dr_32 = float(x_i) - float(x_j)`, :1428-1442) and adds the changeover-weighted fp64 term instead.  Whatever the kernel
+computed for that pair with another `dx` stays in the force as a residual `G m (dx_kernel - dr_32) / r_out^3`.
+
+This test measures exactly that on a Kroupa + binaries case, per coordinate mode of the library:
+
+    kernel force (coords 0 / 1 / 2)  +  float-replay correction (oracle, bit-identical to the reference function,
+                                        tests/test_oracle.py; cross-checked here against oracle/_ref when it travelled)
+    versus  fp64 oracle force + all-double correction   (= the changeover-weighted direct sum the code integrates)
+
+coords = 2 (the library's default, the drop-in mode): neighbour pairs are evaluated from the absolute float-cast `dx` the replay
+uses, everything else from walk-relative two-float positions.  Tolerance of BASELINE.json: <= 1e-6 median, <= 1e-4 max.
+Run as a script for the report that DESIGN.md quotes:  python tests/test_gpu_replay_gap.py
+"""
+import json
+
+import numpy as np
+import pytest
+
+from petar_b200 import engine, harness as hz
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def replay_gap_report(n_star=20000, f_bin=0.2, modes=(0, 1, 2), seed=1):
+    batch, epi_src, prm, P = hz.kroupa_binary_case(n_star, f_bin=f_bin, seed=seed)
+    eps, r_out, G = prm["eps"], prm["r_out"], prm["G"]
+    n = len(P["mass"])
+    p0 = hz.corr_particles(P)
+    off, idx = hz.neighbor_lists(P["pos"], 0.99 * P["rs"])        # FDPS searches with getRSearch() = 0.99 r_search (src/ptcl.hpp:8)
+    n_nb = np.diff(off) - 1                                       # neighbours besides the particle itself
+
+    def corrected(force, replay):
+        p = p0.copy()
+        p["acc"][epi_src] = force["acc"]
+        p["pot_tot"][epi_src] = force["pot"]
+        p["pot_soft"][epi_src] = force["pot"]
+        return ob.correct_force_tree_neighbor(p, off, idx, p0, eps, r_out, G, replay)
+
+    f64 = ob.walks_index(batch, eps, r_out, G)
+    truth = corrected(f64, False)
+    amag = np.linalg.norm(truth["acc"], axis=1)
+    has_nb = n_nb > 0
+    out = {"workload": f"kroupa N={n_star} f_bin={f_bin}: {n} tree particles, {int(off[-1]) - n} neighbour pairs, "
+                       f"{int(has_nb.sum())} particles with a neighbour, r_out={r_out:.3e}",
+           "modes": {}}
+    for mode in modes:
+        engine.set_option("coords", mode)
+        try:
+            f = engine.calc_force_all_and_write_back(batch, eps, r_out, G)
+        finally:
+            engine.set_option("coords", 2)
+        kern = np.linalg.norm(f["acc"] - f64["acc"], axis=1) / np.linalg.norm(f64["acc"], axis=1)
+        got = corrected(f, True)
+        err = np.linalg.norm(got["acc"] - truth["acc"], axis=1) / amag
+        epot = np.abs(got["pot_tot"] - truth["pot_tot"]) / np.abs(truth["pot_tot"])
+        resid = np.linalg.norm(got["acc"] - truth["acc"], axis=1)[has_nb] / n_nb[has_nb]
+        out["modes"][int(mode)] = {
+            "kernel_vs_fp64_oracle_acc": {"median": float(np.median(kern[epi_src.argsort()])), "max": float(kern.max())},
+            "corrected_vs_fp64_acc": {"median": float(np.median(err)), "median_with_neighbours": float(np.median(err[has_nb])),
+                                      "p99": float(np.percentile(err, 99)), "max": float(err.max())},
+            "corrected_vs_fp64_pot_tot": {"median": float(np.median(epot)), "max": float(epot.max())},
+            "abs_residual_per_neighbour": {"median": float(np.median(resid)), "max": float(resid.max())},
+            "n_ngb_equal_oracle": bool(np.array_equal(f["n_ngb"], f64["n_ngb"])),
+        }
+    return out
+
+
+@pytest.fixture(scope="module")
+def report():
+    return replay_gap_report()
+
+
+def test_dropin_default_mode_cancels_the_float_replay(report):
+    """coords = 2 + the reference's float replay: the corrected force meets the tolerance, and is far closer to the fp64
+    changeover force than the walk-relative kernel (coords = 0) combined with the same unmodified replay."""
+    print(json.dumps(report, indent=1))
+    m2, m0 = report["modes"][2], report["modes"][0]
+    assert m2["corrected_vs_fp64_acc"]["median"] <= 1e-6 and m2["corrected_vs_fp64_acc"]["max"] <= 1e-4
+    assert m2["corrected_vs_fp64_pot_tot"]["median"] <= 1e-6 and m2["corrected_vs_fp64_pot_tot"]["max"] <= 1e-4
+    assert m2["n_ngb_equal_oracle"]
+    assert m2["abs_residual_per_neighbour"]["median"] < 0.2 * m0["abs_residual_per_neighbour"]["median"]
+
+
+def test_absolute_mode_also_cancels_but_costs_far_field_accuracy(report):
+    """coords = 1 (the reference kernel's arithmetic for every pair) cancels the replay as well; its price is the fp32
+    rounding of absolute coordinates on all the non-neighbour pairs, visible in the kernel-level error."""
+    m1, m2 = report["modes"][1], report["modes"][2]
+    assert m1["corrected_vs_fp64_acc"]["max"] <= 1e-3
+    assert m2["kernel_vs_fp64_oracle_acc"]["median"] <= m1["kernel_vs_fp64_oracle_acc"]["median"]
+
+
+def test_library_default_is_the_replay_compatible_mode():
+    """The library is a drop-in for an unmodified hard.hpp: its default is coords = 2; the other modes are opt-in.
+    The modes differ on neighbour pairs only, never in the counts."""
+    assert engine.get_option("coords") == 2
+    batch, _, prm, _ = hz.kroupa_binary_case(3000, f_bin=0.2)
+    f2 = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"]).copy()
+    engine.set_option("coords", 0)
+    try:
+        f0 = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"]).copy()
+    finally:
+        engine.set_option("coords", 2)
+    assert not np.array_equal(f0["acc"], f2["acc"])
+    assert np.array_equal(f0["n_ngb"], f2["n_ngb"])
+    alone = f2["n_ngb"] == 1                                      # only itself within r_search: no pair uses the replay form
+    assert alone.any() and np.allclose(f0["acc"][alone], f2["acc"][alone], rtol=1e-12, atol=0)
+
+
+@pytest.mark.skipif(not ob.ref_changeover_available(), reason="oracle/_ref did not travel")
+def test_oracle_replay_equals_reference_function_on_real_neighbour_pairs():
+    """The correction loop used above is the oracle's; on a sample of this case's real neighbour pairs it equals the
+    reference's own pair function compiled with -DUSE_GPU (oracle/_ref/libpetar_ref_changeover_f32.so) bit for bit."""
+    _, _, prm, P = hz.kroupa_binary_case(5000, f_bin=0.2)
+    p0 = hz.corr_particles(P)
+    off, idx = hz.neighbor_lists(P["pos"], 0.99 * P["rs"])
+    rng = np.random.default_rng(0)
+    p0["acc"] = rng.normal(size=(len(p0), 3)); p0["pot_tot"] = rng.normal(size=len(p0)); p0["pot_soft"] = rng.normal(size=len(p0))
+    ii = np.repeat(np.arange(len(p0)), np.diff(off))
+    sel = np.nonzero(ii != idx)[0][:2000]
+    for k in sel:
+        a, b = p0[ii[k]:ii[k] + 1].copy(), p0[idx[k]:idx[k] + 1]
+        want = a.copy(); ob.ref_changeover_pair(want, b, prm["eps"], prm["r_out"], prm["G"], 1)
+        got = a.copy(); ob.changeover_pair(got, b, prm["eps"], prm["r_out"], prm["G"], 1)
+        assert got.tobytes() == want.tobytes()
+
+
+if __name__ == "__main__":
+    print(json.dumps(replay_gap_report(), indent=1))

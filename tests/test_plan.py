@@ -2,7 +2,7 @@
 through the test hook pb_debug_plan.
 
 * every (32-wide i-block, list entry) of every walk is covered by exactly one task of the right kind;
-* chunk starts are multiples of 8 and list offsets multiples of 4 entries: every index tile the force kernel
+* chunk starts are multiples of the 256-entry j tile (hence of 8) and list offsets multiples of 4 entries: every index tile the force kernel
   fetches with a bulk (TMA) copy then starts on a 16-byte boundary;
 * nib * jsplit <= 8 warps, i_first a multiple of 32, groups follow the binary 8/4/2/1 decomposition;
 * partial-sum slots of different (task, i-block) pairs never overlap and the reduction tables point at them."""
