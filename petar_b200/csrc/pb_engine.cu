@@ -151,6 +151,7 @@ struct Engine {
     bool spec_pending = false; int2* d_tree_caps = nullptr; size_t cap_tree_caps = 0;
     int opt_walk_ctas = 148 * 16;                          // CTAs (4 warps each, one warp per i-group at a time) of the tree-walk launches
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
+    int opt_chunk_tile = 1;                                // j chunks are whole 256-entry tiles (0: multiples of 8 entries, the round-1 plan)
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
     long long nb_n_i = 0;
 
@@ -413,7 +414,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
             if (nc == 0) continue;
             // equal chunks of whole j tiles: only the last chunk of a list ends in a ragged tile (which the warps that
             // share an i-block then split evenly, see force_kernel)
-            const int len = (int)align_up((size_t)(nj + nc - 1) / nc, kTileJ);
+            const int len = (int)align_up((size_t)(nj + nc - 1) / nc, E.opt_chunk_tile ? kTileJ : 8);
             for (int c = 0; c < nc; c++) {
                 const int jb = c * len;
                 if (jb >= nj) break;
@@ -888,6 +889,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "tree_streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "tree_streams must be in [1, %d]", kMaxStreams); E.opt_tree_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_spec")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_spec must be 0 or 1"); E.opt_tree_spec = (int)v; return PB_OK; }
     if (!strcmp(key, "walk_ctas")) { if (v < 1 || v > 148 * 16) return fail(PB_ERR_ARG, "walk_ctas must be in [1, 2368]"); E.opt_walk_ctas = (int)v; return PB_OK; }
+    if (!strcmp(key, "chunk_tile")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "chunk_tile must be 0 or 1"); E.opt_chunk_tile = (int)v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
     if (!strcmp(key, "lead"))    { if (v < 0 || v > 15) return fail(PB_ERR_ARG, "lead must be in [0, 15]"); E.opt_lead = (int)v; return PB_OK; }
@@ -902,7 +904,7 @@ int pb_get_option(const char* key, long long* v) {
         {"coords", E.opt_coords}, {"streams", E.opt_streams}, {"jchunk", E.opt_jchunk}, {"cull", E.opt_cull},
         {"tree_fill", E.opt_tree_fill}, {"min_slot_work", E.opt_min_slot_work}, {"tree_streams", E.opt_tree_streams},
         {"tree_spec", E.opt_tree_spec}, {"walk_ctas", E.opt_walk_ctas}, {"nb_lists", E.opt_nb_lists},
-        {"tree_batch", E.opt_tree_batch}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
+        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
     for (const auto& t : tab)
         if (!strcmp(key, t.k)) { *v = t.val; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_get_option: unknown key '%s'", key);

@@ -82,10 +82,43 @@ struct SpTile {                       // 128 pairs, 96 B per pair
     float4 q4[kTilePairs];            // {qxz0, qxz1, qyz0, qyz1}
     float2 q5[kTilePairs];            // {-eps2 tr0, -eps2 tr1}
 };
+constexpr int kTileBufs = 3;         // tile ring: tile k+1 is written while tile k (and, by slower warps, tile k-1) is read
 union __align__(16) Smem {
-    EpTile ep[2];
-    SpTile sp[2];
+    EpTile ep[kTileBufs];
+    SpTile sp[kTileBufs];
     double red[kWarpsPerCta][4][32];  // cross-warp combine when jsplit > 1
+};
+
+// Tile hand-over without a block-wide stall: every thread ARRIVES on the tile's mbarrier right after it has stored its
+// j of that tile and WAITS on it only when it starts to compute the tile — one whole tile of work later.  With three
+// buffers a warp may run a tile ahead of the slowest one, so the warps of a CTA drift apart and one warp's staging
+// overlaps the others' arithmetic (a __syncthreads per tile made all eight warps stage, then stall, together).
+struct TileBars {
+    alignas(8) unsigned long long full[kTileBufs];
+    __device__ __forceinline__ void init(int tid) {                       // followed by a __syncthreads
+        if (tid == 0) {
+            for (int b = 0; b < kTileBufs; ++b) {
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&full[b]);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(kThreads) : "memory");
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __device__ __forceinline__ void arrive(int b) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&full[b]);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+    }
+    __device__ __forceinline__ void wait(int b, unsigned parity) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&full[b]);
+        asm volatile("{\n"
+                     ".reg .pred P1;\n"
+                     "TB_WAIT:\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                     "@P1 bra TB_DONE;\n"
+                     "bra TB_WAIT;\n"
+                     "TB_DONE:\n"
+                     "}" :: "r"(bar), "r"(parity) : "memory");
+    }
 };
 
 constexpr float kPadPos = 1.0e10f;    // padded j: far away, zero mass, never a neighbour
@@ -424,8 +457,8 @@ struct IdPipe {
         return j < j_count ? __ldg(ids + j) : -1;
 #endif
     }
-    // after the block barrier that ends iteration k: every thread has read tiles <= k+2 = ring entries
-    // <= k, so the slot of entry k is free for entry k + kIdRing
+    // once every thread has read tiles <= k+2 = ring entries <= k (the caller knows: all of them have arrived on the
+    // mbarrier of tile k+1, which they do after that read), the slot of entry k is free for entry k + kIdRing
     __device__ __forceinline__ void refill(int k, int tid) const {
 #if PB_TMA_IDS
         if (ids && tid == 0 && k + kIdRing + kIdDirect < n_tiles) issue(k + kIdRing);
@@ -445,9 +478,10 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
              double4* __restrict__ part4, int* __restrict__ partn, Params prm)
 {
     __shared__ Smem sm;
-    __shared__ int near_flag[2][kWarpsPerCta];   // per tile buffer, per staging warp (= 16-pair segment)
+    __shared__ int near_flag[kTileBufs][kWarpsPerCta];   // per tile buffer, per staging warp (= 16-pair segment)
     __shared__ IdRing ring;                      // index tiles, filled by TMA bulk copies
-    __shared__ int jid[EMIT ? 2 : 1][EMIT ? kTileJ : 1];   // store index of every staged j (neighbour-list emission only)
+    __shared__ TileBars bars;                    // tile hand-over (see TileBars)
+    __shared__ int jid[EMIT ? kTileBufs : 1][EMIT ? kTileJ : 1];   // store index of every staged j (neighbour-list emission only)
 
     const Task task = tasks[blockIdx.x];
     const Walk w    = walks[task.walk];
@@ -486,29 +520,37 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
 
     const int n_tiles = (task.j_count + kTileJ - 1) / kTileJ;
 
+    // Tile pipeline (both kinds): index tiles arrive by TMA up to four tiles ahead, ids are picked up two tiles ahead,
+    // the gathered j records one tile ahead; tile k+1 is stored (and its mbarrier arrived on) after tile k was
+    // computed, and waited for only at the start of iteration k+1.
+    bars.init(tid);
     if (task.kind == 0 || task.kind == 2) {
         const bool count_only = (task.kind == 2);     // neighbour search only (tree_nb): no force math
         const int* ids = (w.ej_off >= 0) ? id_epj + w.ej_off + task.j_begin : nullptr;   // ej_off < 0: dense list
         const int dbase = task.j_begin;
-        // software pipeline: index tiles arrive by TMA up to five tiles ahead, ids are picked up two
-        // tiles ahead, the gathered j records one tile ahead
         IdPipe idp;
         idp.init(ids, task.j_count, n_tiles, dbase, &ring, tid);
         int id_cur = idp.get(0, tid);
         EpRegs jr  = ep_load_j(epj, id_cur);
         int id_nxt = idp.get(1, tid);
+        __syncthreads();                               // mbarrier inits (tile ring, index ring) visible to every thread
         {
             const bool nr_ = ep_store(sm.ep[0], tid, id_cur, jr, w, prm.abs_mode);
             const unsigned bal = __ballot_sync(0xffffffffu, nr_);
             if (lane == 0) near_flag[0][warp] = (bal != 0u);
             if (EMIT) jid[0][tid] = id_cur;
+            bars.arrive(0);
         }
-        __syncthreads();
+        int cb = 0; unsigned cpar = 0;                 // buffer and mbarrier phase parity of tile k
         for (int k = 0; k < n_tiles; ++k) {
             const bool more = (k + 1 < n_tiles);
+            const int nb = (cb + 1 == kTileBufs) ? 0 : cb + 1;
             if (more) jr = ep_load_j(epj, id_nxt);
             const int id_nn = idp.get(k + 2, tid);
+            bars.wait(cb, cpar);                       // every thread has stored its j of tile k
+            if (k >= 1) idp.refill(k - 1, tid);        // ... and had read the ids of tile k+1 before that
             if (busy) {
+                const EpTile& T = sm.ep[cb];
                 const int nv  = min(kTileJ, task.j_count - k * kTileJ);
                 const int npu = (((nv + 1) >> 1) + kPairUnroll - 1) & ~(kPairUnroll - 1);
                 // a ragged (last) tile is shared out evenly, in whole 16-pair segments, between the warps of an i-block
@@ -521,29 +563,29 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                     const int seg = seg0 + sub * (16 >> ishift);
                     const int e = min(min(seg0 + 16, p1), seg + (16 >> ishift));
                     if (count_only) {
-                        if (near_flag[k & 1][seg0 >> 4])
-                            ep_count_pairs<EMIT>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, cf,
-                                                 jid[EMIT ? (k & 1) : 0], ivalid ? (unsigned int)(prm.i_base + w.i_off + i_loc) : 0xffffffffu, prm);
-                    } else if (near_flag[k & 1][seg0 >> 4]) {
+                        if (near_flag[cb][seg0 >> 4])
+                            ep_count_pairs<EMIT>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, prm.eps2, cf,
+                                                 jid[EMIT ? cb : 0], ivalid ? (unsigned int)(prm.i_base + w.i_off + i_loc) : 0xffffffffu, prm);
+                    } else if (near_flag[cb][seg0 >> 4]) {
                         if (prm.abs_mode == 2)
-                            ep_pairs<NR, 2>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, pih.x, pih.y, pih.z, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                            ep_pairs<NR, 2>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, pih.x, pih.y, pih.z, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
                         else
-                            ep_pairs<NR, 1>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                            ep_pairs<NR, 1>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
                     } else
-                        ep_pairs<NR, 0>(sm.ep[k & 1], seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                        ep_pairs<NR, 0>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
                 }
                 kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
                 cnt += (int)(cf.x + cf.y);
             }
             if (more) {
-                const bool nr_ = ep_store(sm.ep[(k + 1) & 1], tid, id_nxt, jr, w, prm.abs_mode);
+                const bool nr_ = ep_store(sm.ep[nb], tid, id_nxt, jr, w, prm.abs_mode);
                 const unsigned bal = __ballot_sync(0xffffffffu, nr_);
-                if (lane == 0) near_flag[(k + 1) & 1][warp] = (bal != 0u);
-                if (EMIT) jid[(k + 1) & 1][tid] = id_nxt;
+                if (lane == 0) near_flag[nb][warp] = (bal != 0u);
+                if (EMIT) jid[nb][tid] = id_nxt;
+                bars.arrive(nb);
             }
             id_nxt = id_nn;
-            __syncthreads();
-            idp.refill(k, tid);
+            cb = nb; if (nb == 0) cpar ^= 1u;
         }
     } else {
         const int* ids = id_spj + w.sj_off + task.j_begin;
@@ -552,29 +594,34 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
         int id_cur = idp.get(0, tid);
         SpRegs jr  = sp_load_j(spj, id_cur);
         int id_nxt = idp.get(1, tid);
+        __syncthreads();                               // mbarrier inits visible
         sp_store(sm.sp[0], tid, id_cur, jr, w, prm.eps2);
-        __syncthreads();
+        bars.arrive(0);
+        int cb = 0; unsigned cpar = 0;
         for (int k = 0; k < n_tiles; ++k) {
             const bool more = (k + 1 < n_tiles);
+            const int nb = (cb + 1 == kTileBufs) ? 0 : cb + 1;
             if (more) jr = sp_load_j(spj, id_nxt);
             const int id_nn = idp.get(k + 2, tid);
+            bars.wait(cb, cpar);
+            if (k >= 1) idp.refill(k - 1, tid);
             if (busy) {
                 const int nv  = min(kTileJ, task.j_count - k * kTileJ);
                 const int npu = ((nv + 1) >> 1);          // pairs with at least one real j (padding pairs are inert anyway)
                 const int ppk = (nv == kTileJ) ? ppw : (npu + task.jsplit - 1) / task.jsplit;   // ragged tile: even shares
                 const int p0  = js * ppk, p1 = min(p0 + ppk, npu);
                 float2 ax = bc(0.f), ay = bc(0.f), az = bc(0.f), pt = bc(0.f);
-                const int plen = (p1 - p0 + (1 << ishift) - 1) >> ishift;   // this lane's contiguous share of the warp's pairs
+                const int plen = (max(p1 - p0, 0) + (1 << ishift) - 1) >> ishift;   // this lane's contiguous share of the warp's pairs
                 const int q0 = p0 + sub * plen, q1 = min(p1, q0 + plen);
-                sp_pairs<NR>(sm.sp[k & 1], q0, q1, pi.x, pi.y, pi.z, prm.eps2, ax, ay, az, pt);
+                sp_pairs<NR>(sm.sp[cb], q0, q1, pi.x, pi.y, pi.z, prm.eps2, ax, ay, az, pt);
                 kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
             }
-            if (more) sp_store(sm.sp[(k + 1) & 1], tid, id_nxt, jr, w, prm.eps2);
+            if (more) { sp_store(sm.sp[nb], tid, id_nxt, jr, w, prm.eps2); bars.arrive(nb); }
             id_nxt = id_nn;
-            __syncthreads();
-            idp.refill(k, tid);
+            cb = nb; if (nb == 0) cpar ^= 1u;
         }
     }
+    __syncthreads();       // every warp is done with the tile buffers (they are reused for the cross-warp combine below)
 
     // per-warp totals as exact doubles (hi + lo)
     double dax = kx.value(), day = ky.value(), daz = kz.value(), dpt = kp.value();
@@ -586,7 +633,6 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
 
     if (task.jsplit > 1) {
         // combine the jsplit warps that share an i-block, in fixed order js = 0,1,...
-        // (the loop above ended with __syncthreads, so the tile buffers may be reused)
         if (busy) {
             sm.red[warp][0][lane] = dax; sm.red[warp][1][lane] = day;
             sm.red[warp][2][lane] = daz; sm.red[warp][3][lane] = dpt;

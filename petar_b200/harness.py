@@ -378,3 +378,22 @@ def neighbor_lists(pos, rs):
     off = np.cumsum(off)
     assert off[-1] < 2 ** 31
     return off.astype(np.int32), jj.astype(np.int32)
+
+
+def neighbor_lists_subset(pos, rs, subset):
+    """As :func:`neighbor_lists`, for the particles `subset` only: CSR over the subset, j over ALL particles."""
+    from scipy.spatial import cKDTree
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    rs = np.ascontiguousarray(rs, dtype=np.float64)
+    subset = np.asarray(subset, dtype=np.int64)
+    tree = cKDTree(pos)
+    hits = tree.query_ball_point(pos[subset], float(rs.max()), workers=-1, return_sorted=True)
+    cnt = np.fromiter((len(h) for h in hits), dtype=np.int64, count=len(subset))
+    ii = np.repeat(np.arange(len(subset), dtype=np.int64), cnt)
+    jj = np.fromiter((j for h in hits for j in h), dtype=np.int64, count=int(cnt.sum()))
+    d2 = ((pos[subset[ii]] - pos[jj]) ** 2).sum(axis=1)
+    keep = d2 < np.maximum(rs[subset[ii]], rs[jj]) ** 2
+    ii, jj = ii[keep], jj[keep]
+    off = np.zeros(len(subset) + 1, dtype=np.int64)
+    np.add.at(off, ii + 1, 1)
+    return np.cumsum(off).astype(np.int32), jj.astype(np.int32)

@@ -40,4 +40,17 @@ def _native_libs():
     yield
 
 
+@pytest.fixture
+def coords0():
+    """Kernel-level parity — kernel output against the fp64 NoSimd functors — is a statement about option coords = 0
+    (walk-relative two-float dx for every pair).  The library's default, coords = 2, deliberately evaluates neighbour
+    pairs from the absolute float-cast dx that PeTar's CPU correction replays and subtracts (reference
+    src/hard.hpp:1428-1442); its parity statement is about the CORRECTED force and is tested in
+    tests/test_gpu_replay_gap.py, tests/test_gpu_fullsize.py and by smoke() / bench.py (oracle/dropin_check.py)."""
+    from petar_b200 import engine
+    engine.set_option("coords", 0)
+    yield
+    engine.set_option("coords", 2)
+
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")

@@ -10,7 +10,7 @@ from petar_b200.types import PtclCorr, LARGE_FLOAT
 from petar_b200.walks import WalkBatch
 from oracle import binding as ob
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("coords0")]   # kernel-level parity: see conftest.coords0
 
 
 def _random_set(n, r_out_g, seed, clump=0.3):

@@ -14,7 +14,7 @@ import pytest
 from petar_b200 import engine, harness as hz
 from oracle import binding as ob
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("coords0")]   # kernel-level parity: see conftest.coords0
 
 N, EPS, G = 1024, 0.02, 1.0
 R_OUT = 0.5 * EPS

@@ -11,7 +11,7 @@ from petar_b200 import engine, harness as hz
 from petar_b200.types import EPISoft, EPJSoft
 from oracle import binding as ob
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("coords0")]   # kernel-level parity: see conftest.coords0
 
 
 def _oracle(points, pos, mass, G):

@@ -15,13 +15,20 @@ from petar_b200 import engine, harness as hz
 from petar_b200.walks import WalkBatch
 from oracle import binding as ob
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("coords0")]   # kernel-level parity: see conftest.coords0
+
+
+_FULL = {}
 
 
 @pytest.fixture(scope="module")
 def full():
-    batch, _, prm, P = hz.kroupa_binary_case(1000000)
+    batch, epi_src, prm, P = hz.kroupa_binary_case(1000000)
+    engine.set_option("coords", 2)                       # the library default: the drop-in mode, checked on the corrected force
+    f_dropin = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"]).copy()
+    engine.set_option("coords", 0)                       # kernel-level parity statements below
     f = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"])
+    _FULL.update(epi_src=epi_src, P=P, f_dropin=f_dropin)
     return batch, prm, f
 
 
@@ -55,6 +62,33 @@ def test_fullsize_oracle_sample(full):
     assert np.median(ea) <= 1e-6 and ea.max() <= 1e-4
     assert np.median(ep) <= 1e-6 and ep.max() <= 1e-4
     assert nbad <= 1e-4 * len(ea)
+
+
+def test_fullsize_dropin_mode_sample(full):
+    """The library default (coords = 2) at full size: kernel force + the float-replay correction an unmodified PeTar
+    applies against fp64 oracle + all-double correction, on the particles of 96 sampled walks (oracle/dropin_check.py)."""
+    from oracle.dropin_check import DropinChecker
+    batch, prm, f0 = full
+    fd, epi_src, P = _FULL["f_dropin"], _FULL["epi_src"], _FULL["P"]
+    rng = np.random.default_rng(0)
+    ws = np.sort(rng.choice(batch.n_walk, 96, replace=False))
+    rows = np.concatenate([np.arange(batch.i_off[w], batch.i_off[w + 1]) for w in ws])
+    refs = []
+    for w in ws:
+        i0, i1 = batch.i_off[w], batch.i_off[w + 1]
+        sub = WalkBatch(batch.epj, batch.spj, batch.epi[i0:i1], [0, i1 - i0], batch.id_epj[batch.ej_off[w]:batch.ej_off[w + 1]],
+                        [0, batch.ej_off[w + 1] - batch.ej_off[w]], batch.id_spj[batch.sj_off[w]:batch.sj_off[w + 1]],
+                        [0, batch.sj_off[w + 1] - batch.sj_off[w]])
+        refs.append(ob.walks_index(sub, prm["eps"], prm["r_out"], prm["G"]))
+    ref = np.concatenate(refs)
+    chk = DropinChecker(P, prm, subset=epi_src[rows])
+    rep = chk.compare(fd[rows], ref)
+    rep0 = chk.compare(f0[rows], ref)                    # the walk-relative kernel with the same unmodified replay, for contrast
+    print(f"[N=1e6 drop-in, 96 walks] coords=2 + float replay: {rep}")
+    print(f"[N=1e6 drop-in, 96 walks] coords=0 + float replay: acc {rep0['acc_rel_err']} residual/neighbour {rep0['abs_residual_per_neighbour']}")
+    assert np.array_equal(fd["n_ngb"], f0["n_ngb"])
+    assert rep["pass"], rep
+    assert rep["abs_residual_per_neighbour"]["median"] < 0.2 * rep0["abs_residual_per_neighbour"]["median"]
 
 
 def test_fullsize_determinism_and_mass_scaling(full):

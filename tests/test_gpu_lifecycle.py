@@ -10,7 +10,7 @@ from petar_b200.types import ForceSoft
 from petar_b200.walks import WalkBatch
 from oracle import binding as ob
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("coords0")]   # kernel-level parity: see conftest.coords0
 
 
 def _tol(f_acc, f_pot, ref):

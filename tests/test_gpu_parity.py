@@ -17,7 +17,7 @@ from petar_b200.walks import WalkBatch
 from oracle import binding as ob
 from conftest import GOLDEN
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("coords0")]   # kernel-level parity: see conftest.coords0
 
 TOL_MED = 1e-6
 TOL_MAX = 1e-4
@@ -247,7 +247,7 @@ def test_absolute_coordinate_mode_matches_reference_kernel_arithmetic(plummer100
                     batch.ej_off[:nw + 1], batch.id_spj[:batch.sj_off[nw]], batch.sj_off[:nw + 1])
     engine.set_option("coords", 1)
     f = engine.calc_force_all_and_write_back(sub, prm["eps"], prm["r_out"], prm["G"])
-    engine.set_option("coords", 2)
+    engine.set_option("coords", 0)
     rounded = WalkBatch(sub.epj.copy(), sub.spj.copy(), sub.epi.copy(), sub.i_off, sub.id_epj, sub.ej_off, sub.id_spj, sub.sj_off)
     rounded.epj["pos"] = rounded.epj["pos"].astype(np.float32)
     rounded.epi["pos"] = rounded.epi["pos"].astype(np.float32)

@@ -8,7 +8,7 @@ import pytest
 from petar_b200 import engine, harness as hz
 from oracle import binding as ob
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("coords0")]   # kernel-level parity: see conftest.coords0
 
 
 @pytest.mark.skipif(not ob.ref_cuda_available(), reason="oracle/_ref/libpetar_ref_cuda.so not built")
