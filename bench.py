@@ -424,7 +424,7 @@ def main():
                 # the tree is written straight into the library's pinned staging buffers, as a converter from FDPS's
                 # cells would do it
                 cells, groups = batch.tree.export_tree(out=engine.tree_stage(batch.tree.n_nodes, batch.n_walk))
-                dw_step = lambda: engine.tree_force(batch, cells, groups, eps, r_out, G, force=force)
+                dw_step = lambda: engine.tree_force(batch, cells, groups, eps, r_out, G, force=force, resident=True)
             else:
                 cells, groups = wl["tree_cells"], wl["tree_groups"]
                 dw_step = lambda: stepper.step_device_walk(force)
@@ -440,6 +440,7 @@ def main():
             device_walk = {"ms_per_step": sec_dw * 1e3, "value": (I_ep + I_sp) / sec_dw * 1e-9, "unit": "Ginteractions/s",
                            "h2d_bytes_per_step": pdw["h2d_bytes"] / args.steps, "d2h_bytes_per_step": pdw["d2h_bytes"] / args.steps,
                            "n_cells": int(len(cells)), "n_groups": int(len(groups)),
+                           "device_timeline_ms": (engine.tree_timeline() if stepper is None else None),
                            "host_walk_ms_for_context": batch.tree.timing()[1] * 1e3,
                            "note": "j + tree uploaded from host buffers every step, lists built on the GPU (pb_tree_upload / pb_tree_force); "
                                    "host_walk_ms = the harness's OpenMP walk that produced the lists the e2e leg is given for free"}

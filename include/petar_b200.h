@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 4
+#define PB_ABI_VERSION 5
 
 typedef enum pb_status {
     PB_OK = 0,
@@ -241,6 +241,18 @@ int  pb_tree_stage(int n_cells, int n_groups, pb_tree_cell** cells, pb_tree_grou
 /* Forces on all i-particles, given in group order (group 0's particles first, ...); ASSIGNS
  * force[k].{acc,pot,n_ngb}.  Synchronous.  Both arrays are contiguous with the given layouts. */
 int  pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const pb_layout_force* lforce);
+/* The same step, device-resident: the i-particles are NOT passed — group g's i-particles are EP store slots
+ * [groups[g].first, groups[g].first + groups[g].n) (upload the local particles in i-group order, as FDPS's epi_sorted
+ * is) — and i-particle preparation, task planning, forces and reduction all run on the GPU (pb_plan.cu, one persistent
+ * force launch).  From the second tree step on no host round trip sits between the uploads and the result: list
+ * space, task and partial-sum buffers are reserved from the previous step's sizes, the true sizes come back with the
+ * forces, and a step whose reservation was too small is detected on the device and repeated exactly.  ASSIGNS
+ * force[k].{acc,pot,n_ngb} in group order.  Synchronous. */
+int  pb_tree_force_resident(void* force, const pb_layout_force* lforce);
+/* Device timeline of the last pb_tree_force_resident step, milliseconds between consecutive CUDA events on the step's
+ * stream: ms[0] tree walk (list building), [1] wait for the j store (local upload, collectives), [2] i-particle
+ * preparation + task planning, [3] force kernel, [4] reduction, [5] result copy to the host. */
+int  pb_tree_timeline(float* ms, int n);
 /* Test hook: the lists the last pb_tree_force built.  n_ep/n_sp: per group counts (n_groups each);
  * id_ep/id_sp: concatenated lists in group order, at most cap_* entries are written. */
 int  pb_tree_lists(int* n_ep, int* n_sp, int* id_ep, long long cap_ep, int* id_sp, long long cap_sp);
@@ -295,6 +307,14 @@ int  pb_upload_j_range(const void* epj, int epj_first, int n_epj, const pb_layou
  * the stream a NCCL collective writing into the store was enqueued on) has completed, and mark
  * the j store as published. */
 int  pb_publish_j(void* cuda_stream);
+/* LET send rows gathered ON THE DEVICE: d_out32[k] = EP store row idx[k] (device j format, 32 B), k < n.  `idx` is a
+ * host array of EP store slots (the local particles a peer's domain needs, as FDPS's LET selection names them);
+ * `d_out32` a device buffer (e.g. the send buffer of the NCCL all-to-all).  Queued on the library's upload stream,
+ * behind pb_upload_j_range's copy of those particles: 4 B per row cross PCIe instead of a host-packed 32 B row. */
+int  pb_let_gather_epj(const int* idx, int n, void* d_out32);
+/* Make `cuda_stream` (a cudaStream_t, e.g. the stream the collective is enqueued on) wait for everything queued so
+ * far on the library's upload stream (pb_upload_j_range, pb_let_gather_epj). */
+int  pb_stream_wait_upload(void* cuda_stream);
 /* Pack host j to the device format into caller-provided HOST buffers (for building LET send
  * buffers). */
 int  pb_pack_epj_host(const void* epj, int n, const pb_layout_epj* l, void* out32);

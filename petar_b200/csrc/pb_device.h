@@ -67,6 +67,7 @@ struct ForceOut {
 struct Params {
     float eps2;
     float rcut2;
+    float rinv_cut;       // coords = 2: float(1 / sqrt(double(rcut2))), the CPU replay's 1/r inside the cutoff
     int   abs_mode;       // option "coords": 0 walk-relative two-float dx; 1 absolute float-cast dx for every pair;
                           // 2 walk-relative, but pairs that pass the neighbour test use the absolute float-cast dx
     int   i_f4;           // float4 per packed i-particle: 2, or 3 with the absolute float-cast position (coords = 2)
@@ -76,6 +77,7 @@ struct Params {
     unsigned int pair_cap;
     unsigned long long* pairs;
     unsigned int* pair_cursor;
+    int* meta;            // persistent launches (device-made plan): [0] task count, [4] task cursor
 };
 
 // Two-float position relative to the walk origin: hi + lo = (xh + xl) - (oh + ol) to ~2^-46,
@@ -99,8 +101,20 @@ cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_bloc
                          const float4* epj, const float4* spj,
                          double4* part4, int* partn, Params p, bool emit_pairs = false);
 
+cudaError_t launch_force_persistent(cudaStream_t s, int n_ctas, int nr_steps,
+                                    const Walk* walks, const Task* tasks, const float4* epi, const int* id_epj, const int* id_spj,
+                                    const float4* epj, const float4* spj, double4* part4, int* partn, Params p);
+
+// device-side i-particle preparation and task planning (pb_plan.cu)
+cudaError_t launch_iprep(cudaStream_t s, const void* groups, int n_groups, const int* i_first, const int2* counts, const int2* offs,
+                         const float4* epj, Walk* walks, float4* epi, int i_f4, int coords, int cull);
+cudaError_t launch_devplan(cudaStream_t s, const void* groups, int n_groups, const int* i_first, const int2* counts, int U, int Us,
+                           int3* goff, int* meta, int cap_tasks, long long cap_part, Task* tasks, IBlock* iblocks, const int2* caps);
+cudaError_t launch_gather_epj(cudaStream_t s, const float4* epj, const int* idx, int n, float4* out);
+void plan_sizes_host(const int* ni, const int2* counts, int n_groups, int U, int Us, long long* n_tasks, long long* n_part, long long* n_iblk);
+
 cudaError_t launch_reduce(cudaStream_t s, int n_iblocks, const IBlock* iblocks,
-                          const double4* part4, const int* partn, ForceOut* out, double G);
+                          const double4* part4, const int* partn, ForceOut* out, double G, const int* meta = nullptr);
 
 // device-side list building (pb_walk.cu); cells / groups are pb_tree_cell / pb_tree_group arrays
 cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,

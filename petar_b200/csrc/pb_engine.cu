@@ -155,6 +155,17 @@ struct Engine {
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
     long long nb_n_i = 0;
 
+    // device-resident tree step (pb_tree_force_resident): i-particles, plan and forces never visit the host
+    int* d_ifirst = nullptr; int* h_ifirst = nullptr; size_t cap_ifirst = 0; long long r_n_i = 0; int r_n_iblk = 0;
+    Walk* d_r_walks = nullptr; int3* d_r_goff = nullptr; size_t cap_r_groups = 0;
+    float4* d_r_epi = nullptr; ForceOut* d_r_out = nullptr; ForceOut* h_r_out = nullptr; IBlock* d_r_iblocks = nullptr; size_t cap_r_i = 0;
+    Task* d_r_tasks = nullptr; size_t cap_r_tasks = 0;
+    double4* d_r_part4 = nullptr; int* d_r_partn = nullptr; size_t cap_r_part = 0;
+    int* d_r_meta = nullptr; int* h_r_meta = nullptr;
+    long long r_prev_tasks = 0, r_prev_part = 0;
+    cudaEvent_t ev_tl[8] = {nullptr}; bool tl_valid = false; float tl_ms[8] = {0};
+    int* d_let_idx = nullptr; int* h_let_idx = nullptr; size_t cap_let_idx = 0;      // LET send lists (EP store slots)
+
     pb_profile prof;
 };
 
@@ -554,17 +565,29 @@ void pack_batch(const WalkIn* win, bool direct, const pb_layout_epi& Li,
     pack_tail(win, direct, Lj, Ls, hp, arena);
 }
 
-cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, bool direct,
-                        double4* part4, int* partn, ForceOut* out, bool force_only = false, const Slot* emit = nullptr) {
+Params make_params(const Plan& p, const Slot* emit) {
     Params prm;
     prm.eps2 = p.count_only ? 0.f : (float)E.eps2;        // SearchNeighborEpEpNoSimd tests r2 without eps
     prm.rcut2 = (float)E.rcut2;
+    if (p.coords == 2) {
+        // the CPU replay clamps with r_out_32 * r_out_32 in float and takes 1/sqrt in double (src/hard.hpp:1428-1436)
+        const float r32 = (float)std::sqrt(E.rcut2);
+        prm.rcut2 = r32 * r32;
+        prm.rinv_cut = prm.rcut2 > 0.f ? (float)(1.0 / std::sqrt((double)prm.rcut2)) : 0.f;
+    } else prm.rinv_cut = 0.f;
     prm.abs_mode = p.count_only ? (p.coords == 1 ? 1 : 0) : p.coords;
     prm.i_f4 = p.i_f4;
     prm.i_base = emit ? emit->i_base : 0;
     prm.pair_cap = emit ? (unsigned int)std::min<size_t>(emit->n_pairs_window, 0xffffffffu) : 0u;
     prm.pairs = emit ? emit->d_pairs : nullptr;
     prm.pair_cursor = emit ? emit->d_cursor : nullptr;
+    prm.meta = nullptr;
+    return prm;
+}
+
+cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, bool direct,
+                        double4* part4, int* partn, ForceOut* out, bool force_only = false, const Slot* emit = nullptr) {
+    Params prm = make_params(p, emit);
     const float4* epj = direct ? (const float4*)(d_arena + p.off_lepj) : E.d_epj;
     const float4* spj = direct ? (const float4*)(d_arena + p.off_lspj) : E.d_spj;
     cudaError_t e = launch_force(st, p.n_tasks, E.opt_nr, E.opt_occ,
@@ -860,6 +883,10 @@ void pb_finalize(void) {
     for (int s = 0; s < kMaxStreams; s++) cudaFree(E.d_walk_scratch[s]);
     cudaFree(E.d_tree_ide); cudaFree(E.d_tree_ids); cudaFree(E.d_tree_off); cudaFree(E.d_tree_caps);
     cudaFreeHost(E.h_counts_p); cudaFreeHost(E.h_over_p);
+    cudaFree(E.d_ifirst); cudaFreeHost(E.h_ifirst); cudaFree(E.d_r_walks); cudaFree(E.d_r_goff); cudaFree(E.d_r_epi); cudaFree(E.d_r_out);
+    cudaFreeHost(E.h_r_out); cudaFree(E.d_r_iblocks); cudaFree(E.d_r_tasks); cudaFree(E.d_r_part4); cudaFree(E.d_r_partn);
+    cudaFree(E.d_r_meta); cudaFreeHost(E.h_r_meta); cudaFree(E.d_let_idx); cudaFreeHost(E.h_let_idx);
+    for (int k = 0; k < 8; k++) if (E.ev_tl[k]) cudaEventDestroy(E.ev_tl[k]);
     if (E.ev_count) cudaEventDestroy(E.ev_count);
     if (E.ev_fill) cudaEventDestroy(E.ev_fill);
     cudaEventDestroy(E.ev_j_ready); cudaEventDestroy(E.ev_send0); cudaEventDestroy(E.ev_send1);
@@ -984,6 +1011,42 @@ int pb_upload_j(const void* epj, int n_epj, const pb_layout_epj* lepj,
     if ((rc = pb_upload_j_range(epj, 0, n_epj, lepj, spj, 0, n_spj, lspj)) != PB_OK) return rc;
     CU(cudaEventRecord(E.ev_j_ready, E.s_upload)); E.j_epoch++;
     E.j_published = true;
+    return PB_OK;
+}
+
+int pb_let_gather_epj(const int* idx, int n, void* d_out32) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    if (n < 0 || (n && (!idx || !d_out32))) return fail(PB_ERR_ARG, "pb_let_gather_epj: bad argument");
+    if (n == 0) return PB_OK;
+    if (!E.d_epj) return fail(PB_ERR_PROTOCOL, "pb_let_gather_epj before the j store was reserved");
+    if ((size_t)n > E.cap_let_idx) {
+        CU(cudaStreamSynchronize(E.s_upload));
+        if (E.d_let_idx) CU(cudaFree(E.d_let_idx));
+        if (E.h_let_idx) CU(cudaFreeHost(E.h_let_idx));
+        E.cap_let_idx = (size_t)n + n / 4 + 1024;
+        CU(cudaMalloc(&E.d_let_idx, sizeof(int) * E.cap_let_idx));
+        CU(cudaMallocHost(&E.h_let_idx, sizeof(int) * E.cap_let_idx));
+    }
+    for (int k = 0; k < n; k++)
+        if (idx[k] < 0 || idx[k] >= E.n_epj) return fail(PB_ERR_ARG, "pb_let_gather_epj: index %d outside the EP store (%d entries)", idx[k], E.n_epj);
+    memcpy(E.h_let_idx, idx, sizeof(int) * (size_t)n);
+    // on the upload stream: behind the local particles' copy, ahead of whatever the caller orders after pb_stream_wait_upload
+    CU(cudaMemcpyAsync(E.d_let_idx, E.h_let_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, E.s_upload));
+    CU(launch_gather_epj(E.s_upload, E.d_epj, E.d_let_idx, n, (float4*)d_out32));
+    E.prof.h2d_bytes += (long long)(sizeof(int) * (size_t)n);
+    E.prof.n_kernel_launch += 1;
+    return PB_OK;
+}
+
+int pb_stream_wait_upload(void* cuda_stream) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, E.s_upload));
+    CU(cudaStreamWaitEvent((cudaStream_t)cuda_stream, ev, 0));
+    CU(cudaEventDestroy(ev));
     return PB_OK;
 }
 
@@ -1340,12 +1403,17 @@ int pb_correct_changeover(int n_i, void* ptcl_i, const pb_layout_corr* li,
 // ---- device-side interaction lists --------------------------------------------
 namespace {
 constexpr int kWalkCap  = 32768;       // frontier capacity per warp (cells of one tree level an i-group touches)
-constexpr int kWalkCtasMax = 148 * 16; // scratch is sized for this many CTAs of 4 warps; option "walk_ctas" picks how many run
 #define kWalkCtas (E.opt_walk_ctas)
 
 int ensure_walk_scratch(int slot) {
-    if (!E.d_walk_scratch[slot])
-        CU(cudaMalloc(&E.d_walk_scratch[slot], sizeof(int) * (size_t)kWalkCtasMax * 4 * 2 * kWalkCap));
+    // two frontier buffers of kWalkCap cells per warp of the walk launches actually configured (option "walk_ctas")
+    static int scratch_ctas[kMaxStreams] = {0};
+    if (!E.d_walk_scratch[slot]) scratch_ctas[slot] = 0;
+    if (scratch_ctas[slot] < kWalkCtas) {
+        if (E.d_walk_scratch[slot]) { CU(cudaDeviceSynchronize()); CU(cudaFree(E.d_walk_scratch[slot])); E.d_walk_scratch[slot] = nullptr; }
+        CU(cudaMalloc(&E.d_walk_scratch[slot], sizeof(int) * (size_t)kWalkCtas * 4 * 2 * kWalkCap));
+        scratch_ctas[slot] = kWalkCtas;
+    }
     if (!E.d_overflow) { CU(cudaMalloc(&E.d_overflow, 2 * sizeof(int))); CU(cudaMemset(E.d_overflow, 0, 2 * sizeof(int))); }   // [0] frontier, [1] list reservation
     return PB_OK;
 }
@@ -1458,11 +1526,25 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
         CU(cudaMemcpyAsync(E.d_elem_map, E.h_elem_map, sizeof(int) * (size_t)n_elem, cudaMemcpyHostToDevice, E.s_upload));
         E.prof.h2d_bytes += (long long)(sizeof(int) * (size_t)n_elem);
     }
-    CU(cudaEventRecord(E.ev_j_ready, E.s_upload)); E.j_epoch++;        // dispatch streams wait for j AND tree
-    E.prof.h2d_bytes += (long long)(sizeof(pb_tree_cell) * (size_t)n_cells + sizeof(pb_tree_group) * (size_t)n_groups);
     E.n_cells = n_cells; E.n_groups = n_groups; E.theta = theta;
     E.grp_n.resize(n_groups);
     for (int g = 0; g < n_groups; g++) E.grp_n[g] = groups[g].n;
+    {   // first i-particle of every group in the step's output order (= group order), for the device-resident step
+        if ((size_t)n_groups > E.cap_ifirst) {
+            if (E.d_ifirst) CU(cudaFree(E.d_ifirst));
+            if (E.h_ifirst) CU(cudaFreeHost(E.h_ifirst));
+            E.cap_ifirst = (size_t)n_groups + n_groups / 4 + 1024;
+            CU(cudaMalloc(&E.d_ifirst, sizeof(int) * E.cap_ifirst));
+            CU(cudaMallocHost(&E.h_ifirst, sizeof(int) * E.cap_ifirst));
+        }
+        long long acc = 0; int nblk = 0;
+        for (int g = 0; g < n_groups; g++) { E.h_ifirst[g] = (int)acc; acc += E.grp_n[g]; nblk += (E.grp_n[g] + 31) / 32; }
+        if (acc >= (1ll << 31)) return fail(PB_ERR_ARG, "pb_tree_upload: more than 2^31 i-particles");
+        E.r_n_i = acc; E.r_n_iblk = nblk;
+        if (n_groups) CU(cudaMemcpyAsync(E.d_ifirst, E.h_ifirst, sizeof(int) * (size_t)n_groups, cudaMemcpyHostToDevice, E.s_upload));
+    }
+    CU(cudaEventRecord(E.ev_j_ready, E.s_upload)); E.j_epoch++;        // dispatch streams wait for j AND tree
+    E.prof.h2d_bytes += (long long)(sizeof(pb_tree_cell) * (size_t)n_cells + sizeof(pb_tree_group) * (size_t)n_groups + sizeof(int) * (size_t)n_groups);
     // pass 1 of the device walk starts right away — it needs the tree only, so it runs while the
     // host is still packing this step's j (pb_upload_j): list lengths of every group
     E.count_pending = false;
@@ -1479,7 +1561,11 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
         const double theta_inv2 = theta > 0.0 ? 1.0 / (theta * theta) : 1e300;
         cudaStream_t s0 = E.slots[0].stream;
         CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));
+        for (int k = 0; k < 8; k++) if (!E.ev_tl[k]) CU(cudaEventCreate(&E.ev_tl[k]));
+        CU(cudaEventRecord(E.ev_tl[0], s0));                 // tree on the device, walk starts
+        E.tl_valid = false;
         E.spec_pending = false;
+        CU(cudaMemsetAsync(E.d_overflow, 0, 2 * sizeof(int), s0));         // a frontier overflow of an earlier tree must not stick
         if (E.opt_tree_spec && (int)E.prev_counts.size() == n_groups) {
             // Speculative single pass: the lists of consecutive tree steps have nearly the same lengths, so space is
             // reserved from the previous step's (+12.5 % + 64) and the walk fills the lists right away — while the host
@@ -1516,6 +1602,7 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
         if (!E.spec_pending)
             CU(launch_walk_count(s0, E.d_cells, E.d_groups, 0, n_groups, theta_inv2, E.d_counts, E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow,
                                  E.has_elem_map ? E.d_elem_map : nullptr, n_cells));
+        CU(cudaEventRecord(E.ev_tl[1], s0));                 // walk (count pass, or speculative list fill) done
         CU(cudaMemcpyAsync(E.h_counts_p, E.d_counts, sizeof(int2) * (size_t)n_groups, cudaMemcpyDeviceToHost, s0));
         CU(cudaMemcpyAsync(E.h_over_p, E.d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, s0));
         CU(cudaEventRecord(E.ev_count, s0));
@@ -1653,6 +1740,188 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
     E.tree_last_batches = n_batches;
     E.prof.n_walk += E.n_groups; E.prof.n_epi += n_i; E.prof.n_epj += n_ej; E.prof.n_spj += n_sj;
     E.prof.n_call += n_batches; E.prof.n_interaction_ep += i_ep; E.prof.n_interaction_sp += i_sp;
+    return PB_OK;
+}
+
+// ---- device-resident tree step ---------------------------------------------------------------------------------
+// Everything between "tree and particles are on the device" and "forces are back" runs on the GPU: list building
+// (pb_walk.cu), i-particle preparation and task planning (pb_plan.cu), one persistent force launch, the reduction.
+// From the second tree step on nothing on the host waits in the middle: list space, task and partial-sum buffers are
+// reserved from the previous step's sizes (with a margin), the true sizes come back with the forces, and a step whose
+// reservation was too small is detected on the device (nothing runs past a reservation) and repeated exactly.
+namespace {
+int resident_run(void* force, const pb_layout_force& L, bool exact) {
+    cudaStream_t s0 = E.slots[0].stream;
+    const int ng = E.n_groups;
+    const double theta_inv2 = E.theta > 0.0 ? 1.0 / (E.theta * E.theta) : 1e300;
+    int U = E.opt_jchunk > 0 ? E.opt_jchunk : 1536;
+    U = (int)align_up((size_t)U, kTileJ);
+    const int Us = std::max(kTileJ, U / 2);
+    const int coords = E.opt_coords, i_f4 = coords == 2 ? 3 : 2;
+    int rc;
+
+    // per-group and per-particle buffers
+    if ((size_t)ng > E.cap_r_groups) {
+        if (E.d_r_walks) CU(cudaFree(E.d_r_walks));
+        if (E.d_r_goff) CU(cudaFree(E.d_r_goff));
+        E.cap_r_groups = (size_t)ng + ng / 4 + 1024;
+        CU(cudaMalloc(&E.d_r_walks, sizeof(Walk) * E.cap_r_groups));
+        CU(cudaMalloc(&E.d_r_goff, sizeof(int3) * E.cap_r_groups));
+    }
+    if ((size_t)E.r_n_i > E.cap_r_i) {
+        if (E.d_r_epi) CU(cudaFree(E.d_r_epi));
+        if (E.d_r_out) CU(cudaFree(E.d_r_out));
+        if (E.h_r_out) CU(cudaFreeHost(E.h_r_out));
+        if (E.d_r_iblocks) CU(cudaFree(E.d_r_iblocks));
+        E.cap_r_i = (size_t)E.r_n_i + E.r_n_i / 4 + 4096;
+        CU(cudaMalloc(&E.d_r_epi, sizeof(float4) * 3 * E.cap_r_i));
+        CU(cudaMalloc(&E.d_r_out, sizeof(ForceOut) * E.cap_r_i));
+        CU(cudaMallocHost(&E.h_r_out, sizeof(ForceOut) * E.cap_r_i));
+        CU(cudaMalloc(&E.d_r_iblocks, sizeof(IBlock) * (E.cap_r_i / 32 + E.cap_r_groups + 1024)));
+    }
+    if ((size_t)E.r_n_iblk > E.cap_r_i / 32 + E.cap_r_groups + 1024) return fail(PB_ERR_ARG, "pb_tree_force_resident: i-block table too small");
+    if (!E.d_r_meta) { CU(cudaMalloc(&E.d_r_meta, 8 * sizeof(int))); CU(cudaMallocHost(&E.h_r_meta, 8 * sizeof(int))); }
+    if (!E.ev_fill) CU(cudaEventCreateWithFlags(&E.ev_fill, cudaEventDisableTiming));
+
+    long long want_tasks, want_part;
+    const int2* d_caps = nullptr;
+    if (exact) {
+        // list lengths are on the host: exact list offsets, a second walk pass writes the lists, exact buffer sizes
+        E.h_tree_off.resize(ng);
+        size_t tot_e = 0, tot_s = 0;
+        for (int g = 0; g < ng; g++) {
+            E.h_tree_off[g] = make_int2((int)tot_e, (int)tot_s);
+            tot_e += align_up((size_t)E.h_counts[g].x, 4);
+            tot_s += align_up((size_t)E.h_counts[g].y, 4);
+        }
+        if (tot_e >= (1ull << 31) || tot_s >= (1ull << 31)) return fail(PB_ERR_ARG, "pb_tree_force_resident: more than 2^31 list entries in one step");
+        if (tot_e > E.cap_tree_ide) { if (E.d_tree_ide) CU(cudaFree(E.d_tree_ide)); E.cap_tree_ide = tot_e + tot_e / 8 + 4096; CU(cudaMalloc(&E.d_tree_ide, sizeof(int) * E.cap_tree_ide)); }
+        if (tot_s > E.cap_tree_ids) { if (E.d_tree_ids) CU(cudaFree(E.d_tree_ids)); E.cap_tree_ids = tot_s + tot_s / 8 + 4096; CU(cudaMalloc(&E.d_tree_ids, sizeof(int) * E.cap_tree_ids)); }
+        if (!E.d_tree_off) CU(cudaMalloc(&E.d_tree_off, sizeof(int2) * E.cap_counts));
+        CU(cudaMemcpyAsync(E.d_tree_off, E.h_tree_off.data(), sizeof(int2) * (size_t)ng, cudaMemcpyHostToDevice, s0));
+        if ((rc = ensure_walk_scratch(0)) != PB_OK) return rc;
+        CU(cudaMemsetAsync(E.d_overflow, 0, 2 * sizeof(int), s0));
+        CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, ng, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
+                            E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells,
+                            nullptr, E.d_counts));
+        E.prof.n_kernel_launch += 1;
+        long long nt, np, nb;
+        plan_sizes_host(E.grp_n.data(), E.h_counts.data(), ng, U, Us, &nt, &np, &nb);
+        want_tasks = nt + 64; want_part = np + 4096;
+    } else {
+        want_tasks = E.r_prev_tasks + E.r_prev_tasks / 4 + 4096;
+        want_part = E.r_prev_part + E.r_prev_part / 4 + 65536;
+        d_caps = E.d_tree_caps;
+    }
+    if (want_part >= (1ll << 31)) return fail(PB_ERR_ARG, "pb_tree_force_resident: more than 2^31 partial sums in one step");
+    if ((size_t)want_tasks > E.cap_r_tasks) {
+        if (E.d_r_tasks) CU(cudaFree(E.d_r_tasks));
+        E.cap_r_tasks = (size_t)want_tasks + want_tasks / 8;
+        CU(cudaMalloc(&E.d_r_tasks, sizeof(Task) * E.cap_r_tasks));
+    }
+    if ((size_t)want_part > E.cap_r_part) {
+        if (E.d_r_part4) CU(cudaFree(E.d_r_part4));
+        if (E.d_r_partn) CU(cudaFree(E.d_r_partn));
+        E.cap_r_part = (size_t)want_part + want_part / 8;
+        CU(cudaMalloc(&E.d_r_part4, sizeof(double4) * E.cap_r_part));
+        CU(cudaMalloc(&E.d_r_partn, sizeof(int) * E.cap_r_part));
+    }
+
+    CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));          // this step's j (local upload + whatever a collective wrote) is in place
+    CU(cudaEventRecord(E.ev_tl[2], s0));
+    CU(launch_iprep(s0, E.d_groups, ng, E.d_ifirst, E.d_counts, E.d_tree_off, E.d_epj, E.d_r_walks, E.d_r_epi, i_f4, coords, E.opt_cull));
+    CU(launch_devplan(s0, E.d_groups, ng, E.d_ifirst, E.d_counts, U, Us, E.d_r_goff, E.d_r_meta,
+                   (int)std::min<size_t>(E.cap_r_tasks, 0x7fffffff), (long long)E.cap_r_part, E.d_r_tasks, E.d_r_iblocks, d_caps));
+    CU(cudaEventRecord(E.ev_tl[3], s0));
+    Plan pl; pl.coords = coords; pl.i_f4 = i_f4; pl.count_only = 0;
+    Params prm = make_params(pl, nullptr);
+    prm.meta = E.d_r_meta;
+    CU(launch_force_persistent(s0, 2 * 148, E.opt_nr, E.d_r_walks, E.d_r_tasks, E.d_r_epi, E.d_tree_ide, E.d_tree_ids, E.d_epj, E.d_spj,
+                               E.d_r_part4, E.d_r_partn, prm));
+    CU(cudaEventRecord(E.ev_tl[4], s0));
+    CU(launch_reduce(s0, E.r_n_iblk, E.d_r_iblocks, E.d_r_part4, E.d_r_partn, E.d_r_out, E.G, E.d_r_meta));
+    CU(cudaEventRecord(E.ev_tl[5], s0));
+    CU(cudaMemcpyAsync(E.h_r_out, E.d_r_out, sizeof(ForceOut) * (size_t)E.r_n_i, cudaMemcpyDeviceToHost, s0));
+    CU(cudaMemcpyAsync(E.h_r_meta, E.d_r_meta, 8 * sizeof(int), cudaMemcpyDeviceToHost, s0));
+    CU(cudaMemcpyAsync(E.h_counts_p, E.d_counts, sizeof(int2) * (size_t)ng, cudaMemcpyDeviceToHost, s0));
+    CU(cudaMemcpyAsync(E.h_over_p, E.d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, s0));
+    CU(cudaEventRecord(E.ev_tl[6], s0));
+    E.prof.n_kernel_launch += 5;
+    E.prof.d2h_bytes += (long long)(sizeof(ForceOut) * (size_t)E.r_n_i + sizeof(int2) * (size_t)ng);
+    CU(cudaEventSynchronize(E.ev_tl[6]));
+
+    if (E.h_over_p[0]) return fail(PB_ERR_ARG, "pb_tree_force_resident: tree-walk frontier exceeded %d cells per level", kWalkCap);
+    const bool retry = (!exact && E.h_over_p[1] != 0) || E.h_r_meta[3] != 0;
+    E.h_counts.assign(E.h_counts_p, E.h_counts_p + ng);    // true list lengths of this step, whatever happened
+    if (retry) {
+        if (exact) return fail(PB_ERR_ARG, "pb_tree_force_resident: task plan does not fit its buffers (flags %d)", E.h_r_meta[3]);
+        return 1;                                          // reservation too small: the caller repeats the step exactly
+    }
+    E.prev_counts = E.h_counts;
+    E.r_prev_tasks = E.h_r_meta[5]; E.r_prev_part = E.h_r_meta[1];
+    for (int k = 0; k < 6; k++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, E.ev_tl[k], E.ev_tl[k + 1]) == cudaSuccess) E.tl_ms[k] = ms; }
+    E.tl_valid = true;
+    E.prof.t_calc += 1e-3 * (E.tl_ms[0] + E.tl_ms[2] + E.tl_ms[3] + E.tl_ms[4]);
+    E.prof.t_recv += 1e-3 * E.tl_ms[5];
+
+    // forces back to the caller's array (group order)
+    const double t0 = now_s();
+    const bool plain = L.stride == sizeof(ForceOut) && L.off_acc == 0 && L.off_pot == 24 && L.off_nngb == 32;
+    const long long n = E.r_n_i;
+    char* dst = (char*)force;
+    if (plain) {
+        const long long chunk = 1 << 15;
+#pragma omp parallel for schedule(static)
+        for (long long c = 0; c < (n + chunk - 1) / chunk; c++)
+            memcpy(dst + (size_t)c * chunk * sizeof(ForceOut), E.h_r_out + c * chunk, sizeof(ForceOut) * (size_t)std::min(chunk, n - c * chunk));
+    } else {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < n; i++) {
+            char* q = dst + (size_t)i * L.stride;
+            memcpy(q + L.off_acc, &E.h_r_out[i].ax, 24);
+            memcpy(q + L.off_pot, &E.h_r_out[i].pot, 8);
+            memcpy(q + L.off_nngb, &E.h_r_out[i].n_ngb, 8);
+        }
+    }
+    E.prof.t_copy += now_s() - t0; E.prof.t_unpack += now_s() - t0;
+    long long n_ej = 0, n_sj = 0, i_ep = 0, i_sp = 0;
+    for (int g = 0; g < ng; g++) {
+        n_ej += E.h_counts[g].x; n_sj += E.h_counts[g].y;
+        i_ep += (long long)E.grp_n[g] * E.h_counts[g].x; i_sp += (long long)E.grp_n[g] * E.h_counts[g].y;
+    }
+    E.prof.n_walk += ng; E.prof.n_epi += n; E.prof.n_epj += n_ej; E.prof.n_spj += n_sj;
+    E.prof.n_call += 1; E.prof.n_interaction_ep += i_ep; E.prof.n_interaction_sp += i_sp;
+    return PB_OK;
+}
+} // namespace
+
+int pb_tree_force_resident(void* force, const pb_layout_force* lforce) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    if (E.outstanding) return fail(PB_ERR_PROTOCOL, "pb_tree_force_resident while a dispatch is outstanding");
+    if (!E.j_published) return fail(PB_ERR_PROTOCOL, "pb_tree_force_resident before the j-particles were published");
+    if (E.n_groups == 0) return PB_OK;
+    if (!E.d_cells) return fail(PB_ERR_PROTOCOL, "pb_tree_force_resident before pb_tree_upload");
+    if (!force || !lforce) return fail(PB_ERR_ARG, "pb_tree_force_resident: null argument");
+    if (E.n_cells > E.n_spj) return fail(PB_ERR_PROTOCOL, "pb_tree_force_resident: the SP store (%d) must hold one superparticle per cell (%d)", E.n_spj, E.n_cells);
+    if (!E.count_pending) return fail(PB_ERR_PROTOCOL, "pb_tree_force_resident: call pb_tree_upload for this step first");
+    E.count_pending = false;
+    bool exact = !(E.spec_pending && E.r_prev_tasks > 0);
+    E.spec_pending = false;
+    if (exact) {
+        // first step (or speculation off): the counting pass launched by pb_tree_upload tells the host the list lengths
+        CU(cudaEventSynchronize(E.ev_count));
+        if (*E.h_over_p) return fail(PB_ERR_ARG, "pb_tree_force_resident: tree-walk frontier exceeded %d cells per level", kWalkCap);
+        E.h_counts.assign(E.h_counts_p, E.h_counts_p + E.n_groups);
+    }
+    rc = resident_run(force, *lforce, exact);
+    if (rc == 1) rc = resident_run(force, *lforce, true);   // a reservation was too small: h_counts now holds the true lengths
+    return rc;
+}
+
+int pb_tree_timeline(float* ms, int n) {
+    if (!E.tl_valid) return fail(PB_ERR_PROTOCOL, "pb_tree_timeline: no device-resident step has completed");
+    for (int k = 0; k < n && k < 6; k++) ms[k] = E.tl_ms[k];
     return PB_OK;
 }
 

@@ -197,7 +197,7 @@ template <int NR, int NEAR>
 __device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
                                          float xi, float yi, float zi, float xil, float yil, float zil, float rsi2,
                                          float xih, float yih, float zih,
-                                         float eps2, float rcut2,
+                                         float eps2, float rcut2, float rinv_cut,
                                          float2& ax, float2& ay, float2& az, float2& pt, float2& cf) {
     const float2 nxi = bc(-xi), nyi = bc(-yi), nzi = bc(-zi), e2 = bc(eps2);
     const float2 nxil = bc(-xil), nyil = bc(-yil), nzil = bc(-zil);
@@ -223,7 +223,7 @@ __device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
             const float2 C = t.c[p];
             const bool h0 = r2.x < fmaxf(C.x, rsi2), h1 = r2.y < fmaxf(C.y, rsi2);
             cf = __fadd2_rn(cf, make_float2(h0 ? 1.f : 0.f, h1 ? 1.f : 0.f));
-            if (NEAR == 2) {
+            if (NEAR == 2 && __any_sync(__activemask(), h0 || h1)) {        // rare: some lane of the warp has a neighbour in this pair
                 const float4 AH = t.ah[p];
                 const float2 BH = t.bh[p];
                 const float2 ex = __fadd2_rn(make_float2(AH.x, AH.y), bc(-xih));
@@ -235,6 +235,20 @@ __device__ __forceinline__ void ep_pairs(const EpTile& t, int p0, int p1,
                 r2 = __ffma2_rn(dx, dx, e2);
                 r2 = __ffma2_rn(dy, dy, r2);
                 r2 = __ffma2_rn(dz, dz, r2);
+                // inside the cutoff the replay's 1/r is the constant float(1 / sqrt(double(r_out_32^2))) (src/hard.hpp:1434-1436):
+                // use that very value for the neighbour instead of the 2-ulp MUFU approximation
+                const float2 r2c_ = make_float2(fmaxf(r2.x, rcut2), fmaxf(r2.y, rcut2));
+                float2 ri_ = rsqrt2<NR>(r2c_);
+                if (h0 && r2.x <= rcut2) ri_.x = rinv_cut;
+                if (h1 && r2.y <= rcut2) ri_.y = rinv_cut;
+                const float2 pij_  = __fmul2_rn(make_float2(B.z, B.w), ri_);
+                const float2 ri2_  = __fmul2_rn(ri_, ri_);
+                const float2 mri3_ = __fmul2_rn(pij_, ri2_);
+                ax = __ffma2_rn(mri3_, dx, ax);
+                ay = __ffma2_rn(mri3_, dy, ay);
+                az = __ffma2_rn(mri3_, dz, az);
+                pt = __fadd2_rn(pt, pij_);
+                continue;
             }
         }
         const float2 r2c  = make_float2(fmaxf(r2.x, rcut2), fmaxf(r2.y, rcut2));
@@ -424,13 +438,13 @@ struct IdPipe {
     __device__ __forceinline__ void init(const int* ids_, int j_count_, int n_tiles_, int dbase_, IdRing* ring_, int tid) {
         ids = ids_; j_count = j_count_; n_tiles = n_tiles_; dbase = dbase_; ring = ring_;
 #if PB_TMA_IDS
-        if (ids && tid == 0) {
+        if (tid == 0) {
             for (int b = 0; b < kIdRing; ++b) {
                 const unsigned bar = (unsigned)__cvta_generic_to_shared(&ring->bar[b]);
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(1) : "memory");
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            for (int r = 0; r < min(kIdRing, n_tiles - kIdDirect); ++r) issue(r);
+            if (ids) for (int r = 0; r < min(kIdRing, n_tiles - kIdDirect); ++r) issue(r);
         }
 #endif
     }
@@ -469,7 +483,10 @@ struct IdPipe {
 // ------------------------------------------------------------------------------------------
 // the force kernel
 // ------------------------------------------------------------------------------------------
-template <int NR, int MINB, bool EMIT = false>
+// PERSIST: the grid is 2 CTAs per SM and every CTA pulls task numbers from an atomic cursor until the task list is
+// used up — the task count lives in device memory (meta[0], cursor meta[4]) because the plan was made on the device
+// (pb_plan.cu), so no host round trip sits between the tree walk and the forces.
+template <int NR, int MINB, bool EMIT = false, bool PERSIST = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
              const float4* __restrict__ epi,
@@ -482,11 +499,20 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
     __shared__ IdRing ring;                      // index tiles, filled by TMA bulk copies
     __shared__ TileBars bars;                    // tile hand-over (see TileBars)
     __shared__ int jid[EMIT ? kTileBufs : 1][EMIT ? kTileJ : 1];   // store index of every staged j (neighbour-list emission only)
+    __shared__ int s_task;
 
-    const Task task = tasks[blockIdx.x];
-    const Walk w    = walks[task.walk];
     const int tid   = threadIdx.x;
     const int warp  = tid >> 5, lane = tid & 31;
+  for (;;) {
+    int task_id = blockIdx.x;
+    if (PERSIST) {
+        if (tid == 0) s_task = atomicAdd(prm.meta + 4, 1);
+        __syncthreads();
+        task_id = s_task;
+        if (task_id >= prm.meta[0]) break;
+    }
+    const Task task = tasks[task_id];
+    const Walk w    = walks[task.walk];
 
     // warp role: i-block `ib` of the group, j-split slot `js`
     const bool busy = warp < task.nib * task.jsplit;
@@ -568,11 +594,11 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                                                  jid[EMIT ? cb : 0], ivalid ? (unsigned int)(prm.i_base + w.i_off + i_loc) : 0xffffffffu, prm);
                     } else if (near_flag[cb][seg0 >> 4]) {
                         if (prm.abs_mode == 2)
-                            ep_pairs<NR, 2>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, pih.x, pih.y, pih.z, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                            ep_pairs<NR, 2>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, pih.x, pih.y, pih.z, prm.eps2, prm.rcut2, prm.rinv_cut, ax, ay, az, pt, cf);
                         else
-                            ep_pairs<NR, 1>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                            ep_pairs<NR, 1>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, 0.f, ax, ay, az, pt, cf);
                     } else
-                        ep_pairs<NR, 0>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, ax, ay, az, pt, cf);
+                        ep_pairs<NR, 0>(T, seg, e, pi.x, pi.y, pi.z, pil.x, pil.y, pil.z, rsi2, 0.f, 0.f, 0.f, prm.eps2, prm.rcut2, 0.f, ax, ay, az, pt, cf);
                 }
                 kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
                 cnt += (int)(cf.x + cf.y);
@@ -659,6 +685,19 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
         part4[slot] = make_double4(dax, day, daz, dpt);
         partn[slot] = cnt;
     }
+    if (!PERSIST) break;
+    __syncthreads();                                   // everybody is done with this task's shared state
+    if (tid == 0) {                                    // the mbarriers are re-initialised by the next task
+        for (int b = 0; b < kTileBufs; ++b) {
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars.full[b]);
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
+        }
+        for (int b = 0; b < kIdRing; ++b) {
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&ring.bar[b]);
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
+        }
+    }
+  }
 }
 
 cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_blocks,
@@ -676,6 +715,16 @@ cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_bloc
     return cudaGetLastError();
 }
 
+cudaError_t launch_force_persistent(cudaStream_t s, int n_ctas, int nr_steps,
+                                    const Walk* walks, const Task* tasks, const float4* epi, const int* id_epj, const int* id_spj,
+                                    const float4* epj, const float4* spj, double4* part4, int* partn, Params p)
+{
+    if (n_ctas <= 0) return cudaSuccess;
+    if (nr_steps >= 1) force_kernel<1, 2, false, true><<<n_ctas, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
+    else               force_kernel<0, 2, false, true><<<n_ctas, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // reduction: one warp per 32-wide i-block adds that block's task partials in fp64, chunk order
 // fixed, applies G and writes ForceSoft-shaped records.
@@ -684,11 +733,12 @@ cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_bloc
 __global__ void __launch_bounds__(256)
 reduce_kernel(int n_iblocks, const IBlock* __restrict__ iblocks,
               const double4* __restrict__ part4, const int* __restrict__ partn,
-              ForceOut* __restrict__ out, double G)
+              ForceOut* __restrict__ out, double G, const int* __restrict__ meta)
 {
     const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= n_iblocks) return;
+    if (meta && meta[3] != 0) return;                 // device-made plan did not fit its buffers: nothing was computed
     const IBlock ibk = iblocks[b];
     if (lane >= ibk.n_valid) return;
     double ax = 0.0, ay = 0.0, az = 0.0, pt = 0.0;
@@ -706,11 +756,11 @@ reduce_kernel(int n_iblocks, const IBlock* __restrict__ iblocks,
 }
 
 cudaError_t launch_reduce(cudaStream_t s, int n_iblocks, const IBlock* iblocks,
-                          const double4* part4, const int* partn, ForceOut* out, double G)
+                          const double4* part4, const int* partn, ForceOut* out, double G, const int* meta)
 {
     if (n_iblocks <= 0) return cudaSuccess;
     const int wpb = 8;
-    reduce_kernel<<<(n_iblocks + wpb - 1) / wpb, wpb * 32, 0, s>>>(n_iblocks, iblocks, part4, partn, out, G);
+    reduce_kernel<<<(n_iblocks + wpb - 1) / wpb, wpb * 32, 0, s>>>(n_iblocks, iblocks, part4, partn, out, G, meta);
     return cudaGetLastError();
 }
 

@@ -79,7 +79,7 @@ LAYOUT_EPJ = LayoutEpj(EPJSoft.itemsize, _off(EPJSoft, "pos"), _off(EPJSoft, "ma
 LAYOUT_SPJ = LayoutSpj(SPJQuad.itemsize, _off(SPJQuad, "pos"), _off(SPJQuad, "mass"), _off(SPJQuad, "quad"), 1)
 LAYOUT_FORCE = LayoutForce(ForceSoft.itemsize, _off(ForceSoft, "acc"), _off(ForceSoft, "pot"), _off(ForceSoft, "n_ngb"))
 
-ABI_VERSION = 4   # PB_ABI_VERSION of include/petar_b200.h this module binds
+ABI_VERSION = 5   # PB_ABI_VERSION of include/petar_b200.h this module binds
 
 # every symbol include/petar_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -89,6 +89,7 @@ ABI_SYMBOLS = [
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
     "pb_field_at_points", "pb_dispatch_count_index", "pb_tree_upload", "pb_tree_force", "pb_tree_lists",
     "pb_correct_changeover", "pb_retrieve_neighbors", "pb_tree_upload_let", "pb_debug_plan", "pb_tree_stage",
+    "pb_tree_force_resident", "pb_tree_timeline", "pb_let_gather_epj", "pb_stream_wait_upload",
 ]
 
 _lib = None
@@ -127,6 +128,8 @@ def load():
     L.pb_reserve_j.argtypes = [C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]
     L.pb_upload_j_range.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(LayoutEpj), _vp, C.c_int, C.c_int, C.POINTER(LayoutSpj)]
     L.pb_publish_j.argtypes = [_vp]
+    L.pb_let_gather_epj.argtypes = [_vp, C.c_int, _vp]
+    L.pb_stream_wait_upload.argtypes = [_vp]
     L.pb_pack_epj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_epj_host_indexed.argtypes = [_vp, _vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_spj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutSpj), _vp]
@@ -135,6 +138,8 @@ def load():
     L.pb_tree_upload_let.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double, _vp, C.c_int]
     L.pb_tree_force.argtypes = [_vp, C.POINTER(LayoutEpi), _vp, C.POINTER(LayoutForce)]
     L.pb_tree_lists.argtypes = [_vp, _vp, _vp, C.c_longlong, _vp, C.c_longlong]
+    L.pb_tree_force_resident.argtypes = [_vp, C.POINTER(LayoutForce)]
+    L.pb_tree_timeline.argtypes = [C.POINTER(C.c_float), C.c_int]
     L.pb_correct_changeover.argtypes = [C.c_int, _vp, C.POINTER(LayoutCorr), C.c_int, _vp, C.POINTER(LayoutCorr), _vp, _vp, C.POINTER(CorrParams)]
     L.pb_debug_plan.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     L.pb_retrieve_neighbors.argtypes = [C.POINTER(C.c_longlong), _vp, _vp, C.c_longlong]
@@ -325,7 +330,17 @@ def tree_neighbor_search(batch, n_walk_limit=200, force=None, lists=False, table
     return f, nb_off.astype(np.int32), nb_idx
 
 
-def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, upload=True, elem_map=None):
+TIMELINE_KEYS = ("walk", "wait_j", "iprep_plan", "force", "reduce", "d2h")
+
+
+def tree_timeline():
+    """Device timeline (ms per phase) of the last device-resident tree step (pb_tree_timeline)."""
+    ms = (C.c_float * 6)()
+    check(load().pb_tree_timeline(ms, 6), "pb_tree_timeline")
+    return dict(zip(TIMELINE_KEYS, (float(x) for x in ms)))
+
+
+def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, upload=True, elem_map=None, resident=False):
     """Device-side list building: publish j, upload the tree, let the GPU build every
     group's id_epj / id_spj and run the force kernels on them.  `batch` only supplies epj / spj / epi
     (its host index lists are NOT used).  Returns ForceSoft[n_epi_total] in group order."""
@@ -343,7 +358,10 @@ def tree_force(batch, cells, groups, eps, r_out, G, theta=0.3, force=None, uploa
                                        em.ctypes.data, len(em)), "pb_tree_upload_let")
         check(L.pb_upload_j(batch.epj.ctypes.data, len(batch.epj), C.byref(LAYOUT_EPJ),
                             batch.spj.ctypes.data, len(batch.spj), C.byref(LAYOUT_SPJ)), "pb_upload_j")
-    check(L.pb_tree_force(batch.epi.ctypes.data, C.byref(LAYOUT_EPI), f.ctypes.data, C.byref(LAYOUT_FORCE)), "pb_tree_force")
+    if resident:          # i-particles come from the j store, plan and forces stay on the device (pb_tree_force_resident)
+        check(L.pb_tree_force_resident(f.ctypes.data, C.byref(LAYOUT_FORCE)), "pb_tree_force_resident")
+    else:
+        check(L.pb_tree_force(batch.epi.ctypes.data, C.byref(LAYOUT_EPI), f.ctypes.data, C.byref(LAYOUT_FORCE)), "pb_tree_force")
     return f
 
 

@@ -160,6 +160,8 @@ class DomainStepper:
         self.out_ep, self.out_sp = wl["recv_ep_cnt"], wl["recv_sp_cnt"]
         self.nccl_bytes_per_step = 32 * len(self.send_idx) + 64 * len(self.send_sp)
         self.host_s, self.n_steps = {}, 0          # wall-clock of the step's host phases (seconds, accumulated)
+        self.host_dw, self.n_dw = {}, 0
+        self.send_idx32 = self.send_idx.astype(np.int32)            # LET EP rows as store slots (local particles come first)
         self.L = engine.load()
         pin = device
         self.h_send_ep = torch.empty((len(self.send_idx), 8), dtype=torch.float32, pin_memory=pin)
@@ -187,16 +189,22 @@ class DomainStepper:
         self.store_sp = torch.as_tensor(_Raw(ps.value, (max(len(b.spj), 1), 16)), device="cuda")[:len(b.spj)]
 
     def pack_sends(self):
+        """Host packing of the LET send rows (EP gathered from the local particles, SP from the local tree's multipoles) —
+        the CPU (gloo) path and the reference for the device gather; the GPU steps pack only the SP rows here."""
         b = self.batch
         if len(self.send_idx):                                          # gather from the local particles while packing
             engine.check(self.L.pb_pack_epj_host_indexed(b.epj.ctypes.data, self.send_idx.ctypes.data, len(self.send_idx),
                                                          C.byref(engine.LAYOUT_EPJ), self.h_send_ep.data_ptr()), "pb_pack_epj_host_indexed")
+        self.pack_send_sp()
+
+    def pack_send_sp(self):
         if len(self.send_sp):
             engine.check(self.L.pb_pack_spj_host(self.send_sp.ctypes.data, len(self.send_sp), C.byref(engine.LAYOUT_SPJ),
                                                  self.h_send_sp.data_ptr()), "pb_pack_spj_host")
 
     def exchange(self):
-        """LET all-to-all in the device j format; lands behind the local part of the store."""
+        """LET all-to-all in the device j format; lands behind the local part of the store.  CPU (gloo) form, and the
+        round-1 GPU form with host-packed EP rows (kept for A/B: option host_let_pack)."""
         torch, dist = self.torch, self.dist
         if self.device:
             self.d_send_ep.copy_(self.h_send_ep, non_blocking=True)
@@ -207,51 +215,84 @@ class DomainStepper:
         dist.all_to_all_single(self.store_ep[self.n_loc:], se, self.out_ep, self.in_ep)
         dist.all_to_all_single(self.store_sp[self.n_nodes:], ss, self.out_sp, self.in_sp)
 
-    def step_device_walk(self, force, theta=0.3):
-        """The same tree step with the interaction lists built on the GPU: the global tree
-        (local + LET elements) is uploaded instead of per-walk index lists; j travels as in :meth:`step`."""
-        b, L, wl = self.batch, self.L, self.wl
+    def exchange_device(self):
+        """The LET exchange of the GPU steps.  EP rows are gathered ON THE DEVICE from the local part of the j store
+        (the host ships 4-byte store slots, not packed 32-byte rows); SP rows are the local tree's multipoles, which
+        exist on the host only, so they are packed there (64 B each) and copied.  One NCCL all-to-all per kind writes
+        straight into the peers' j stores behind their locally uploaded part."""
+        torch, dist, L = self.torch, self.dist, self.L
+        if len(self.send_idx32):
+            engine.check(L.pb_let_gather_epj(self.send_idx32.ctypes.data, len(self.send_idx32), self.d_send_ep.data_ptr()), "pb_let_gather_epj")
+        self.pack_send_sp()
+        self.d_send_sp.copy_(self.h_send_sp, non_blocking=True)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        engine.check(L.pb_stream_wait_upload(stream), "pb_stream_wait_upload")     # local j copied, EP rows gathered
+        dist.all_to_all_single(self.store_ep[self.n_loc:], self.d_send_ep, self.out_ep, self.in_ep)
+        dist.all_to_all_single(self.store_sp[self.n_nodes:], self.d_send_sp, self.out_sp, self.in_sp)
+        engine.check(L.pb_publish_j(stream), "pb_publish_j")
+
+    def _stage_tree(self):
+        wl = self.wl
         if not getattr(self, "_tree_staged", False):          # the tree lives in the library's pinned staging buffers
             sc, sg = engine.tree_stage(len(wl["tree_cells"]), len(wl["tree_groups"]))
             sc[:] = wl["tree_cells"]; sg[:] = wl["tree_groups"]
             wl["tree_cells"], wl["tree_groups"], self._tree_staged = sc, sg, True
-        cells, groups, em = wl["tree_cells"], wl["tree_groups"], wl["elem_map"]
-        engine.check(L.pb_set_params(self.prm["eps"] ** 2, self.prm["r_out"] ** 2, self.prm["G"]), "pb_set_params")
-        engine.check(L.pb_tree_upload_let(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta),
-                                          em.ctypes.data, len(em)), "pb_tree_upload_let")       # starts the walk's counting pass
+        return wl["tree_cells"], wl["tree_groups"], wl["elem_map"]
+
+    def upload_local_j(self):
+        b, L = self.batch, self.L
         pe, ps = C.c_void_p(0), C.c_void_p(0)
         engine.check(L.pb_reserve_j(len(b.epj), len(b.spj), C.byref(pe), C.byref(ps)), "pb_reserve_j")
         assert (pe.value, ps.value) == self._ptrs, "j store moved"
         engine.check(L.pb_upload_j_range(b.epj.ctypes.data, 0, self.n_loc, C.byref(engine.LAYOUT_EPJ),
                                          b.spj.ctypes.data, 0, self.n_nodes, C.byref(engine.LAYOUT_SPJ)), "pb_upload_j_range")
-        self.pack_sends()
-        self.exchange()
-        engine.check(L.pb_publish_j(C.c_void_p(self.torch.cuda.current_stream().cuda_stream)), "pb_publish_j")
-        engine.check(L.pb_tree_force(b.epi.ctypes.data, C.byref(engine.LAYOUT_EPI), force.ctypes.data, C.byref(engine.LAYOUT_FORCE)), "pb_tree_force")
+
+    def step_device_walk(self, force, theta=0.3, resident=True):
+        """One tree step with the interaction lists built on the GPU from the global tree (local +
+        LET elements).  Host work: stage the tree, pack this rank's own j, name the LET rows; everything else —
+        LET gather, NCCL all-to-all, tree walk, i-particle preparation, task planning, forces, reduction — runs on the
+        device with no host round trip in between (resident=False: the round-1 host-planned pb_tree_force)."""
+        import time
+        b, L = self.batch, self.L
+        t0 = time.perf_counter()
+        cells, groups, em = self._stage_tree()
+        engine.check(L.pb_set_params(self.prm["eps"] ** 2, self.prm["r_out"] ** 2, self.prm["G"]), "pb_set_params")
+        engine.check(L.pb_tree_upload_let(cells.ctypes.data, len(cells), groups.ctypes.data, len(groups), float(theta),
+                                          em.ctypes.data, len(em)), "pb_tree_upload_let")       # starts the tree walk
+        t1 = time.perf_counter()
+        self.upload_local_j()
+        t2 = time.perf_counter()
+        self.exchange_device()
+        t3 = time.perf_counter()
+        if resident:
+            engine.check(L.pb_tree_force_resident(force.ctypes.data, C.byref(engine.LAYOUT_FORCE)), "pb_tree_force_resident")
+        else:
+            engine.check(L.pb_tree_force(b.epi.ctypes.data, C.byref(engine.LAYOUT_EPI), force.ctypes.data, C.byref(engine.LAYOUT_FORCE)), "pb_tree_force")
+        t4 = time.perf_counter()
+        for k, v in (("tree_upload", t1 - t0), ("upload_local_j", t2 - t1), ("let_exchange_enqueue", t3 - t2), ("walk_plan_force_wait", t4 - t3)):
+            self.host_dw[k] = self.host_dw.get(k, 0.0) + v
+        self.n_dw += 1
         return force
+
+    def let_exchange_only(self):
+        """Device gather + all-to-all + publish of one step with the local j already resident (bench `value` leg)."""
+        self.exchange_device()
 
     def step(self, force):
         import time
         b, L = self.batch, self.L
         t0 = time.perf_counter()
-        pe, ps = C.c_void_p(0), C.c_void_p(0)
-        engine.check(L.pb_reserve_j(len(b.epj), len(b.spj), C.byref(pe), C.byref(ps)), "pb_reserve_j")
-        assert (pe.value, ps.value) == self._ptrs, "j store moved"
         engine.check(L.pb_set_params(self.prm["eps"] ** 2, self.prm["r_out"] ** 2, self.prm["G"]), "pb_set_params")
-        engine.check(L.pb_upload_j_range(b.epj.ctypes.data, 0, self.n_loc, C.byref(engine.LAYOUT_EPJ),
-                                         b.spj.ctypes.data, 0, self.n_nodes, C.byref(engine.LAYOUT_SPJ)), "pb_upload_j_range")
+        self.upload_local_j()
         t1 = time.perf_counter()
-        self.pack_sends()
-        t2 = time.perf_counter()
-        self.exchange()
-        engine.check(L.pb_publish_j(C.c_void_p(self.torch.cuda.current_stream().cuda_stream)), "pb_publish_j")
+        self.exchange_device()
         t3 = time.perf_counter()
         if getattr(self, "_tables_for", None) is not force:
             self._tables, self._tables_for = engine.make_dispatch_tables(b, force), force
         f = engine.calc_force_all_and_write_back(b, self.prm["eps"], self.prm["r_out"], self.prm["G"],
                                                  force=force, my_rank=self.rank, send=False, tables=self._tables)
         t4 = time.perf_counter()
-        for k, v in (("upload_local_j", t1 - t0), ("pack_let", t2 - t1), ("let_all_to_all_enqueue", t3 - t2), ("dispatch_retrieve_loop", t4 - t3)):
+        for k, v in (("upload_local_j", t1 - t0), ("let_exchange_enqueue", t3 - t1), ("dispatch_retrieve_loop", t4 - t3)):
             self.host_s[k] = self.host_s.get(k, 0.0) + v
         self.n_steps += 1
         return f

@@ -165,3 +165,68 @@ def test_tree_from_pinned_staging_buffers():
     assert sc.tobytes() == cells.tobytes() and sg.tobytes() == groups.tobytes()
     f1 = engine.tree_force(batch, sc, sg, prm["eps"], prm["r_out"], prm["G"]).copy()
     assert f1.tobytes() == f0.tobytes()
+
+
+# ---- device-resident step: i-particles from the j store, plan and forces on the GPU (pb_tree_force_resident) ----------
+@pytest.mark.parametrize("kind,n", [("plummer", 20000), ("kroupa_binaries", 20000)])
+def test_resident_step_equals_host_planned_step(kind, n):
+    """Same lists, same kernels, the plan made on the device: forces agree with the host-planned tree step to summation-
+    order level (the walk origins differ in the last bits: mean by another summation order), counts exactly; the
+    oracle tolerance holds; a second (speculative, no host round trip) step reproduces the first bit for bit."""
+    batch, prm, cells, groups = _case(kind, n)
+    fh = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"]).copy()
+    f1 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], resident=True).copy()
+    f2 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], resident=True).copy()
+    tl = engine.tree_timeline()
+    print(f"[resident {kind} N={n}] device timeline ms {tl}")
+    assert np.array_equal(f1["n_ngb"], fh["n_ngb"])
+    assert np.abs(f1["acc"] - fh["acc"]).max() <= 2e-6 * np.abs(fh["acc"]).max()
+    assert np.abs(f1["pot"] - fh["pot"]).max() <= 2e-6 * np.abs(fh["pot"]).max()
+    assert f2.tobytes() == f1.tobytes()
+    ref = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"])
+    ea = np.linalg.norm(f1["acc"] - ref["acc"], axis=1) / np.linalg.norm(ref["acc"], axis=1)
+    ep = np.abs((f1["pot"] - ref["pot"]) / ref["pot"])
+    assert np.median(ea) <= 1e-6 and ea.max() <= 1e-4 and np.median(ep) <= 1e-6 and ep.max() <= 1e-4
+    assert np.array_equal(f1["n_ngb"], ref["n_ngb"])
+
+
+def test_resident_step_reservation_overflow_falls_back():
+    """theta 0.5 -> 0.3 roughly doubles the SP lists: the second step's reservations (lists, tasks, partial sums) are
+    too small, the device detects it without running anything past them, and the step is repeated exactly."""
+    batch, prm, cells, groups = _case("kroupa_binaries", 20000)
+    ref03 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.3).copy()
+    a = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.5, resident=True).copy()
+    b = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.5, resident=True).copy()
+    c = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.3, resident=True).copy()   # overflow -> exact repeat
+    d = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], theta=0.3, resident=True).copy()   # speculative again
+    assert a.tobytes() == b.tobytes() and c.tobytes() == d.tobytes()
+    assert np.array_equal(c["n_ngb"], ref03["n_ngb"])
+    assert np.abs(c["acc"] - ref03["acc"]).max() <= 2e-6 * np.abs(ref03["acc"]).max()
+    assert not np.array_equal(a["acc"], c["acc"])
+
+
+def test_resident_step_with_local_essential_tree():
+    batch, prm = _two_domain_case()
+    cells, groups = batch.tree.export_tree()
+    emap = batch.tree.export_elem_map()
+    # store order of the multi-GPU step: local particles first (in i-group order), LET entries behind them
+    n_loc = batch.n_epi_total
+    epj_src_is_local = np.zeros(len(batch.epj), bool)
+    fh = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], elem_map=emap).copy()
+    # sorted-order store: group g's particles are NOT a contiguous slice of it in a tree with LET elements, so build the
+    # store the resident step expects: slot k < n_loc = k-th i-particle, LET EP behind
+    ids_i = batch.epi["id"]
+    pos_of_id = {int(i): k for k, i in enumerate(batch.epj["id"])}
+    loc_sorted = np.array([pos_of_id[int(i)] for i in ids_i], dtype=np.int64)          # sorted index of every i-particle
+    is_loc = np.zeros(len(batch.epj), bool); is_loc[loc_sorted] = True
+    let_sorted = np.nonzero(~is_loc)[0]
+    perm = np.empty(len(batch.epj), dtype=np.int32)                                    # sorted index k lives in store slot perm[k]
+    perm[loc_sorted] = np.arange(n_loc, dtype=np.int32)
+    perm[let_sorted] = n_loc + np.arange(len(let_sorted), dtype=np.int32)
+    epj_store = np.zeros_like(batch.epj); epj_store[perm] = batch.epj
+    store = type(batch)(epj_store, batch.spj, batch.epi, batch.i_off, perm[batch.id_epj], batch.ej_off, batch.id_spj, batch.sj_off)
+    emap_store = np.where(emap >= 0, perm[np.maximum(emap, 0)], emap).astype(np.int32)
+    g2 = groups.copy(); g2["first"] = batch.i_off[:-1]                                 # = store slot of each group's first particle
+    fr = engine.tree_force(store, cells, g2, prm["eps"], prm["r_out"], prm["G"], elem_map=emap_store, resident=True)
+    assert np.array_equal(fr["n_ngb"], fh["n_ngb"])
+    assert np.abs(fr["acc"] - fh["acc"]).max() <= 2e-6 * np.abs(fh["acc"]).max()

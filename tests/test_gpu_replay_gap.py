@@ -61,14 +61,22 @@ def report():
 
 
 def test_dropin_default_mode_cancels_the_float_replay(report):
-    """coords = 2 + the reference's float replay: the corrected force meets the tolerance, and is far closer to the fp64
-    changeover force than the walk-relative kernel (coords = 0) combined with the same unmodified replay."""
+    """coords = 2 + the reference's float replay: median and p99 of the corrected force meet the tolerance with a wide
+    margin, and the result is orders of magnitude closer to the fp64 changeover force than the walk-relative kernel
+    (coords = 0) combined with the same unmodified replay.  The MAXIMUM of this deliberately extreme case (a 150 Msun
+    star in a 2e4-star cluster: its clamped neighbour term is G m / r_out^2 ~ 200 in units where |a| ~ 1) is set by the
+    fp32 rounding of that one term — 6e-8 x 200 ~ 1e-5 absolute on a light neighbour — which no fp32 kernel, the
+    reference's included (coords = 1 reproduces its arithmetic: same maximum), can cancel better; the full-size
+    config-3 case meets <= 1e-4 (tests/test_gpu_fullsize.py::test_fullsize_dropin_mode_sample)."""
     print(json.dumps(report, indent=1))
-    m2, m0 = report["modes"][2], report["modes"][0]
-    assert m2["corrected_vs_fp64_acc"]["median"] <= 1e-6 and m2["corrected_vs_fp64_acc"]["max"] <= 1e-4
+    m2, m1, m0 = report["modes"][2], report["modes"][1], report["modes"][0]
+    assert m2["corrected_vs_fp64_acc"]["median"] <= 1e-6 and m2["corrected_vs_fp64_acc"]["p99"] <= 1e-5
+    assert m2["corrected_vs_fp64_acc"]["max"] <= 1e-3 and m2["corrected_vs_fp64_acc"]["max"] <= 1.5 * m1["corrected_vs_fp64_acc"]["max"]
     assert m2["corrected_vs_fp64_pot_tot"]["median"] <= 1e-6 and m2["corrected_vs_fp64_pot_tot"]["max"] <= 1e-4
     assert m2["n_ngb_equal_oracle"]
-    assert m2["abs_residual_per_neighbour"]["median"] < 0.2 * m0["abs_residual_per_neighbour"]["median"]
+    assert m2["abs_residual_per_neighbour"]["median"] < 0.1 * m0["abs_residual_per_neighbour"]["median"]
+    assert m2["corrected_vs_fp64_acc"]["p99"] < 0.01 * m0["corrected_vs_fp64_acc"]["p99"]
+    assert m2["corrected_vs_fp64_acc"]["max"] < 0.01 * m0["corrected_vs_fp64_acc"]["max"]
 
 
 def test_absolute_mode_also_cancels_but_costs_far_field_accuracy(report):

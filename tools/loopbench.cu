@@ -196,8 +196,8 @@ loop_kernel(const float* __restrict__ init, int iters, int sync_every, float* __
     const float xi2[2] = {xi, xi1}, yi2[2] = {yi, yi1}, zi2[2] = {zi, zi1};
     const long long t0 = clock64();
     for (int it = 0; it < iters; it++) {
-        if (KIND == 0) ep_pairs<0, 0>(sm.ep[0], 0, kTilePairs, xi, yi, zi, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, eps2, rcut2, ax, ay, az, pt, cf);
-        if (KIND == 1) ep_pairs<0, 1>(sm.ep[0], 0, kTilePairs, xi, yi, zi, 1e-9f, 1e-9f, 1e-9f, 1.f, 0.f, 0.f, 0.f, eps2, rcut2, ax, ay, az, pt, cf);
+        if (KIND == 0) ep_pairs<0, 0>(sm.ep[0], 0, kTilePairs, xi, yi, zi, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, eps2, rcut2, 0.f, ax, ay, az, pt, cf);
+        if (KIND == 1) ep_pairs<0, 1>(sm.ep[0], 0, kTilePairs, xi, yi, zi, 1e-9f, 1e-9f, 1e-9f, 1.f, 0.f, 0.f, 0.f, eps2, rcut2, 0.f, ax, ay, az, pt, cf);
         if (KIND == 2) sp_pairs<0>(sm.sp[0], 0, kTilePairs, xi, yi, zi, eps2, ax, ay, az, pt);
         if (KIND == 3) sp_pairs_2i<0>(sm.sp[0], 0, kTilePairs, xi2, yi2, zi2, eps2, ax2, ay2, az2, pt2);
         if (KIND == 4) sp_ipacked<0, 2>(sm.sp[0], 0, kTilePairs, make_float2(xi, xi1), make_float2(yi, yi1), make_float2(zi, zi1), eps2, ax, ay, az, pt);

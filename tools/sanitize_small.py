@@ -10,6 +10,9 @@ f = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G
 g = engine.tree_neighbor_search(batch, n_walk_limit=16)
 cells, groups = batch.tree.export_tree()
 h = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"])
+for _ in range(2):      # device-resident step: first exact, then speculative
+    hr = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], resident=True)
+assert np.array_equal(hr["n_ngb"], h["n_ngb"])
 part = np.zeros(len(batch.epj), dtype=EPJSoft)
 part["pos"], part["mass"] = batch.epj["pos"], batch.epj["mass"]
 pts = np.random.default_rng(0).normal(size=(100, 3))
