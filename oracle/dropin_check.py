@@ -20,15 +20,18 @@ class DropinChecker:
     """Neighbour lists (FDPS's search: |dx| < max of the 0.99 r_search, src/ptcl.hpp:8) and correction inputs for a
     particle set of harness.kroupa_binary_particles / a plain Plummer set; `subset` = particle indices to check."""
 
-    def __init__(self, P, prm, subset=None):
+    def __init__(self, P, prm, subset=None, p0=None, rs=None):
+        """Either P (particle dict) or p0 (PtclCorr rows of the particle set, e.g. what one rank's j store holds: its own
+        particles and the LET particles) + rs (their r_search)."""
         self.prm = prm
-        self.p0 = hz.corr_particles(P)
+        self.p0 = hz.corr_particles(P) if p0 is None else np.ascontiguousarray(p0)
+        rs = P["rs"] if rs is None else rs
         n = len(self.p0)
         self.subset = np.arange(n) if subset is None else np.asarray(subset)
         if subset is None:
-            self.off, self.idx = hz.neighbor_lists(P["pos"], 0.99 * P["rs"])
+            self.off, self.idx = hz.neighbor_lists(self.p0["pos"], 0.99 * rs)
         else:
-            self.off, self.idx = hz.neighbor_lists_subset(P["pos"], 0.99 * P["rs"], self.subset)
+            self.off, self.idx = hz.neighbor_lists_subset(self.p0["pos"], 0.99 * rs, self.subset)
         self.n_nb = np.diff(self.off) - 1
 
     def corrected(self, acc, pot, replay_fp32):
@@ -54,8 +57,4 @@ class DropinChecker:
                 "pass": bool(np.median(ea) <= 1e-6 and ea.max() <= 1e-4 and np.median(ep) <= 1e-6 and ep.max() <= 1e-4)}
 
 
-def plummer_particles(mass, pos, vel, prm):
-    """The dict shape of harness.kroupa_binary_particles for a set of single stars."""
-    r_in, r_out, rs = hz.particle_rout_rsearch(mass, vel, prm)
-    return dict(pos=pos, mass=mass, vel=vel, rs=rs, r_in=r_in, r_out=r_out, ptype=np.ones(len(mass), np.int32), prm=prm,
-                n_star=len(mass), n_bin=0)
+plummer_particles = hz.plummer_particles      # (lives with the other input generators)

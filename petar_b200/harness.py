@@ -380,6 +380,13 @@ def neighbor_lists(pos, rs):
     return off.astype(np.int32), jj.astype(np.int32)
 
 
+def plummer_particles(mass, pos, vel, prm):
+    """The dict shape of :func:`kroupa_binary_particles` for a set of single stars."""
+    r_in, r_out, rs = particle_rout_rsearch(mass, vel, prm)
+    return dict(pos=pos, mass=mass, vel=vel, rs=rs, r_in=r_in, r_out=r_out, ptype=np.ones(len(mass), np.int32), prm=prm,
+                n_star=len(mass), n_bin=0)
+
+
 def neighbor_lists_subset(pos, rs, subset):
     """As :func:`neighbor_lists`, for the particles `subset` only: CSR over the subset, j over ALL particles."""
     from scipy.spatial import cKDTree

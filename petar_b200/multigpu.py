@@ -99,11 +99,12 @@ def build_domain_workload(pos, mass, vel, rs, r_in, r_out, rank, world, dist=Non
             send_ep_idx.append(e); send_sp.append(s)
 
     # fp64 LET exchange for the (untimed) global-tree build: what FDPS's MPI exchange carries
-    ep_rows = [np.column_stack([lpos[e], lmass[e], lrs[e]]) if len(e) else np.zeros((0, 5)) for e in send_ep_idx]
+    # (sixth column: the particle's global index, so that checkers can look up its other attributes)
+    ep_rows = [np.column_stack([lpos[e], lmass[e], lrs[e], my[e].astype(np.float64)]) if len(e) else np.zeros((0, 6)) for e in send_ep_idx]
     sp_rows = [s.view(np.float64).reshape(-1, 10) for s in send_sp]
-    recv_ep, recv_ep_cnt = exchange_rows(dist, ep_rows, 5, np.float64)
+    recv_ep, recv_ep_cnt = exchange_rows(dist, ep_rows, 6, np.float64)
     recv_sp, recv_sp_cnt = exchange_rows(dist, sp_rows, 10, np.float64)
-    let_ep = np.concatenate(recv_ep) if recv_ep else np.zeros((0, 5))
+    let_ep = np.concatenate(recv_ep) if recv_ep else np.zeros((0, 6))
     let_sp = np.ascontiguousarray(np.concatenate(recv_sp)).view(SPJQuad).reshape(-1)
     let = dict(pos=let_ep[:, 0:3], mass=let_ep[:, 3], rsearch=let_ep[:, 4], spj=let_sp)
 
@@ -141,7 +142,8 @@ def build_domain_workload(pos, mass, vel, rs, r_in, r_out, rank, world, dist=Non
     elem_map = np.where(em >= 0, epj_src[np.maximum(em, 0)], ~sp_src[np.maximum(~em, 0)] if n_let_sp else em).astype(np.int32)
     return dict(batch=batch, my=my, epi_src=epi_src, n_loc=n_loc, n_nodes=n_nodes, n_let_ep=n_let_ep, n_let_sp=n_let_sp,
                 send_ep_idx=send_ep_idx, send_sp=send_sp, recv_ep_cnt=recv_ep_cnt, recv_sp_cnt=recv_sp_cnt, let=let, local_tree=tloc,
-                tree_cells=cells, tree_groups=groups, elem_map=elem_map)
+                tree_cells=cells, tree_groups=groups, elem_map=elem_map,
+                store_gid=np.concatenate([my, let_ep[:, 5].astype(np.int64)]))
 
 
 class DomainStepper:

@@ -8,8 +8,16 @@ import pytest
 from conftest import ROOT
 
 
-@pytest.mark.parametrize("world,port", [(2, 29611), (4, 29612)])
-def test_domain_decomposition_and_let_exchange_gloo(world, port):
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_domain_decomposition_and_let_exchange_gloo(world):
+    port = _free_port()
     env = dict(os.environ, OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "_multirank_worker.py")]
