@@ -145,6 +145,9 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "min_slot_work"  a dispatch is not cut into per-stream sub-batches smaller than this many EP-equivalent
  *                interactions (n_epi * (n_epj + 2 n_spj)); default 0 = always "streams" (measured: 4e7 saves enqueue time
  *                at 8 ranks per node but costs more pipelining than it saves at 4).
+ *   "ws"         1 (default): persistent force launches (the device-resident tree step) run the warp-specialised kernel —
+ *                8 compute warps that only wait for tiles and run the pair loops, 1 producer warp that fetches tasks and
+ *                stages j tiles four deep (pb_kernels_ws.cu); 0: every warp stages and computes (pb::force_kernel).
  *   "chunk_tile" 1 (default): the j chunks of the task plan are whole 256-entry tiles, so only the last chunk of a list ends
  *                in a ragged tile; 0: equal chunks in multiples of 8 entries (the round-1 plan, kept for A/B runs).
  *   "nb_lists"   1: pb_dispatch_count_index also collects the neighbour PAIRS (see pb_retrieve_neighbors);

@@ -105,6 +105,11 @@ cudaError_t launch_force_persistent(cudaStream_t s, int n_ctas, int nr_steps,
                                     const Walk* walks, const Task* tasks, const float4* epi, const int* id_epj, const int* id_spj,
                                     const float4* epj, const float4* spj, double4* part4, int* partn, Params p);
 
+// warp-specialised persistent force kernel (pb_kernels_ws.cu): 8 compute warps + 1 producer warp per CTA
+cudaError_t launch_force_ws(cudaStream_t s, int n_ctas, int nr_steps,
+                            const Walk* walks, const Task* tasks, const float4* epi, const int* id_epj, const int* id_spj,
+                            const float4* epj, const float4* spj, double4* part4, int* partn, Params p);
+
 // device-side i-particle preparation and task planning (pb_plan.cu)
 cudaError_t launch_iprep(cudaStream_t s, const void* groups, int n_groups, const int* i_first, const int2* counts, const int2* offs,
                          const float4* epj, Walk* walks, float4* epi, int i_f4, int coords, int cull);

@@ -151,6 +151,7 @@ struct Engine {
     bool spec_pending = false; int2* d_tree_caps = nullptr; size_t cap_tree_caps = 0;
     int opt_walk_ctas = 148 * 16;                          // CTAs (4 warps each, one warp per i-group at a time) of the tree-walk launches
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
+    int opt_ws = 1;                                        // persistent launches use the warp-specialised kernel (pb_kernels_ws.cu)
     int opt_chunk_tile = 1;                                // j chunks are whole 256-entry tiles (0: multiples of 8 entries, the round-1 plan)
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
     long long nb_n_i = 0;
@@ -916,6 +917,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "tree_streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "tree_streams must be in [1, %d]", kMaxStreams); E.opt_tree_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_spec")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_spec must be 0 or 1"); E.opt_tree_spec = (int)v; return PB_OK; }
     if (!strcmp(key, "walk_ctas")) { if (v < 1 || v > 148 * 16) return fail(PB_ERR_ARG, "walk_ctas must be in [1, 2368]"); E.opt_walk_ctas = (int)v; return PB_OK; }
+    if (!strcmp(key, "ws")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "ws must be 0 or 1"); E.opt_ws = (int)v; return PB_OK; }
     if (!strcmp(key, "chunk_tile")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "chunk_tile must be 0 or 1"); E.opt_chunk_tile = (int)v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
@@ -931,7 +933,7 @@ int pb_get_option(const char* key, long long* v) {
         {"coords", E.opt_coords}, {"streams", E.opt_streams}, {"jchunk", E.opt_jchunk}, {"cull", E.opt_cull},
         {"tree_fill", E.opt_tree_fill}, {"min_slot_work", E.opt_min_slot_work}, {"tree_streams", E.opt_tree_streams},
         {"tree_spec", E.opt_tree_spec}, {"walk_ctas", E.opt_walk_ctas}, {"nb_lists", E.opt_nb_lists},
-        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
+        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"ws", E.opt_ws}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
     for (const auto& t : tab)
         if (!strcmp(key, t.k)) { *v = t.val; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_get_option: unknown key '%s'", key);
@@ -1754,7 +1756,7 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
     cudaStream_t s0 = E.slots[0].stream;
     const int ng = E.n_groups;
     const double theta_inv2 = E.theta > 0.0 ? 1.0 / (E.theta * E.theta) : 1e300;
-    int U = E.opt_jchunk > 0 ? E.opt_jchunk : 1536;
+    int U = E.opt_jchunk > 0 ? E.opt_jchunk : 4096;       // j per warp and task: the persistent launch balances itself, bigger tasks cost less (swept 1024..8192)
     U = (int)align_up((size_t)U, kTileJ);
     const int Us = std::max(kTileJ, U / 2);
     const int coords = E.opt_coords, i_f4 = coords == 2 ? 3 : 2;
@@ -1836,8 +1838,12 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
     Plan pl; pl.coords = coords; pl.i_f4 = i_f4; pl.count_only = 0;
     Params prm = make_params(pl, nullptr);
     prm.meta = E.d_r_meta;
-    CU(launch_force_persistent(s0, 2 * 148, E.opt_nr, E.d_r_walks, E.d_r_tasks, E.d_r_epi, E.d_tree_ide, E.d_tree_ids, E.d_epj, E.d_spj,
-                               E.d_r_part4, E.d_r_partn, prm));
+    if (E.opt_ws)
+        CU(launch_force_ws(s0, 2 * 148, E.opt_nr, E.d_r_walks, E.d_r_tasks, E.d_r_epi, E.d_tree_ide, E.d_tree_ids, E.d_epj, E.d_spj,
+                           E.d_r_part4, E.d_r_partn, prm));
+    else
+        CU(launch_force_persistent(s0, 2 * 148, E.opt_nr, E.d_r_walks, E.d_r_tasks, E.d_r_epi, E.d_tree_ide, E.d_tree_ids, E.d_epj, E.d_spj,
+                                   E.d_r_part4, E.d_r_partn, prm));
     CU(cudaEventRecord(E.ev_tl[4], s0));
     CU(launch_reduce(s0, E.r_n_iblk, E.d_r_iblocks, E.d_r_part4, E.d_r_partn, E.d_r_out, E.G, E.d_r_meta));
     CU(cudaEventRecord(E.ev_tl[5], s0));
