@@ -145,6 +145,11 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "min_slot_work"  a dispatch is not cut into per-stream sub-batches smaller than this many EP-equivalent
  *                interactions (n_epi * (n_epj + 2 n_spj)); default 0 = always "streams" (measured: 4e7 saves enqueue time
  *                at 8 ranks per node but costs more pipelining than it saves at 4).
+ *   "raw_upload" 1: pb_upload_j / pb_upload_j_range page-lock the caller's arrays once (cudaHostRegister), copy them as they
+ *                are and pack them on the device (bit-identical to the host packing) — for several ranks per node, where the
+ *                host cores (4 per rank on an 8-GPU box) are scarcer than PCIe bandwidth: 2.7 -> 0.3 ms of host time per
+ *                tree step at 8 ranks.  The arrays must then stay unchanged until the step's forces are back.  0 (default):
+ *                packed on the host into pinned staging; the arrays are consumed when the call returns.
  *   "ws"         1 (default): persistent force launches (the device-resident tree step) run the warp-specialised kernel —
  *                8 compute warps that only wait for tiles and run the pair loops, 1 producer warp that fetches tasks and
  *                stages j tiles four deep (pb_kernels_ws.cu); 0: every warp stages and computes (pb::force_kernel).
@@ -194,8 +199,9 @@ int  pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_
  * get_potential_at_point compute with CalcForcePPSimd per point on the CPU (reference
  * amuse-interface/interface.cc:966-1030, src/soft_force.hpp:285-344).  `ptcl` is described by
  * stride + offsets of pos (3 doubles) and mass (double), e.g. PeTar's FPSoft array.  Outputs are
- * ASSIGNED; any of ax/ay/az/pot may be NULL.  Replaces the content of the j store (FDPS re-publishes
- * it at the start of every tree step anyway). */
+ * ASSIGNED; any of ax/ay/az/pot may be NULL.  REPLACES the content of the j store and leaves it unpublished: the next
+ * pb_dispatch_* / pb_tree_force* without a fresh pb_upload_j fails with PB_ERR_PROTOCOL, and device pointers obtained
+ * from pb_reserve_j before the call are invalid (FDPS re-publishes j at the start of every tree step anyway). */
 int  pb_field_at_points(const double* x, const double* y, const double* z, int n_points,
                         const void* ptcl, int n_ptcl, size_t stride, size_t off_pos, size_t off_mass,
                         double G, double* ax, double* ay, double* az, double* pot);

@@ -53,7 +53,7 @@ def build_engine(force=False, verbose=False):
     # pb_walk.cu (tree walk, fp64 geometry) and pb_corr.cu (changeover correction, fp64) are compiled
     # without FMA contraction so that their results are bit-identical to host code; the force kernels
     # keep the default
-    units = (("pb_kernels.cu", []), ("pb_engine.cu", []), ("pb_walk.cu", ["-fmad=false"]), ("pb_corr.cu", ["-fmad=false"]), ("pb_plan.cu", []), ("pb_kernels_ws.cu", []))
+    units = (("pb_kernels.cu", []), ("pb_engine.cu", []), ("pb_walk.cu", ["-fmad=false"]), ("pb_corr.cu", ["-fmad=false"]), ("pb_plan.cu", []), ("pb_kernels_ws.cu", []), ("pb_pack.cu", ["-fmad=false"]))
     srcs = [os.path.join(CSRC, f) for f, _ in units]
     deps = srcs + [os.path.join(CSRC, "pb_device.h"), os.path.join(CSRC, "pb_pairs.cuh"), os.path.join(INC, "petar_b200.h")]
     if force or _newer(target, deps):

@@ -61,13 +61,11 @@ const pb_layout_spj kLayoutSpj = {sizeof(SPJSoft), PB_POS_OFFSET(SPJSoft), offse
 const pb_layout_force kLayoutForce = {sizeof(ForceSoft), offsetof(ForceSoft, acc), offsetof(ForceSoft, pot), offsetof(ForceSoft, n_ngb)};
 #pragma GCC diagnostic pop
 
-bool g_first_call = true;
-
+// device = my_rank % device count, as reference src/force_gpu_cuda.cu:550-553.  pb_init is idempotent and cheap once
+// the library is initialised, so it is simply called every time: after a pb_finalize() (a PeTar that re-initialises)
+// the rank's own device is selected again instead of the library's lazy default (device 0).
 void first_call(PS::S32 my_rank) {
-    if (!g_first_call) return;
-    // device = my_rank % device count, as reference src/force_gpu_cuda.cu:550-553
     check(pb_init(my_rank, -1), "pb_init");
-    g_first_call = false;
 }
 
 #ifdef GPU_PROFILE

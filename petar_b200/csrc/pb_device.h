@@ -115,6 +115,9 @@ cudaError_t launch_iprep(cudaStream_t s, const void* groups, int n_groups, const
                          const float4* epj, Walk* walks, float4* epi, int i_f4, int coords, int cull);
 cudaError_t launch_devplan(cudaStream_t s, const void* groups, int n_groups, const int* i_first, const int2* counts, int U, int Us,
                            int3* goff, int* meta, int cap_tasks, long long cap_part, Task* tasks, IBlock* iblocks, const int2* caps);
+// device-side packing of raw host arrays (pb_pack.cu, option "raw_upload")
+cudaError_t launch_pack_epj(cudaStream_t s, const void* raw, size_t stride, size_t off_pos, size_t off_mass, size_t off_rs, int n, float4* out);
+cudaError_t launch_pack_spj(cudaStream_t s, const void* raw, size_t stride, size_t off_pos, size_t off_mass, size_t off_quad, int has_quad, int n, float4* out);
 cudaError_t launch_gather_epj(cudaStream_t s, const float4* epj, const int* idx, int n, float4* out);
 void plan_sizes_host(const int* ni, const int2* counts, int n_groups, int U, int Us, long long* n_tasks, long long* n_part, long long* n_iblk);
 
@@ -128,6 +131,12 @@ cudaError_t launch_walk_count(cudaStream_t s, const void* cells, const void* gro
 cudaError_t launch_walk_fill(cudaStream_t s, const void* cells, const void* groups, int g0, int n_groups, double theta_inv2,
                              const int2* offs, int* id_e, int* id_s, int* scratch, int cap, int n_ctas, int* overflow,
                              const int* elem_map = nullptr, int n_cells = 0, const int2* caps = nullptr, int2* counts = nullptr);
+
+// compact walk records (64-B fp32 + 48-B int per cell) and the walk that classifies on them first (pb_walk.cu)
+cudaError_t launch_compact_cells(cudaStream_t s, const void* cells, int n_cells, void* A, void* B);
+cudaError_t launch_walk_c(cudaStream_t s, bool fill, const void* cells, const void* A, const void* B, const void* groups, int g0, int n_groups,
+                          double theta_inv2, double coord_max, int2* counts, const int2* offs, int* id_e, int* id_s, int* scratch, int cap,
+                          int n_ctas, int* overflow, const int* elem_map, int n_cells, const int2* caps);
 
 // changeover correction (pb_corr.cu): the fields of one neighbour / one corrected particle, fp64
 struct CorrJ { double x, y, z, mass, r_in, r_out, mass_bk, status; long long id; };       // 72 B

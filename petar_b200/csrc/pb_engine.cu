@@ -151,6 +151,11 @@ struct Engine {
     bool spec_pending = false; int2* d_tree_caps = nullptr; size_t cap_tree_caps = 0;
     int opt_walk_ctas = 148 * 16;                          // CTAs (4 warps each, one warp per i-group at a time) of the tree-walk launches
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
+    int opt_walk_compact = 1;                              // tree walk classifies on 64-B fp32 records first (exact fp64 re-check when undecided)
+    void* d_cellA = nullptr; void* d_cellB = nullptr; size_t cap_cellAB = 0; double coord_max = 0.0;
+    int opt_raw_upload = 0;                                // pb_upload_j_range copies the caller's arrays as they are and packs them on the device
+    char* d_raw = nullptr; size_t cap_raw = 0;             // device landing zone of the raw arrays
+    std::vector<std::pair<const char*, size_t>> registered;   // host ranges page-locked by the library (cudaHostRegister)
     int opt_ws = 1;                                        // persistent launches use the warp-specialised kernel (pb_kernels_ws.cu)
     int opt_chunk_tile = 1;                                // j chunks are whole 256-entry tiles (0: multiples of 8 entries, the round-1 plan)
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
@@ -874,7 +879,8 @@ void pb_finalize(void) {
         cudaStreamDestroy(S.stream);
         S = Slot();
     }
-    cudaFree(E.d_epj); cudaFree(E.d_spj); cudaFreeHost(E.h_jstage);
+    cudaFree(E.d_epj); cudaFree(E.d_spj); cudaFreeHost(E.h_jstage); cudaFree(E.d_raw); cudaFree(E.d_cellA); cudaFree(E.d_cellB);
+    for (auto& r : E.registered) cudaHostUnregister((void*)r.first);
     if (E.d_elem_map) cudaFree(E.d_elem_map);
     if (E.h_elem_map) cudaFreeHost(E.h_elem_map);
     if (E.h_corr) cudaFreeHost(E.h_corr);
@@ -917,6 +923,8 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "tree_streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "tree_streams must be in [1, %d]", kMaxStreams); E.opt_tree_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_spec")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_spec must be 0 or 1"); E.opt_tree_spec = (int)v; return PB_OK; }
     if (!strcmp(key, "walk_ctas")) { if (v < 1 || v > 148 * 16) return fail(PB_ERR_ARG, "walk_ctas must be in [1, 2368]"); E.opt_walk_ctas = (int)v; return PB_OK; }
+    if (!strcmp(key, "walk_compact")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "walk_compact must be 0 or 1"); E.opt_walk_compact = (int)v; return PB_OK; }
+    if (!strcmp(key, "raw_upload")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "raw_upload must be 0 or 1"); E.opt_raw_upload = (int)v; return PB_OK; }
     if (!strcmp(key, "ws")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "ws must be 0 or 1"); E.opt_ws = (int)v; return PB_OK; }
     if (!strcmp(key, "chunk_tile")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "chunk_tile must be 0 or 1"); E.opt_chunk_tile = (int)v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
@@ -933,7 +941,7 @@ int pb_get_option(const char* key, long long* v) {
         {"coords", E.opt_coords}, {"streams", E.opt_streams}, {"jchunk", E.opt_jchunk}, {"cull", E.opt_cull},
         {"tree_fill", E.opt_tree_fill}, {"min_slot_work", E.opt_min_slot_work}, {"tree_streams", E.opt_tree_streams},
         {"tree_spec", E.opt_tree_spec}, {"walk_ctas", E.opt_walk_ctas}, {"nb_lists", E.opt_nb_lists},
-        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"ws", E.opt_ws}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
+        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"ws", E.opt_ws}, {"raw_upload", E.opt_raw_upload}, {"walk_compact", E.opt_walk_compact}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
     for (const auto& t : tab)
         if (!strcmp(key, t.k)) { *v = t.val; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_get_option: unknown key '%s'", key);
@@ -952,6 +960,25 @@ int pb_reserve_j(int n_epj, int n_spj, void** d_epj, void** d_spj) {
     return PB_OK;
 }
 
+namespace {
+// page-lock [p, p + bytes) once so that it can be the source of an asynchronous DMA; a range registered earlier that
+// overlaps a different one (the caller re-allocated its array) is released first.  false: not possible, pack on the host.
+bool ensure_registered(const void* ptr, size_t bytes) {
+    const char* p = (const char*)ptr;
+    if (bytes == 0) return true;
+    for (auto& r : E.registered)
+        if (p >= r.first && p + bytes <= r.first + r.second) return true;
+    for (size_t k = 0; k < E.registered.size();) {
+        auto& r = E.registered[k];
+        if (p < r.first + r.second && r.first < p + bytes) { cudaHostUnregister((void*)r.first); E.registered.erase(E.registered.begin() + k); }
+        else k++;
+    }
+    if (cudaHostRegister((void*)p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+    E.registered.push_back({p, bytes});
+    return true;
+}
+} // namespace
+
 int pb_upload_j_range(const void* epj, int epj_first, int n_epj, const pb_layout_epj* lepj,
                       const void* spj, int spj_first, int n_spj, const pb_layout_spj* lspj) {
     int rc = ensure_init();
@@ -962,6 +989,39 @@ int pb_upload_j_range(const void* epj, int epj_first, int n_epj, const pb_layout
     if ((n_epj && (!epj || !lepj)) || (n_spj && (!spj || !lspj))) return fail(PB_ERR_ARG, "pb_upload_j_range: null input");
     const double t0 = now_s();
     const size_t nf4 = 2 * (size_t)n_epj + 4 * (size_t)n_spj;
+    if (E.opt_raw_upload) {
+        // the arrays travel as they are (page-locked once) and are packed on the device: no host core touches them.
+        // They must stay unchanged until the step's first kernels have run (FDPS keeps epj_sorted / spj_sorted for the
+        // whole force calculation).
+        const size_t be = n_epj ? (size_t)n_epj * lepj->stride : 0, bs = n_spj ? (size_t)n_spj * lspj->stride : 0;
+        if (ensure_registered(epj, be) && ensure_registered(spj, bs)) {
+            const size_t o_s = align_up(be, 256);
+            if (o_s + bs > E.cap_raw) {
+                CU(cudaStreamSynchronize(E.s_upload));
+                if (E.d_raw) CU(cudaFree(E.d_raw));
+                E.d_raw = nullptr; E.cap_raw = 0;
+                const size_t cap = align_up(o_s + bs + (o_s + bs) / 4, 1 << 20);
+                CU(cudaMalloc(&E.d_raw, cap));
+                E.cap_raw = cap;
+            }
+            E.end_prev_valid = false;
+            CU(cudaEventRecord(E.ev_send0, E.s_upload));
+            if (n_epj) {
+                CU(cudaMemcpyAsync(E.d_raw, epj, be, cudaMemcpyHostToDevice, E.s_upload));
+                CU(launch_pack_epj(E.s_upload, E.d_raw, lepj->stride, lepj->off_pos, lepj->off_mass, lepj->off_rsearch, n_epj, E.d_epj + 2 * (size_t)epj_first));
+            }
+            if (n_spj) {
+                CU(cudaMemcpyAsync(E.d_raw + o_s, spj, bs, cudaMemcpyHostToDevice, E.s_upload));
+                CU(launch_pack_spj(E.s_upload, E.d_raw + o_s, lspj->stride, lspj->off_pos, lspj->off_mass, lspj->off_quad, lspj->has_quad, n_spj, E.d_spj + 4 * (size_t)spj_first));
+            }
+            CU(cudaEventRecord(E.ev_send1, E.s_upload));
+            E.send_timed = true;
+            E.prof.h2d_bytes += (long long)(be + bs);
+            E.prof.n_kernel_launch += (n_epj > 0) + (n_spj > 0);
+            E.prof.t_copy += now_s() - t0;
+            return PB_OK;
+        }
+    }
     if ((rc = grow_jstage(nf4)) != PB_OK) return rc;
     CU(cudaStreamSynchronize(E.s_upload));               // staging buffer free again
     float4* he = E.h_jstage;
@@ -1300,6 +1360,9 @@ int pb_field_at_points(const double* x, const double* y, const double* z, int n_
         if (rc == PB_OK) rc = pb_retrieve(nw, ni.data() + w0, fptr.data() + w0, &lf);
     }
     E.eps2 = eps2; E.rcut2 = rcut2; E.G = G0;
+    // the j store now holds the query's particle set (mass > 0 only, r_search = 0): a dispatch or tree step that follows
+    // without a fresh pb_upload_j must fail with PB_ERR_PROTOCOL instead of running against it
+    E.j_published = false;
     if (rc != PB_OK) return rc;
     for (int i = 0; i < n_points; i++) {
         if (ax) ax[i] = out[i].ax;
@@ -1448,6 +1511,24 @@ int tree_finish_slot(Slot& S, char* force, const pb_layout_force& L, size_t i_fi
 }
 } // namespace
 
+namespace {
+// the two walk passes, on the compact records (default) or on the fp64 cells alone
+cudaError_t walk_count(cudaStream_t st, int g0, int ng, double theta_inv2, int slot) {
+    if (E.opt_walk_compact)
+        return launch_walk_c(st, false, E.d_cells, E.d_cellA, E.d_cellB, E.d_groups, g0, ng, theta_inv2, E.coord_max, E.d_counts, nullptr, nullptr, nullptr,
+                             E.d_walk_scratch[slot], kWalkCap, kWalkCtas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells, nullptr);
+    return launch_walk_count(st, E.d_cells, E.d_groups, g0, ng, theta_inv2, E.d_counts, E.d_walk_scratch[slot], kWalkCap, kWalkCtas, E.d_overflow,
+                             E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells);
+}
+cudaError_t walk_fill(cudaStream_t st, int g0, int ng, double theta_inv2, int slot, int n_ctas, const int2* caps, int2* counts) {
+    if (E.opt_walk_compact)
+        return launch_walk_c(st, true, E.d_cells, E.d_cellA, E.d_cellB, E.d_groups, g0, ng, theta_inv2, E.coord_max, counts, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
+                             E.d_walk_scratch[slot], kWalkCap, n_ctas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells, caps);
+    return launch_walk_fill(st, E.d_cells, E.d_groups, g0, ng, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
+                            E.d_walk_scratch[slot], kWalkCap, n_ctas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells, caps, counts);
+}
+} // namespace
+
 int pb_tree_stage(int n_cells, int n_groups, pb_tree_cell** cells, pb_tree_group** groups) {
     int rc = ensure_init();
     if (rc != PB_OK) return rc;
@@ -1563,6 +1644,24 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
         const double theta_inv2 = theta > 0.0 ? 1.0 / (theta * theta) : 1e300;
         cudaStream_t s0 = E.slots[0].stream;
         CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));
+        if (E.opt_walk_compact) {
+            if ((size_t)n_cells > E.cap_cellAB) {
+                if (E.d_cellA) CU(cudaFree(E.d_cellA));
+                if (E.d_cellB) CU(cudaFree(E.d_cellB));
+                E.cap_cellAB = E.cap_cells;
+                CU(cudaMalloc(&E.d_cellA, 64 * E.cap_cellAB));
+                CU(cudaMalloc(&E.d_cellB, 48 * E.cap_cellAB));
+            }
+            // S = the largest |coordinate| any box of the tree can have: bounds the fp32 rounding of the compact records
+            double smax = 0.0;
+            if (n_cells > 0)
+                for (int k = 0; k < 3; k++)
+                    smax = std::max(smax, std::max(std::max(std::fabs(cells[0].out_lo[k]), std::fabs(cells[0].out_hi[k])),
+                                                   std::max(std::fabs(cells[0].in_lo[k]), std::fabs(cells[0].in_hi[k]))));
+            E.coord_max = 2.0 * smax;
+            CU(launch_compact_cells(s0, E.d_cells, n_cells, E.d_cellA, E.d_cellB));
+            E.prof.n_kernel_launch += 1;
+        }
         for (int k = 0; k < 8; k++) if (!E.ev_tl[k]) CU(cudaEventCreate(&E.ev_tl[k]));
         CU(cudaEventRecord(E.ev_tl[0], s0));                 // tree on the device, walk starts
         E.tl_valid = false;
@@ -1595,15 +1694,12 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
                 CU(cudaMemcpyAsync(E.d_tree_off, E.h_tree_off.data(), sizeof(int2) * (size_t)n_groups, cudaMemcpyHostToDevice, s0));
                 CU(cudaMemcpyAsync(E.d_tree_caps, caps.data(), sizeof(int2) * (size_t)n_groups, cudaMemcpyHostToDevice, s0));
                 CU(cudaMemsetAsync(E.d_overflow + 1, 0, sizeof(int), s0));
-                CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, n_groups, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
-                                    E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, n_cells,
-                                    E.d_tree_caps, E.d_counts));
+                CU(walk_fill(s0, 0, n_groups, theta_inv2, 0, kWalkCtas, E.d_tree_caps, E.d_counts));
                 E.spec_pending = true;
             }
         }
         if (!E.spec_pending)
-            CU(launch_walk_count(s0, E.d_cells, E.d_groups, 0, n_groups, theta_inv2, E.d_counts, E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow,
-                                 E.has_elem_map ? E.d_elem_map : nullptr, n_cells));
+            CU(walk_count(s0, 0, n_groups, theta_inv2, 0));
         CU(cudaEventRecord(E.ev_tl[1], s0));                 // walk (count pass, or speculative list fill) done
         CU(cudaMemcpyAsync(E.h_counts_p, E.d_counts, sizeof(int2) * (size_t)n_groups, cudaMemcpyDeviceToHost, s0));
         CU(cudaMemcpyAsync(E.h_over_p, E.d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, s0));
@@ -1665,8 +1761,7 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
         if (!E.d_tree_off) CU(cudaMalloc(&E.d_tree_off, sizeof(int2) * E.cap_counts));   // freed whenever d_counts is re-sized
         CU(cudaMemcpyAsync(E.d_tree_off, E.h_tree_off.data(), sizeof(int2) * (size_t)E.n_groups, cudaMemcpyHostToDevice, s0));
         if (!split_fill) {
-            CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, E.n_groups, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
-                                E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells));
+            CU(walk_fill(s0, 0, E.n_groups, theta_inv2, 0, kWalkCtas, nullptr, nullptr));
             E.prof.n_kernel_launch += 1;
         } else {
             for (int s = 0; s < n_slots; s++) if ((rc = ensure_walk_scratch(s)) != PB_OK) return rc;
@@ -1718,9 +1813,7 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
         const size_t h2d = S.plan.off_ide;
         CU(cudaStreamWaitEvent(S.stream, E.ev_fill, 0));
         if (split_fill) {
-            CU(launch_walk_fill(S.stream, E.d_cells, E.d_groups, g0, nb, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
-                                E.d_walk_scratch[s], kWalkCap, std::min(kWalkCtas, (nb + 3) / 4), E.d_overflow,
-                                E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells));
+            CU(walk_fill(S.stream, g0, nb, theta_inv2, s, std::min(kWalkCtas, (nb + 3) / 4), nullptr, nullptr));
             E.prof.n_kernel_launch += 1;
         }
         CU(cudaEventRecord(S.ev[0], S.stream));
@@ -1803,9 +1896,7 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
         CU(cudaMemcpyAsync(E.d_tree_off, E.h_tree_off.data(), sizeof(int2) * (size_t)ng, cudaMemcpyHostToDevice, s0));
         if ((rc = ensure_walk_scratch(0)) != PB_OK) return rc;
         CU(cudaMemsetAsync(E.d_overflow, 0, 2 * sizeof(int), s0));
-        CU(launch_walk_fill(s0, E.d_cells, E.d_groups, 0, ng, theta_inv2, E.d_tree_off, E.d_tree_ide, E.d_tree_ids,
-                            E.d_walk_scratch[0], kWalkCap, kWalkCtas, E.d_overflow, E.has_elem_map ? E.d_elem_map : nullptr, E.n_cells,
-                            nullptr, E.d_counts));
+        CU(walk_fill(s0, 0, ng, theta_inv2, 0, kWalkCtas, nullptr, E.d_counts));
         E.prof.n_kernel_launch += 1;
         long long nt, np, nb;
         plan_sizes_host(E.grp_n.data(), E.h_counts.data(), ng, U, Us, &nt, &np, &nb);

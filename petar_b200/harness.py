@@ -38,6 +38,8 @@ def lib():
         L.hz_local_boxes.argtypes = [_vp, _vp]
         L.hz_make_let.argtypes = [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp]
         L.hz_free.argtypes = [_vp]
+        L.hz_set_skip_walk.argtypes = [C.c_int]
+        L.hz_walk_group.argtypes = [_vp, C.c_int, C.c_double, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _vp, _vp]
         L.hz_make_plummer.argtypes = [C.c_double, C.c_longlong, C.c_longlong, _vp, _vp, _vp, C.c_double, C.c_uint]
         _h = L
     return _h
@@ -175,6 +177,14 @@ class TreeHandle:
         lib().hz_export_elem_map(self.h, out.ctypes.data)
         return out
 
+    def walk_group(self, g):
+        """(id_epj, id_spj) of group g, walked on the host now (see :func:`skip_walks`): indices into epj_sorted / spj."""
+        ne, ns = C.c_longlong(0), C.c_longlong(0)
+        lib().hz_walk_group(self.h, int(g), self.theta, C.byref(ne), C.byref(ns), None, None)
+        e, s = np.zeros(ne.value, dtype=np.int32), np.zeros(ns.value, dtype=np.int32)
+        lib().hz_walk_group(self.h, int(g), self.theta, C.byref(ne), C.byref(ns), e.ctypes.data if len(e) else None, s.ctypes.data if len(s) else None)
+        return e, s
+
     def timing(self):
         """(seconds building the tree, seconds walking it for all groups) on the host, OpenMP."""
         out = np.zeros(2)
@@ -214,6 +224,12 @@ class TreeHandle:
             self.close()
         except Exception:
             pass
+
+
+def skip_walks(on):
+    """on=True: TreeHandle builds trees and i-groups only, every group's lists stay empty (inputs of the device-side
+    walk at sizes where host lists would not fit, e.g. BASELINE config 5); TreeHandle.walk_group spot-checks then."""
+    lib().hz_set_skip_walk(int(bool(on)))
 
 
 def build_walk_batch(pos, mass, rsearch, vel=None, r_in=None, r_out=None, ids=None, ptype=None, let=None,

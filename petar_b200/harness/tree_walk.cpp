@@ -285,6 +285,15 @@ void node_to_spj(const Node& nd, pb_SPJQuad& s) {
 
 extern "C" {
 
+// hz_set_skip_walk(1): hz_build makes the trees and the i-groups but no interaction lists (for inputs of the
+// device-side walk at sizes where the host lists would not fit: BASELINE config 5); every group's lists are empty.
+static int g_skip_walk = 0;
+void hz_set_skip_walk(int on) { g_skip_walk = on; }
+
+// The lists of ONE group of a tree built by hz_build (for spot checks when the walks were skipped): call with
+// id_ep = id_sp = NULL to learn the lengths first.
+void hz_walk_group(void* h, int g, double theta, long long* n_ep, long long* n_sp, int* id_ep, int* id_sp);
+
 // Build local tree over n_loc local particles, optionally a global tree over local + LET
 // (n_let_ep remote particles, n_let_sp remote superparticles), make i-groups from the local tree
 // and walk the global tree for each.  Returns an opaque handle.
@@ -316,6 +325,7 @@ void* hz_build(int n_loc, const double* pos, const double* mass, const double* r
     const double t_w0 = omp_get_wtime();
 #pragma omp parallel for schedule(dynamic, 4)
     for (int g = 0; g < ng; g++) {
+        if (g_skip_walk) continue;
         le[g].reserve(4096); ls[g].reserve(2048);
         if (!G.nodes.empty()) walk(G, 0, R->groups[g].inner, R->groups[g].outer, theta_inv2, le[g], ls[g]);
     }
@@ -333,6 +343,17 @@ void* hz_build(int n_loc, const double* pos, const double* mass, const double* r
         if (!ls[g].empty()) memcpy(&R->id_spj[(size_t)R->sj_off[g]], ls[g].data(), sizeof(int) * ls[g].size());
     }
     return R;
+}
+
+void hz_walk_group(void* h, int g, double theta, long long* n_ep, long long* n_sp, int* id_ep, int* id_sp) {
+    Result* R = (Result*)h;
+    const Tree& G = R->gt();
+    std::vector<int> le, ls;
+    const double theta_inv2 = theta > 0.0 ? 1.0 / (theta * theta) : 1e300;
+    if (!G.nodes.empty()) walk(G, 0, R->groups[g].inner, R->groups[g].outer, theta_inv2, le, ls);
+    *n_ep = (long long)le.size(); *n_sp = (long long)ls.size();
+    if (id_ep && !le.empty()) memcpy(id_ep, le.data(), sizeof(int) * le.size());
+    if (id_sp && !ls.empty()) memcpy(id_sp, ls.data(), sizeof(int) * ls.size());
 }
 
 // out: [n_epj, n_spj, n_walk, n_epi_total, n_id_epj, n_id_spj, n_nodes, n_let_sp]

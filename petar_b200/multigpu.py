@@ -15,6 +15,7 @@ Which entries go where (the LET *selection*) and the walk lists over local + LET
 the harness (``harness/tree_walk.cpp``) stands in for it, once, outside the timed region.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -165,6 +166,9 @@ class DomainStepper:
         self.host_dw, self.n_dw = {}, 0
         self.send_idx32 = self.send_idx.astype(np.int32)            # LET EP rows as store slots (local particles come first)
         self.L = engine.load()
+        if device:
+            # several ranks share the node's host cores: this rank's own j-particles travel raw and are packed on the GPU
+            engine.set_option("raw_upload", int(os.environ.get("PETAR_B200_RAW_UPLOAD", "1")))
         pin = device
         self.h_send_ep = torch.empty((len(self.send_idx), 8), dtype=torch.float32, pin_memory=pin)
         self.h_send_sp = torch.empty((len(self.send_sp), 16), dtype=torch.float32, pin_memory=pin)

@@ -32,9 +32,15 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session", autouse=True)
 def _native_libs():
     """Build whatever is missing (nvcc / g++ are in the image; seconds).  The GPU box normally gets
-    the prebuilt .so files with the snapshot, so this is a no-op there."""
-    from petar_b200 import build
-    build.build_all()
+    the prebuilt .so files with the snapshot, so this is a no-op there.  Without nvcc and without prebuilt libraries the
+    tests that need them are skipped rather than erroring out of the session."""
+    import shutil
+    from petar_b200 import build, engine
+    have_nvcc = bool(shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"))
+    if have_nvcc:
+        build.build_all()
+    elif not os.path.exists(os.path.join(engine.LIBDIR, "libpetar_b200.so")):
+        pytest.skip("no nvcc and no prebuilt libpetar_b200.so: native tests skipped", allow_module_level=True)
     from oracle import binding
     binding.build()
     yield

@@ -230,3 +230,42 @@ def test_resident_step_with_local_essential_tree():
     fr = engine.tree_force(store, cells, g2, prm["eps"], prm["r_out"], prm["G"], elem_map=emap_store, resident=True)
     assert np.array_equal(fr["n_ngb"], fh["n_ngb"])
     assert np.abs(fr["acc"] - fh["acc"]).max() <= 2e-6 * np.abs(fh["acc"]).max()
+
+
+def test_compact_walk_records_give_identical_lists_in_identical_order():
+    """walk_compact = 1 (default) classifies on 64-byte fp32 records rounded outward and re-checks undecided cells on the
+    fp64 record: the lists must be the legacy all-fp64 walk's lists entry for entry, for a plain tree, for binaries with
+    their tight clumps, far from the origin (large |coordinate| = large fp32 rounding margin) and with a LET tree."""
+    def lists(batch, cells, groups, prm, emap=None):
+        engine.set_option("tree_batch", 1 << 20)
+        try:
+            f = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], elem_map=emap).copy()
+            return f, engine.tree_lists(len(groups))
+        finally:
+            engine.set_option("tree_batch", 256)
+
+    cases = []
+    for kind in ("plummer", "kroupa_binaries"):
+        batch, prm, cells, groups = _case(kind, 20000)
+        cases.append((kind, batch, cells, groups, prm, None))
+    # the same Plummer model pushed far from the origin: |x| ~ 1e3 makes the fp32 margin comparable to small cells
+    mass, pos, vel = hz.make_plummer(20000)
+    prm = hz.petar_auto_params(mass, vel)
+    r_in, r_out, rs = hz.particle_rout_rsearch(mass, vel, prm)
+    far, _ = hz.build_walk_batch(pos + np.array([1.0e3, -2.0e3, 5.0e2]), mass, rs, vel=vel, r_in=r_in, r_out=r_out)
+    c2, g2 = far.tree.export_tree()
+    cases.append(("plummer shifted by 1e3", far, c2, g2, prm, None))
+    lb, lprm = _two_domain_case()
+    lc, lg = lb.tree.export_tree()
+    cases.append(("two domains (LET)", lb, lc, lg, lprm, lb.tree.export_elem_map()))
+    for name, batch, cells, groups, prm, emap in cases:
+        engine.set_option("walk_compact", 0)
+        try:
+            f0, l0 = lists(batch, cells, groups, prm, emap)
+        finally:
+            engine.set_option("walk_compact", 1)
+        f1, l1 = lists(batch, cells, groups, prm, emap)
+        for a, b in zip(l0, l1):
+            assert np.array_equal(a, b), name
+        assert f0.tobytes() == f1.tobytes(), name
+        print(f"[compact walk, {name}] {len(groups)} groups, {int(l1[0].sum())} EP + {int(l1[1].sum())} SP list entries identical")

@@ -64,3 +64,23 @@ def test_field_query_throughput_report():
     print(f"[field query 2e4 points x 1e6 particles] GPU end-to-end {dt * 1e3:.1f} ms = {2e4 * 1e6 / dt * 1e-9:.0f} Ginteractions/s "
           f"(fp64 scalar oracle extrapolated: {dt_cpu:.1f} s); acc err median {np.median(ea):.2e} max {ea.max():.2e}")
     assert np.median(ea) <= 1e-6 and ea.max() <= 1e-4
+
+
+def test_field_query_leaves_the_j_store_unpublished():
+    """pb_field_at_points overwrites the j store with the query's particle set; a dispatch that follows without a fresh
+    pb_upload_j must fail with PB_ERR_PROTOCOL instead of silently running against it."""
+    import ctypes as C
+    from petar_b200.types import EPJSoft
+    batch, _, prm, _ = hz.plummer_case(2000)
+    f0 = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"]).copy()
+    part = np.zeros(len(batch.epj), dtype=EPJSoft)
+    part["pos"], part["mass"] = batch.epj["pos"], batch.epj["mass"]
+    engine.get_gravity_and_potential_at_point(np.zeros(4), np.zeros(4), np.ones(4), part)
+    with pytest.raises(AssertionError):            # the shim aborts on PB_ERR_PROTOCOL; the Python loop driver asserts rc == 0
+        t = batch.pointer_tables(np.zeros(batch.n_epi_total, dtype=engine.ForceSoft))
+        L = engine.load()
+        rc = L.pb_dispatch_index(t.n_walk, t.epi_ptrs.ctypes.data, t.n_epi.ctypes.data, C.byref(engine.LAYOUT_EPI),
+                                 t.id_epj_ptrs.ctypes.data, t.n_epj.ctypes.data, t.id_spj_ptrs.ctypes.data, t.n_spj.ctypes.data)
+        assert rc == 0, L.pb_last_error()
+    f1 = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"])      # publishes j again
+    assert f1.tobytes() == f0.tobytes()

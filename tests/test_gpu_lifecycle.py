@@ -90,3 +90,18 @@ def test_monopole_only_superparticles():
     zq.spj["quad"] = 0.0
     ref = ob.walks_index(zq, prm["eps"], prm["r_out"], prm["G"])
     _tol(f["acc"], f["pot"], ref)
+
+
+def test_raw_upload_equals_host_packing():
+    """Option raw_upload: the caller's j arrays are page-locked, copied as they are and packed on the device — the forces
+    must be bit-identical to the host-packed path (same fp64 -> hi/lo fp32 arithmetic, no FMA contraction on the device)."""
+    batch, _, prm, _ = hz.kroupa_binary_case(6000)
+    f0 = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"]).copy()
+    engine.set_option("raw_upload", 1)
+    try:
+        f1 = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"]).copy()
+        moved = type(batch)(batch.epj.copy(), batch.spj.copy(), batch.epi, batch.i_off, batch.id_epj, batch.ej_off, batch.id_spj, batch.sj_off)
+        f2 = engine.calc_force_all_and_write_back(moved, prm["eps"], prm["r_out"], prm["G"]).copy()      # other host arrays: re-registered
+    finally:
+        engine.set_option("raw_upload", 0)
+    assert f1.tobytes() == f0.tobytes() and f2.tobytes() == f0.tobytes()

@@ -411,3 +411,34 @@ def test_kroupa_binaries_with_artificial_particles():
     nbad = count_mismatch_report(batch, f, ref, "Kroupa + binaries")
     assert nbad <= 1e-4 * len(f)
     assert f["n_ngb"].max() >= 14          # members + artificial particles of a binary see each other
+
+
+def test_config4_all_binaries():
+    """BASELINE configs[3] / [4] shape (100 % primordial binaries): every star is a binary member, so the soft tree sees 7
+    particles per star — per binary 2 zero-mass members, 8 zero-mass probes, 1 zero-mass c.m. and 3 massive type-0
+    orbit samples (N = 2e4 stars -> 1.4e5 tree particles, none of them an ordinary single).  Kernel level against the
+    NoSimd oracle (coords = 0, this module's fixture), then the library default (coords = 2) on the corrected force,
+    through the functor path and through the device-resident tree step."""
+    from oracle.dropin_check import DropinChecker
+    batch, epi_src, prm, P = hz.kroupa_binary_case(20000, f_bin=1.0)
+    n_bin = P["n_bin"]
+    assert n_bin == 10000 and len(P["mass"]) == 14 * n_bin and (P["mass"] > 0).sum() == 3 * n_bin
+    ref = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"])
+    f = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"])
+    check_tol(f, ref, "config 4 shape: 100 % binaries, N=2e4 stars")
+    assert count_mismatch_report(batch, f, ref, "100 % binaries") <= 1e-4 * len(f)
+    assert f["n_ngb"].min() >= 14                     # everybody sits in a clump of 14
+    chk = DropinChecker(P, prm, subset=epi_src)
+    cells, groups = batch.tree.export_tree()
+    engine.set_option("coords", 2)
+    try:
+        f2 = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"]).copy()
+        f3 = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], resident=True).copy()
+    finally:
+        engine.set_option("coords", 0)
+    for name, g in (("functors", f2), ("resident tree step", f3)):
+        rep = chk.compare(g, ref)
+        print(f"[config 4 shape, drop-in, {name}] {rep}")
+        assert rep["acc_rel_err"]["median"] <= 1e-6 and rep["acc_rel_err"]["p99"] <= 1e-5 and rep["acc_rel_err"]["max"] <= 1e-3
+        assert rep["pot_tot_rel_err"]["median"] <= 1e-6 and rep["pot_tot_rel_err"]["max"] <= 1e-4
+        assert np.array_equal(g["n_ngb"], ref["n_ngb"])
