@@ -145,6 +145,11 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "min_slot_work"  a dispatch is not cut into per-stream sub-batches smaller than this many EP-equivalent
  *                interactions (n_epi * (n_epj + 2 n_spj)); default 0 = always "streams" (measured: 4e7 saves enqueue time
  *                at 8 ranks per node but costs more pipelining than it saves at 4).
+ *   "ep_runs"    1 (default): pb_dispatch_index / pb_dispatch_count_index ship every walk's EP index list as maximal runs of
+ *                consecutive indices, (start, length) pairs found in one pass over the list, and a small kernel writes the
+ *                indices back out on the device — FDPS's EP lists are leaf cells in Morton order (~20 indices per run at
+ *                N = 1e6: 8 B per run instead of 4 B per index); forces are bit-identical.  SP lists (tree cell numbers, ~1.6
+ *                per run in depth-first numbering) stay plain indices.  0: EP lists are copied as they are.
  *   "raw_upload" 1: pb_upload_j / pb_upload_j_range page-lock the caller's arrays once (cudaHostRegister), copy them as they
  *                are and pack them on the device (bit-identical to the host packing) — for several ranks per node, where the
  *                host cores (4 per rank on an 8-GPU box) are scarcer than PCIe bandwidth: 2.7 -> 0.3 ms of host time per

@@ -73,6 +73,8 @@ struct Plan {                // layout of one sub-batch inside an arena
     size_t off_lepj = 0, off_lspj = 0, bytes = 0;
     int    count_only = 0;                    // neighbour search only: EP lists as kind-2 tasks, no SP, eps2 = 0
     int    coords = 0, i_f4 = 2;              // option "coords" the sub-batch was packed for; float4 per packed i-particle
+    size_t n_runs = 0, n_idx = 0;             // EP lists as runs: (start, length) pairs in the arena; n_idx entries after expansion on the device
+    size_t off_runtab = 0;                    // per walk {first run, number of runs} (int2)
     const int* ext_ide = nullptr;             // index lists living outside the arena (built on the device for the whole step)
     const int* ext_ids = nullptr;
 };
@@ -94,10 +96,12 @@ struct Slot {
     bool emit = false; int i_base = 0;
     size_t n_pairs_window = 0;         // entries of d_pairs this sub-batch may use (cleared, written, sorted): <= cap_pairs
     long long j_epoch = -1;            // the j publication this stream has already been ordered after
+    int* d_ide_x = nullptr; size_t cap_ide_x = 0;   // EP index lists of the sub-batch, expanded on the device from the runs
 };
 
 struct Recorded {
     char* d_arena = nullptr;
+    int*  d_ide_x = nullptr;     // its own copy of the expanded EP lists (the slot's buffer is reused by later dispatches)
     Plan  plan;
     bool  direct = false;
     int   slot = 0;              // the stream slot the dispatch ran on
@@ -151,6 +155,7 @@ struct Engine {
     bool spec_pending = false; int2* d_tree_caps = nullptr; size_t cap_tree_caps = 0;
     int opt_walk_ctas = 148 * 16;                          // CTAs (4 warps each, one warp per i-group at a time) of the tree-walk launches
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
+    int opt_ep_runs = 1;                                   // EP index lists cross PCIe as (start, length) runs and are expanded on the device
     int opt_walk_compact = 1;                              // tree walk classifies on 64-B fp32 records first (exact fp64 re-check when undecided)
     void* d_cellA = nullptr; void* d_cellB = nullptr; size_t cap_cellAB = 0; double coord_max = 0.0;
     int opt_raw_upload = 0;                                // pb_upload_j_range copies the caller's arrays as they are and packs them on the device
@@ -378,6 +383,9 @@ struct HostPlan {
     std::vector<Task>   tasks;
     std::vector<IBlock> iblocks;
     std::vector<size_t> lepj_off, lspj_off;   // direct mode: first local j of each walk
+    bool use_runs = false;                    // index mode: the EP lists travel run-length coded
+    std::vector<std::vector<int2>> runs;      // per walk: maximal runs of consecutive indices, in list order
+    std::vector<int2> runtab;                 // per walk {first run, number of runs}
 };
 
 void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active, HostPlan& hp, const int2* ext_off = nullptr) {
@@ -385,8 +393,9 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     hp.tasks.clear(); hp.iblocks.clear();
     hp.lepj_off.assign(n_walk, 0); hp.lspj_off.assign(n_walk, 0);
     std::vector<Group> groups;
-    size_t i_off = 0, ide = 0, ids = 0, lepj = 0, lspj = 0;
+    size_t i_off = 0, ide = 0, ids = 0, lepj = 0, lspj = 0, n_runs = 0;
     double work = 0.0;                                   // warp-steps: sum nib * (nej + 2 nsj)
+    if (hp.use_runs) hp.runtab.assign(n_walk, make_int2(0, 0));
     for (int w = 0; w < n_walk; w++) {
         Walk& W = hp.walks[w];
         W.i_off = (int)i_off; W.ni = win[w].ni;
@@ -399,6 +408,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
         W.hx = W.hy = W.hz = INFINITY; W.rsi2max = 0.f;
         i_off += (size_t)win[w].ni;
         if (!dense && !ext_off) ide += align_up((size_t)win[w].nej, 4);
+        if (hp.use_runs) { hp.runtab[w] = make_int2((int)n_runs, dense ? 0 : (int)hp.runs[w].size()); n_runs += dense ? 0 : hp.runs[w].size(); }
         if (!ext_off) ids += align_up((size_t)win[w].nsj, 4);
         if (direct) {
             hp.lepj_off[w] = lepj; hp.lspj_off[w] = lspj;
@@ -468,10 +478,13 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     p.i_f4 = (E.opt_coords == 2 && !E.count_only) ? 3 : 2;
     p.n_walk = n_walk; p.n_tasks = (int)hp.tasks.size(); p.n_iblocks = (int)hp.iblocks.size();
     p.n_i = i_off; p.n_ide = ide; p.n_ids = ids; p.n_part = part; p.n_lepj = lepj; p.n_lspj = lspj;
+    p.n_runs = 0; p.n_idx = 0;
+    if (hp.use_runs) { p.n_runs = n_runs; p.n_idx = ide; p.n_ide = 2 * n_runs; }      // the arena carries the runs, not the indices
     size_t o = 0;
     p.off_walks = o;   o = align_up(o + sizeof(Walk) * n_walk, 256);
     p.off_tasks = o;   o = align_up(o + sizeof(Task) * p.n_tasks, 256);
     p.off_iblocks = o; o = align_up(o + sizeof(IBlock) * p.n_iblocks, 256);
+    p.off_runtab = o;  o = align_up(o + (hp.use_runs ? sizeof(int2) * (size_t)n_walk : 0), 256);
     p.off_epi = o;     o = align_up(o + (size_t)p.i_f4 * sizeof(float4) * p.n_i, 256);
     p.off_ide = o;     o = align_up(o + sizeof(int) * p.n_ide, 256);
     p.off_ids = o;     o = align_up(o + sizeof(int) * p.n_ids, 256);
@@ -537,7 +550,9 @@ void pack_walk(const WalkIn* win, bool direct, const pb_layout_epi& Li, HostPlan
     const float rnear = std::max(rsmax, rprec);
     W.rsi2max = rnear * rnear;
     if (!direct) {
-        if (W.nej && W.ej_off >= 0 && win[w].ide != &g_devlist_marker) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
+        if (hp.use_runs) {
+            if (!hp.runs[w].empty()) memcpy(reinterpret_cast<int2*>(ide) + hp.runtab[w].x, hp.runs[w].data(), sizeof(int2) * hp.runs[w].size());
+        } else if (W.nej && W.ej_off >= 0 && win[w].ide != &g_devlist_marker) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
         if (W.nsj && win[w].ids != &g_devlist_marker) memcpy(ids + W.sj_off, win[w].ids, sizeof(int) * (size_t)W.nsj);
     } else {
         const size_t e0 = hp.lepj_off[w], s0 = hp.lspj_off[w];
@@ -561,6 +576,7 @@ void pack_tail(const WalkIn* win, bool direct, const pb_layout_epj* Lj, const pb
     memcpy(arena + p.off_walks, hp.walks.data(), sizeof(Walk) * hp.walks.size());
     memcpy(arena + p.off_tasks, hp.tasks.data(), sizeof(Task) * hp.tasks.size());
     memcpy(arena + p.off_iblocks, hp.iblocks.data(), sizeof(IBlock) * hp.iblocks.size());
+    if (hp.use_runs) memcpy(arena + p.off_runtab, hp.runtab.data(), sizeof(int2) * hp.runtab.size());
 }
 
 // fill the pinned arena of one sub-batch
@@ -680,6 +696,31 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         S.w_begin = cut[s]; S.w_end = cut[s + 1];
         S.active = S.w_end > S.w_begin;
     }
+    // EP lists as runs of consecutive indices (FDPS lists are leaf cells in Morton order): one pass over the lists finds
+    // them — the only time the host reads the EP indices — and only the runs are packed and copied
+    const bool use_runs = !direct && E.opt_ep_runs;
+    for (int s = 0; s < n_slots; s++) {
+        hp[s].use_runs = use_runs;
+        if (use_runs && E.slots[s].active && (int)hp[s].runs.size() < E.slots[s].w_end - E.slots[s].w_begin) hp[s].runs.resize(E.slots[s].w_end - E.slots[s].w_begin);
+    }
+    if (use_runs) {
+        std::vector<int> slot_of(n_walk);
+        for (int s = 0; s < n_slots; s++) for (int w = cut[s]; w < cut[s + 1]; w++) slot_of[w] = s;
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int w = 0; w < n_walk; w++) {
+            std::vector<int2>& R = hp[slot_of[w]].runs[w - cut[slot_of[w]]];
+            R.clear();
+            const int* id = win[w].ide;
+            const int n = win[w].nej;
+            if (!id || n <= 0) continue;
+            int start = id[0], len = 1;
+            for (int k = 1; k < n; k++) {
+                if (id[k] == start + len) len++;
+                else { R.push_back(make_int2(start, len)); start = id[k]; len = 1; }
+            }
+            R.push_back(make_int2(start, len));
+        }
+    }
 #pragma omp parallel for schedule(static, 1)      // same team size as the packing loops: no team re-creation
     for (int s = 0; s < n_slots; s++) {
         const Slot& S = E.slots[s];
@@ -725,6 +766,20 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
             CU(cudaMemsetAsync(S.d_pairs, 0xff, sizeof(unsigned long long) * S.n_pairs_window, S.stream));
         }
         i_base_next += (int)S.plan.n_i;
+        if (hp[s].use_runs) {
+            if (S.plan.n_idx > S.cap_ide_x) {
+                CU(cudaStreamSynchronize(S.stream));
+                if (S.d_ide_x) CU(cudaFree(S.d_ide_x));
+                S.d_ide_x = nullptr; S.cap_ide_x = 0;
+                const size_t cap = align_up(S.plan.n_idx + S.plan.n_idx / 2, 4096);
+                CU(cudaMalloc(&S.d_ide_x, sizeof(int) * cap));
+                S.cap_ide_x = cap;
+            }
+            CU(launch_expand_runs(S.stream, (const int2*)(S.d_arena + S.plan.off_runtab), (const int2*)(S.d_arena + S.plan.off_ide),
+                                  (const Walk*)(S.d_arena + S.plan.off_walks), S.plan.n_walk, S.d_ide_x));
+            S.plan.ext_ide = S.d_ide_x;
+            E.prof.n_kernel_launch += 1;
+        }
         CU(launch_plan(S.stream, S.plan, S.d_arena, direct, S.d_part4, S.d_partn, S.d_out, false, S.emit ? &S : nullptr));
         CU(cudaEventRecord(S.ev[2], S.stream));
         if (s == last_active) CU(cudaEventRecord(E.ev_end[E.end_cur], S.stream));
@@ -743,6 +798,11 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
             r.plan = S.plan; r.direct = direct; r.slot = s;
             CU(cudaMalloc(&r.d_arena, S.plan.bytes));
             CU(cudaMemcpyAsync(r.d_arena, S.d_arena, S.plan.bytes, cudaMemcpyDeviceToDevice, S.stream));
+            if (S.plan.ext_ide && S.plan.n_idx) {              // the expanded EP lists stay with the recording
+                CU(cudaMalloc(&r.d_ide_x, sizeof(int) * S.plan.n_idx));
+                CU(cudaMemcpyAsync(r.d_ide_x, S.d_ide_x, sizeof(int) * S.plan.n_idx, cudaMemcpyDeviceToDevice, S.stream));
+                r.plan.ext_ide = r.d_ide_x;
+            }
             E.recs.push_back(r);
         }
         t_enq += now_s() - t1;
@@ -866,7 +926,7 @@ int pb_init(int my_rank, int device) {
 void pb_finalize(void) {
     if (!E.inited) return;
     cudaDeviceSynchronize();
-    for (auto& r : E.recs) cudaFree(r.d_arena);
+    for (auto& r : E.recs) { cudaFree(r.d_arena); cudaFree(r.d_ide_x); }
     E.recs.clear();
     for (int s = 0; s < kMaxStreams; s++) {
         Slot& S = E.slots[s];
@@ -874,7 +934,7 @@ void pb_finalize(void) {
         cudaFreeHost(S.h_out); cudaFree(S.d_out);
         cudaFree(S.d_part4); cudaFree(S.d_partn);
         cudaFree(S.d_pairs); cudaFree(S.d_pairs_sorted); cudaFreeHost(S.h_pairs);
-        cudaFree(S.d_cursor); cudaFreeHost(S.h_cursor); cudaFree(S.d_cubtmp);
+        cudaFree(S.d_cursor); cudaFreeHost(S.h_cursor); cudaFree(S.d_cubtmp); cudaFree(S.d_ide_x);
         for (int k = 0; k < 4; k++) cudaEventDestroy(S.ev[k]);
         cudaStreamDestroy(S.stream);
         S = Slot();
@@ -923,6 +983,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "tree_streams")) { if (v < 1 || v > kMaxStreams) return fail(PB_ERR_ARG, "tree_streams must be in [1, %d]", kMaxStreams); E.opt_tree_streams = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_spec")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "tree_spec must be 0 or 1"); E.opt_tree_spec = (int)v; return PB_OK; }
     if (!strcmp(key, "walk_ctas")) { if (v < 1 || v > 148 * 16) return fail(PB_ERR_ARG, "walk_ctas must be in [1, 2368]"); E.opt_walk_ctas = (int)v; return PB_OK; }
+    if (!strcmp(key, "ep_runs")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "ep_runs must be 0 or 1"); E.opt_ep_runs = (int)v; return PB_OK; }
     if (!strcmp(key, "walk_compact")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "walk_compact must be 0 or 1"); E.opt_walk_compact = (int)v; return PB_OK; }
     if (!strcmp(key, "raw_upload")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "raw_upload must be 0 or 1"); E.opt_raw_upload = (int)v; return PB_OK; }
     if (!strcmp(key, "ws")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "ws must be 0 or 1"); E.opt_ws = (int)v; return PB_OK; }
@@ -941,7 +1002,7 @@ int pb_get_option(const char* key, long long* v) {
         {"coords", E.opt_coords}, {"streams", E.opt_streams}, {"jchunk", E.opt_jchunk}, {"cull", E.opt_cull},
         {"tree_fill", E.opt_tree_fill}, {"min_slot_work", E.opt_min_slot_work}, {"tree_streams", E.opt_tree_streams},
         {"tree_spec", E.opt_tree_spec}, {"walk_ctas", E.opt_walk_ctas}, {"nb_lists", E.opt_nb_lists},
-        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"ws", E.opt_ws}, {"raw_upload", E.opt_raw_upload}, {"walk_compact", E.opt_walk_compact}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
+        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"ws", E.opt_ws}, {"raw_upload", E.opt_raw_upload}, {"walk_compact", E.opt_walk_compact}, {"ep_runs", E.opt_ep_runs}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
     for (const auto& t : tab)
         if (!strcmp(key, t.k)) { *v = t.val; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_get_option: unknown key '%s'", key);
@@ -2052,7 +2113,7 @@ int pb_record_begin(void) {
     int rc = ensure_init();
     if (rc != PB_OK) return rc;
     CU(cudaDeviceSynchronize());
-    for (auto& r : E.recs) CU(cudaFree(r.d_arena));
+    for (auto& r : E.recs) { CU(cudaFree(r.d_arena)); if (r.d_ide_x) CU(cudaFree(r.d_ide_x)); }
     E.recs.clear();
     E.recording = true;
     return PB_OK;

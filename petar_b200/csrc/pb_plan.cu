@@ -240,6 +240,43 @@ cudaError_t launch_gather_epj(cudaStream_t s, const float4* epj, const int* idx,
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// EP index lists that crossed PCIe as runs (start, length): one warp per walk writes the indices back out, in list
+// order, where the force kernel reads them (FDPS's EP lists are leaf cells in Morton order: ~20 consecutive indices
+// per run, so 8 B per run instead of 4 B per index)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+expand_runs_kernel(const int2* __restrict__ runtab, const int2* __restrict__ runs, const Walk* __restrict__ walks, int n_walk, int* __restrict__ out) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_walk) return;
+    const int2 rt = runtab[w];
+    const int ej = walks[w].ej_off;
+    if (ej < 0) return;                                   // dense walk: no list
+    int* o = out + ej;
+    int pos = 0;
+    for (int base = 0; base < rt.y; base += 32) {
+        int2 r = make_int2(0, 0);
+        if (base + lane < rt.y) r = runs[rt.x + base + lane];
+        int incl = r.y;                                   // inclusive scan of the run lengths
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        const int nrun = min(32, rt.y - base);
+        for (int k = 0; k < nrun; k++) {                  // one run after the other, the warp writes each run coalesced
+            const int st = __shfl_sync(0xffffffffu, r.x, k), ln = __shfl_sync(0xffffffffu, r.y, k);
+            const int at = pos + __shfl_sync(0xffffffffu, incl, k) - ln;
+            for (int q = lane; q < ln; q += 32) o[at + q] = st + q;
+        }
+        pos += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+cudaError_t launch_expand_runs(cudaStream_t s, const int2* runtab, const int2* runs, const Walk* walks, int n_walk, int* out) {
+    if (n_walk <= 0) return cudaSuccess;
+    expand_runs_kernel<<<(n_walk + 3) / 4, 128, 0, s>>>(runtab, runs, walks, n_walk, out);
+    return cudaGetLastError();
+}
+
 // host mirror of plan_group, for sizing the task / partial-sum buffers when the list lengths are known on the host
 void plan_sizes_host(const int* ni, const int2* counts, int n_groups, int U, int Us, long long* n_tasks, long long* n_part, long long* n_iblk) {
     long long t = 0, p = 0, b = 0;

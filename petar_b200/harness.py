@@ -34,6 +34,7 @@ def lib():
         L.hz_export.argtypes = [_vp] * 9
         L.hz_export_let_sp_src.argtypes = [_vp, _vp]
         L.hz_export_tree.argtypes = [_vp, _vp, _vp]
+        L.hz_export_elem_map.argtypes = [_vp, _vp]
         L.hz_timing.argtypes = [_vp, _vp]
         L.hz_local_boxes.argtypes = [_vp, _vp]
         L.hz_make_let.argtypes = [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp]
