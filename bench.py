@@ -62,12 +62,13 @@ def measured_peaks():
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per force-kernel launch from the committed ncu
     --set full capture (it cannot be measured inside a timed run); None if no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1_force_kernel_traffic.json")
-    try:
-        with open(p) as f:
-            return json.load(f)["dram_bytes_per_launch"]
-    except (OSError, KeyError, ValueError):
-        return None
+    for name in ("r2_force_kernel_traffic.json", "r1_force_kernel_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)["dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 class ClockSampler:

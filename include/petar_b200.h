@@ -145,11 +145,15 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "min_slot_work"  a dispatch is not cut into per-stream sub-batches smaller than this many EP-equivalent
  *                interactions (n_epi * (n_epj + 2 n_spj)); default 0 = always "streams" (measured: 4e7 saves enqueue time
  *                at 8 ranks per node but costs more pipelining than it saves at 4).
- *   "ep_runs"    1 (default): pb_dispatch_index / pb_dispatch_count_index ship every walk's EP index list as maximal runs of
- *                consecutive indices, (start, length) pairs found in one pass over the list, and a small kernel writes the
+ *   "ep_runs"    1: pb_dispatch_index / pb_dispatch_count_index ship every walk's EP index list as maximal runs of
+ *                consecutive indices, (start, length) pairs found while the walk is packed, and a small kernel writes the
  *                indices back out on the device — FDPS's EP lists are leaf cells in Morton order (~20 indices per run at
  *                N = 1e6: 8 B per run instead of 4 B per index); forces are bit-identical.  SP lists (tree cell numbers, ~1.6
- *                per run in depth-first numbering) stay plain indices.  0: EP lists are copied as they are.
+ *                per run in depth-first numbering) stay plain indices.  0 (default): EP lists are copied as they are —
+ *                measured at N = 1e6 the runs cut the H2D volume of a tree step from 0.76 to 0.57 GB but make the step 3.8 ms
+ *                SLOWER (47.0 vs 43.2 ms): the PCIe time saved was hidden under the kernels anyway, while the extra
+ *                expansion launch per stream and dispatch (448 per step) sits on the critical path of the tag_max = 1
+ *                protocol.  The device-resident tree step removes the lists altogether instead.
  *   "raw_upload" 1: pb_upload_j / pb_upload_j_range page-lock the caller's arrays once (cudaHostRegister), copy them as they
  *                are and pack them on the device (bit-identical to the host packing) — for several ranks per node, where the
  *                host cores (4 per rank on an 8-GPU box) are scarcer than PCIe bandwidth: 2.7 -> 0.3 ms of host time per

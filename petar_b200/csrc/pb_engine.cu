@@ -155,7 +155,7 @@ struct Engine {
     bool spec_pending = false; int2* d_tree_caps = nullptr; size_t cap_tree_caps = 0;
     int opt_walk_ctas = 148 * 16;                          // CTAs (4 warps each, one warp per i-group at a time) of the tree-walk launches
     int opt_nb_lists = 0;                                  // count-only dispatches also return the neighbour pairs
-    int opt_ep_runs = 1;                                   // EP index lists cross PCIe as (start, length) runs and are expanded on the device
+    int opt_ep_runs = 0;                                   // 1: EP index lists cross PCIe as (start, length) runs and are expanded on the device (measured: does not pay)
     int opt_walk_compact = 1;                              // tree walk classifies on 64-B fp32 records first (exact fp64 re-check when undecided)
     void* d_cellA = nullptr; void* d_cellB = nullptr; size_t cap_cellAB = 0; double coord_max = 0.0;
     int opt_raw_upload = 0;                                // pb_upload_j_range copies the caller's arrays as they are and packs them on the device
@@ -384,7 +384,7 @@ struct HostPlan {
     std::vector<IBlock> iblocks;
     std::vector<size_t> lepj_off, lspj_off;   // direct mode: first local j of each walk
     bool use_runs = false;                    // index mode: the EP lists travel run-length coded
-    std::vector<std::vector<int2>> runs;      // per walk: maximal runs of consecutive indices, in list order
+    long long run_cursor = 0;                 // runs appended so far to the arena's run section (walks are packed concurrently: atomic adds)
     std::vector<int2> runtab;                 // per walk {first run, number of runs}
 };
 
@@ -393,9 +393,9 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     hp.tasks.clear(); hp.iblocks.clear();
     hp.lepj_off.assign(n_walk, 0); hp.lspj_off.assign(n_walk, 0);
     std::vector<Group> groups;
-    size_t i_off = 0, ide = 0, ids = 0, lepj = 0, lspj = 0, n_runs = 0;
+    size_t i_off = 0, ide = 0, ids = 0, lepj = 0, lspj = 0;
     double work = 0.0;                                   // warp-steps: sum nib * (nej + 2 nsj)
-    if (hp.use_runs) hp.runtab.assign(n_walk, make_int2(0, 0));
+    if (hp.use_runs) { hp.runtab.assign(n_walk, make_int2(0, 0)); hp.run_cursor = 0; }
     for (int w = 0; w < n_walk; w++) {
         Walk& W = hp.walks[w];
         W.i_off = (int)i_off; W.ni = win[w].ni;
@@ -408,7 +408,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
         W.hx = W.hy = W.hz = INFINITY; W.rsi2max = 0.f;
         i_off += (size_t)win[w].ni;
         if (!dense && !ext_off) ide += align_up((size_t)win[w].nej, 4);
-        if (hp.use_runs) { hp.runtab[w] = make_int2((int)n_runs, dense ? 0 : (int)hp.runs[w].size()); n_runs += dense ? 0 : hp.runs[w].size(); }
+
         if (!ext_off) ids += align_up((size_t)win[w].nsj, 4);
         if (direct) {
             hp.lepj_off[w] = lepj; hp.lspj_off[w] = lspj;
@@ -479,7 +479,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     p.n_walk = n_walk; p.n_tasks = (int)hp.tasks.size(); p.n_iblocks = (int)hp.iblocks.size();
     p.n_i = i_off; p.n_ide = ide; p.n_ids = ids; p.n_part = part; p.n_lepj = lepj; p.n_lspj = lspj;
     p.n_runs = 0; p.n_idx = 0;
-    if (hp.use_runs) { p.n_runs = n_runs; p.n_idx = ide; p.n_ide = 2 * n_runs; }      // the arena carries the runs, not the indices
+    if (hp.use_runs) { p.n_idx = ide; p.n_ide = 0; }      // the arena carries the runs (appended while packing, at its end), not the indices
     size_t o = 0;
     p.off_walks = o;   o = align_up(o + sizeof(Walk) * n_walk, 256);
     p.off_tasks = o;   o = align_up(o + sizeof(Task) * p.n_tasks, 256);
@@ -491,6 +491,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     p.off_lepj = o;    o = align_up(o + (size_t)PB_EPJ_DEV_BYTES * p.n_lepj, 256);
     p.off_lspj = o;    o = align_up(o + (size_t)PB_SPJ_DEV_BYTES * p.n_lspj, 256);
     p.bytes = o;
+    if (hp.use_runs) { p.off_ide = o; p.bytes = o + sizeof(int2) * p.n_idx; }   // capacity; the copy ends after the runs actually found
 }
 
 // one walk of a sub-batch into its pinned arena: i-particles relative to the walk origin, index lists
@@ -551,7 +552,23 @@ void pack_walk(const WalkIn* win, bool direct, const pb_layout_epi& Li, HostPlan
     W.rsi2max = rnear * rnear;
     if (!direct) {
         if (hp.use_runs) {
-            if (!hp.runs[w].empty()) memcpy(reinterpret_cast<int2*>(ide) + hp.runtab[w].x, hp.runs[w].data(), sizeof(int2) * hp.runs[w].size());
+            // maximal runs of consecutive indices (FDPS lists are leaf cells in Morton order), found in the one pass the
+            // host makes over the list; appended to the arena's run section wherever the cursor stands
+            static thread_local std::vector<int2> R;
+            R.clear();
+            const int* id = win[w].ide;
+            const int n = W.nej;
+            if (id && n > 0 && W.ej_off >= 0) {
+                int start = id[0], len = 1;
+                for (int k = 1; k < n; k++) {
+                    if (id[k] == start + len) len++;
+                    else { R.push_back(make_int2(start, len)); start = id[k]; len = 1; }
+                }
+                R.push_back(make_int2(start, len));
+            }
+            const long long at = __atomic_fetch_add(&hp.run_cursor, (long long)R.size(), __ATOMIC_RELAXED);
+            hp.runtab[w] = make_int2((int)at, (int)R.size());
+            if (!R.empty()) memcpy(reinterpret_cast<int2*>(arena + p.off_ide) + at, R.data(), sizeof(int2) * R.size());
         } else if (W.nej && W.ej_off >= 0 && win[w].ide != &g_devlist_marker) memcpy(ide + W.ej_off, win[w].ide, sizeof(int) * (size_t)W.nej);
         if (W.nsj && win[w].ids != &g_devlist_marker) memcpy(ids + W.sj_off, win[w].ids, sizeof(int) * (size_t)W.nsj);
     } else {
@@ -699,28 +716,7 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
     // EP lists as runs of consecutive indices (FDPS lists are leaf cells in Morton order): one pass over the lists finds
     // them — the only time the host reads the EP indices — and only the runs are packed and copied
     const bool use_runs = !direct && E.opt_ep_runs;
-    for (int s = 0; s < n_slots; s++) {
-        hp[s].use_runs = use_runs;
-        if (use_runs && E.slots[s].active && (int)hp[s].runs.size() < E.slots[s].w_end - E.slots[s].w_begin) hp[s].runs.resize(E.slots[s].w_end - E.slots[s].w_begin);
-    }
-    if (use_runs) {
-        std::vector<int> slot_of(n_walk);
-        for (int s = 0; s < n_slots; s++) for (int w = cut[s]; w < cut[s + 1]; w++) slot_of[w] = s;
-#pragma omp parallel for schedule(dynamic, 4)
-        for (int w = 0; w < n_walk; w++) {
-            std::vector<int2>& R = hp[slot_of[w]].runs[w - cut[slot_of[w]]];
-            R.clear();
-            const int* id = win[w].ide;
-            const int n = win[w].nej;
-            if (!id || n <= 0) continue;
-            int start = id[0], len = 1;
-            for (int k = 1; k < n; k++) {
-                if (id[k] == start + len) len++;
-                else { R.push_back(make_int2(start, len)); start = id[k]; len = 1; }
-            }
-            R.push_back(make_int2(start, len));
-        }
-    }
+    for (int s = 0; s < n_slots; s++) hp[s].use_runs = use_runs;
 #pragma omp parallel for schedule(static, 1)      // same team size as the packing loops: no team re-creation
     for (int s = 0; s < n_slots; s++) {
         const Slot& S = E.slots[s];
@@ -753,6 +749,10 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
         Slot& S = E.slots[s];
         const double t1 = now_s();
         S.plan = hp[s].p;
+        if (hp[s].use_runs) {
+            S.plan.n_runs = (size_t)__atomic_load_n(&hp[s].run_cursor, __ATOMIC_ACQUIRE);
+            S.plan.bytes = S.plan.off_ide + sizeof(int2) * S.plan.n_runs;
+        }
         if (!direct && S.j_epoch != E.j_epoch) {          // once per stream and j publication
             CU(cudaStreamWaitEvent(S.stream, E.ev_j_ready, 0));
             S.j_epoch = E.j_epoch;

@@ -261,12 +261,8 @@ expand_runs_kernel(const int2* __restrict__ runtab, const int2* __restrict__ run
         int incl = r.y;                                   // inclusive scan of the run lengths
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-        const int nrun = min(32, rt.y - base);
-        for (int k = 0; k < nrun; k++) {                  // one run after the other, the warp writes each run coalesced
-            const int st = __shfl_sync(0xffffffffu, r.x, k), ln = __shfl_sync(0xffffffffu, r.y, k);
-            const int at = pos + __shfl_sync(0xffffffffu, incl, k) - ln;
-            for (int q = lane; q < ln; q += 32) o[at + q] = st + q;
-        }
+        int* dst = o + pos + incl - r.y;                  // every lane writes out its own run
+        for (int q = 0; q < r.y; q++) dst[q] = r.x + q;
         pos += __shfl_sync(0xffffffffu, incl, 31);
     }
 }

@@ -108,7 +108,7 @@ def test_raw_upload_equals_host_packing():
 
 
 def test_ep_lists_as_runs_are_bitwise_equivalent():
-    """Option ep_runs (default 1): the EP index lists cross PCIe as (start, length) runs and are expanded on the device;
+    """Option ep_runs (opt-in): the EP index lists cross PCIe as (start, length) runs and are expanded on the device;
     forces, potentials and counts must equal the plain-index path bit for bit — also for lists without any run
     (shuffled j store: every run has length 1), for the neighbour search, and in the device-resident replay."""
     batch, _, prm, _ = hz.kroupa_binary_case(6000)
@@ -127,7 +127,7 @@ def test_ep_lists_as_runs_are_bitwise_equivalent():
             c = engine.tree_neighbor_search(batch, n_walk_limit=16).copy()
             out[runs] = (a, b, c, h2d)
         finally:
-            engine.set_option("ep_runs", 1)
+            engine.set_option("ep_runs", 0)
     for k in range(3):
         assert out[1][k].tobytes() == out[0][k].tobytes()
     assert out[1][3] < 0.8 * out[0][3]                     # fewer bytes cross PCIe
@@ -135,10 +135,12 @@ def test_ep_lists_as_runs_are_bitwise_equivalent():
     assert np.array_equal(out[1][0]["n_ngb"], ref["n_ngb"])
     # recorded dispatches keep their own expanded lists
     L = engine.load()
+    engine.set_option("ep_runs", 1)
     engine.check(L.pb_record_begin(), "record")
     engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G"], n_walk_limit=16)
     engine.check(L.pb_record_end(), "record")
     engine.calc_force_all_and_write_back(shuffled, prm["eps"], prm["r_out"], prm["G"], n_walk_limit=16)      # overwrites the slots' buffers
     ms = C.c_float(0)
     engine.check(L.pb_replay(2, C.byref(ms), None), "replay")
+    engine.set_option("ep_runs", 0)
     assert ms.value > 0
