@@ -160,8 +160,12 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *                tree step at 8 ranks.  The arrays must then stay unchanged until the step's forces are back.  0 (default):
  *                packed on the host into pinned staging; the arrays are consumed when the call returns.
  *   "ws"         1 (default): persistent force launches (the device-resident tree step) run the warp-specialised kernel —
- *                8 compute warps that only wait for tiles and run the pair loops, 1 producer warp that fetches tasks and
- *                stages j tiles four deep (pb_kernels_ws.cu); 0: every warp stages and computes (pb::force_kernel).
+ *                8 compute warps that only wait for tiles and run the pair loops, 2 producer warps that fetch tasks and
+ *                stage j tiles four deep (pb_kernels_ws.cu); 0: every warp stages and computes (pb::force_kernel).
+ *   "sp2i"       1 (default): EP-SP tasks of i-groups with at least two 32-particle blocks keep TWO i-particles per lane, so
+ *                every superparticle pair read from shared memory serves four interactions (+6 % on the SP loop, -3.6 %
+ *                kernel time per tree step); 0: one i-particle per lane everywhere.  Sums differ from sp2i = 0 only in
+ *                the order in which a block's j are spread over warps (both are within the fp32 tolerance of the oracle).
  *   "chunk_tile" 1 (default): the j chunks of the task plan are whole 256-entry tiles, so only the last chunk of a list ends
  *                in a ragged tile; 0: equal chunks in multiples of 8 entries (the round-1 plan, kept for A/B runs).
  *   "nb_lists"   1: pb_dispatch_count_index also collects the neighbour PAIRS (see pb_retrieve_neighbors);

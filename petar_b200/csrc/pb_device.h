@@ -99,16 +99,17 @@ cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_bloc
                          const Walk* walks, const Task* tasks,
                          const float4* epi, const int* id_epj, const int* id_spj,
                          const float4* epj, const float4* spj,
-                         double4* part4, int* partn, Params p, bool emit_pairs = false);
+                         double4* part4, int* partn, Params p, bool emit_pairs = false, bool two_i = false);
 
 cudaError_t launch_force_persistent(cudaStream_t s, int n_ctas, int nr_steps,
                                     const Walk* walks, const Task* tasks, const float4* epi, const int* id_epj, const int* id_spj,
-                                    const float4* epj, const float4* spj, double4* part4, int* partn, Params p);
+                                    const float4* epj, const float4* spj, double4* part4, int* partn, Params p, bool two_i);
 
-// warp-specialised persistent force kernel (pb_kernels_ws.cu): 8 compute warps + 1 producer warp per CTA
+// warp-specialised persistent force kernel (pb_kernels_ws.cu): 8 compute warps + 2 producer warps per CTA;
+// two_i: SP tasks of groups with at least two i-blocks keep two i-particles per lane
 cudaError_t launch_force_ws(cudaStream_t s, int n_ctas, int nr_steps,
                             const Walk* walks, const Task* tasks, const float4* epi, const int* id_epj, const int* id_spj,
-                            const float4* epj, const float4* spj, double4* part4, int* partn, Params p);
+                            const float4* epj, const float4* spj, double4* part4, int* partn, Params p, bool two_i);
 
 // device-side i-particle preparation and task planning (pb_plan.cu)
 cudaError_t launch_iprep(cudaStream_t s, const void* groups, int n_groups, const int* i_first, const int2* counts, const int2* offs,

@@ -162,6 +162,7 @@ struct Engine {
     char* d_raw = nullptr; size_t cap_raw = 0;             // device landing zone of the raw arrays
     std::vector<std::pair<const char*, size_t>> registered;   // host ranges page-locked by the library (cudaHostRegister)
     int opt_ws = 1;                                        // persistent launches use the warp-specialised kernel (pb_kernels_ws.cu)
+    int opt_sp2i = 1;                                      // SP tasks of groups with >= 2 i-blocks keep two i-particles per lane (sp_pairs_2i)
     int opt_chunk_tile = 1;                                // j chunks are whole 256-entry tiles (0: multiples of 8 entries, the round-1 plan)
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
     long long nb_n_i = 0;
@@ -634,7 +635,7 @@ cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, boo
                                  (const float4*)(d_arena + p.off_epi),
                                  p.ext_ide ? p.ext_ide : (const int*)(d_arena + p.off_ide),
                                  p.ext_ids ? p.ext_ids : (const int*)(d_arena + p.off_ids),
-                                 epj, spj, part4, partn, prm, emit != nullptr);
+                                 epj, spj, part4, partn, prm, emit != nullptr, E.opt_sp2i != 0);
     if (e != cudaSuccess || force_only) return e;
     return launch_reduce(st, p.n_iblocks, (const IBlock*)(d_arena + p.off_iblocks), part4, partn, out, E.G);
 }
@@ -987,6 +988,7 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "walk_compact")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "walk_compact must be 0 or 1"); E.opt_walk_compact = (int)v; return PB_OK; }
     if (!strcmp(key, "raw_upload")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "raw_upload must be 0 or 1"); E.opt_raw_upload = (int)v; return PB_OK; }
     if (!strcmp(key, "ws")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "ws must be 0 or 1"); E.opt_ws = (int)v; return PB_OK; }
+    if (!strcmp(key, "sp2i")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "sp2i must be 0 or 1"); E.opt_sp2i = (int)v; return PB_OK; }
     if (!strcmp(key, "chunk_tile")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "chunk_tile must be 0 or 1"); E.opt_chunk_tile = (int)v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
     if (!strcmp(key, "tree_batch")) { if (v < 1 || v > (1 << 24)) return fail(PB_ERR_ARG, "tree_batch out of range"); E.opt_tree_batch = (int)v; return PB_OK; }
@@ -1002,7 +1004,7 @@ int pb_get_option(const char* key, long long* v) {
         {"coords", E.opt_coords}, {"streams", E.opt_streams}, {"jchunk", E.opt_jchunk}, {"cull", E.opt_cull},
         {"tree_fill", E.opt_tree_fill}, {"min_slot_work", E.opt_min_slot_work}, {"tree_streams", E.opt_tree_streams},
         {"tree_spec", E.opt_tree_spec}, {"walk_ctas", E.opt_walk_ctas}, {"nb_lists", E.opt_nb_lists},
-        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"ws", E.opt_ws}, {"raw_upload", E.opt_raw_upload}, {"walk_compact", E.opt_walk_compact}, {"ep_runs", E.opt_ep_runs}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
+        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"ws", E.opt_ws}, {"sp2i", E.opt_sp2i}, {"raw_upload", E.opt_raw_upload}, {"walk_compact", E.opt_walk_compact}, {"ep_runs", E.opt_ep_runs}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
     for (const auto& t : tab)
         if (!strcmp(key, t.k)) { *v = t.val; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_get_option: unknown key '%s'", key);
@@ -1992,10 +1994,10 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
     prm.meta = E.d_r_meta;
     if (E.opt_ws)
         CU(launch_force_ws(s0, 2 * 148, E.opt_nr, E.d_r_walks, E.d_r_tasks, E.d_r_epi, E.d_tree_ide, E.d_tree_ids, E.d_epj, E.d_spj,
-                           E.d_r_part4, E.d_r_partn, prm));
+                           E.d_r_part4, E.d_r_partn, prm, E.opt_sp2i != 0));
     else
         CU(launch_force_persistent(s0, 2 * 148, E.opt_nr, E.d_r_walks, E.d_r_tasks, E.d_r_epi, E.d_tree_ide, E.d_tree_ids, E.d_epj, E.d_spj,
-                                   E.d_r_part4, E.d_r_partn, prm));
+                                   E.d_r_part4, E.d_r_partn, prm, E.opt_sp2i != 0));
     CU(cudaEventRecord(E.ev_tl[4], s0));
     CU(launch_reduce(s0, E.r_n_iblk, E.d_r_iblocks, E.d_r_part4, E.d_r_partn, E.d_r_out, E.G, E.d_r_meta));
     CU(cudaEventRecord(E.ev_tl[5], s0));

@@ -113,7 +113,9 @@ struct IdPipe {
 // PERSIST: the grid is 2 CTAs per SM and every CTA pulls task numbers from an atomic cursor until the task list is
 // used up — the task count lives in device memory (meta[0], cursor meta[4]) because the plan was made on the device
 // (pb_plan.cu), so no host round trip sits between the tree walk and the forces.
-template <int NR, int MINB, bool EMIT = false, bool PERSIST = false>
+// TWOI: SP tasks of groups with at least two i-blocks give every warp TWO blocks (one particle of each per lane) and half as
+// much of every j tile (sp_pairs_2i in pb_pairs.cuh: +6 % on the SP loop).
+template <int NR, int MINB, bool EMIT = false, bool PERSIST = false, bool TWOI = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
              const float4* __restrict__ epi,
@@ -172,6 +174,19 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
     int cnt = 0;
 
     const int n_tiles = (task.j_count + kTileJ - 1) / kTileJ;
+
+    // two i-particles per lane (SP tasks only): block pair (b0, b0 + npair), j-split slot js2 of jsp = 2 jsplit
+    const bool two_i = TWOI && task.kind == 1 && task.nib >= 2;
+    const int  npair = task.nib >> 1, jsp = 2 * task.jsplit;
+    const int  b0 = two_i ? warp % npair : 0, js2 = two_i ? warp / npair : 0;
+    KSum k2x, k2y, k2z, k2p;
+    k2x.init(); k2y.init(); k2z.init(); k2p.init();
+    float xi2[2] = {0.f, 0.f}, yi2[2] = {0.f, 0.f}, zi2[2] = {0.f, 0.f};
+    if (two_i) {
+        const int ia = task.i_first + b0 * 32 + lane, ib2 = ia + npair * 32;
+        if (ia < w.ni)  { const float4 q = __ldg(epi + (size_t)prm.i_f4 * (size_t)(w.i_off + ia));  xi2[0] = q.x; yi2[0] = q.y; zi2[0] = q.z; }
+        if (ib2 < w.ni) { const float4 q = __ldg(epi + (size_t)prm.i_f4 * (size_t)(w.i_off + ib2)); xi2[1] = q.x; yi2[1] = q.y; zi2[1] = q.z; }
+    }
 
     // Tile pipeline (both kinds): index tiles arrive by TMA up to four tiles ahead, ids are picked up two tiles ahead,
     // the gathered j records one tile ahead; tile k+1 is stored (and its mbarrier arrived on) after tile k was
@@ -258,7 +273,16 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             const int id_nn = idp.get(k + 2, tid);
             bars.wait(cb, cpar);
             if (k >= 1) idp.refill(k - 1, tid);
-            if (busy) {
+            if (two_i) {
+                const int nv  = min(kTileJ, task.j_count - k * kTileJ);
+                const int npu = ((nv + 1) >> 1);
+                const int ppk = (nv == kTileJ) ? kTilePairs / jsp : (npu + jsp - 1) / jsp;
+                const int p0  = js2 * ppk, p1 = min(p0 + ppk, npu);
+                float2 ax[2] = {bc(0.f), bc(0.f)}, ay[2] = {bc(0.f), bc(0.f)}, az[2] = {bc(0.f), bc(0.f)}, pt[2] = {bc(0.f), bc(0.f)};
+                sp_pairs_2i<NR>(sm.sp[cb], p0, p1, xi2, yi2, zi2, prm.eps2, ax, ay, az, pt);
+                kx.add(ax[0].x + ax[0].y); ky.add(ay[0].x + ay[0].y); kz.add(az[0].x + az[0].y); kp.add(pt[0].x + pt[0].y);
+                k2x.add(ax[1].x + ax[1].y); k2y.add(ay[1].x + ay[1].y); k2z.add(az[1].x + az[1].y); k2p.add(pt[1].x + pt[1].y);
+            } else if (busy) {
                 const int nv  = min(kTileJ, task.j_count - k * kTileJ);
                 const int npu = ((nv + 1) >> 1);          // pairs with at least one real j (padding pairs are inert anyway)
                 const int ppk = (nv == kTileJ) ? ppw : (npu + task.jsplit - 1) / task.jsplit;   // ragged tile: even shares
@@ -276,6 +300,25 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
     }
     __syncthreads();       // every warp is done with the tile buffers (they are reused for the cross-warp combine below)
 
+    if (two_i) {
+        // both particles of a lane: combine the jsp warps of a block pair in fixed order js2 = 0,1,..., warp b0 writes
+        for (int set = 0; set < 2; ++set) {
+            double d0 = set ? k2x.value() : kx.value(), d1 = set ? k2y.value() : ky.value();
+            double d2 = set ? k2z.value() : kz.value(), d3 = set ? k2p.value() : kp.value();
+            sm.red[warp][0][lane] = d0; sm.red[warp][1][lane] = d1; sm.red[warp][2][lane] = d2; sm.red[warp][3][lane] = d3;
+            __syncthreads();
+            if (js2 == 0) {
+                for (int s = 1; s < jsp; ++s) {
+                    const int ww = s * npair + b0;
+                    d0 += sm.red[ww][0][lane]; d1 += sm.red[ww][1][lane]; d2 += sm.red[ww][2][lane]; d3 += sm.red[ww][3][lane];
+                }
+                const int slot = task.part_base + (b0 + set * npair) * 32 + lane;
+                part4[slot] = make_double4(d0, d1, d2, d3);
+                partn[slot] = 0;
+            }
+            __syncthreads();
+        }
+    } else {
     // per-warp totals as exact doubles (hi + lo)
     double dax = kx.value(), day = ky.value(), daz = kz.value(), dpt = kp.value();
     for (int o = lanes_i; o < 32; o <<= 1) {              // lanes that shared a particle (isplit > 1): fixed-order butterfly
@@ -312,6 +355,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
         part4[slot] = make_double4(dax, day, daz, dpt);
         partn[slot] = cnt;
     }
+    }
     if (!PERSIST) break;
     __syncthreads();                                   // everybody is done with this task's shared state
     if (tid == 0) {                                    // the mbarriers are re-initialised by the next task
@@ -331,24 +375,27 @@ cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_bloc
                          const Walk* walks, const Task* tasks,
                          const float4* epi, const int* id_epj, const int* id_spj,
                          const float4* epj, const float4* spj,
-                         double4* part4, int* partn, Params p, bool emit_pairs)
+                         double4* part4, int* partn, Params p, bool emit_pairs, bool two_i)
 {
     if (n_tasks <= 0) return cudaSuccess;
 #define PB_LAUNCH(...) force_kernel<__VA_ARGS__><<<n_tasks, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p)
     if (emit_pairs)          PB_LAUNCH(0, 2, true);        // neighbour lists: count-only tasks, no rsqrt involved
-    else if (nr_steps >= 1) { if (min_blocks >= 3) PB_LAUNCH(1, 3); else PB_LAUNCH(1, 2); }
-    else                    { if (min_blocks >= 3) PB_LAUNCH(0, 3); else PB_LAUNCH(0, 2); }
+    else if (min_blocks >= 3) { if (nr_steps >= 1) PB_LAUNCH(1, 3); else PB_LAUNCH(0, 3); }       // occupancy experiment: one i per lane only
+    else if (two_i)         { if (nr_steps >= 1) PB_LAUNCH(1, 2, false, false, true); else PB_LAUNCH(0, 2, false, false, true); }
+    else                    { if (nr_steps >= 1) PB_LAUNCH(1, 2); else PB_LAUNCH(0, 2); }
 #undef PB_LAUNCH
     return cudaGetLastError();
 }
 
 cudaError_t launch_force_persistent(cudaStream_t s, int n_ctas, int nr_steps,
                                     const Walk* walks, const Task* tasks, const float4* epi, const int* id_epj, const int* id_spj,
-                                    const float4* epj, const float4* spj, double4* part4, int* partn, Params p)
+                                    const float4* epj, const float4* spj, double4* part4, int* partn, Params p, bool two_i)
 {
     if (n_ctas <= 0) return cudaSuccess;
-    if (nr_steps >= 1) force_kernel<1, 2, false, true><<<n_ctas, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
-    else               force_kernel<0, 2, false, true><<<n_ctas, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
+#define PB_LAUNCH(...) force_kernel<__VA_ARGS__><<<n_ctas, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p)
+    if (two_i) { if (nr_steps >= 1) PB_LAUNCH(1, 2, false, true, true); else PB_LAUNCH(0, 2, false, true, true); }
+    else       { if (nr_steps >= 1) PB_LAUNCH(1, 2, false, true); else PB_LAUNCH(0, 2, false, true); }
+#undef PB_LAUNCH
     return cudaGetLastError();
 }
 

@@ -34,6 +34,7 @@ struct WsCtl {
     int   next_task[2];
     double red[kWarpsPerCta][4][32];
     int    redn[kWarpsPerCta][32];
+    double red2[kWarpsPerCta][4][32];                        // second i-particle of a lane (SP tasks with two i-blocks per warp)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -62,7 +63,7 @@ __device__ __forceinline__ void producer_bar() {           // the producer warps
 
 } // namespace
 
-template <int NR>
+template <int NR, int TWOI>
 __global__ void __maxnreg__(96)
 force_kernel_ws(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 const float4* __restrict__ epi,
@@ -236,6 +237,51 @@ force_kernel_ws(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 kx.add(ax.x + ax.y); ky.add(ay.x + ay.y); kz.add(az.x + az.y); kp.add(pt.x + pt.y);
                 cnt += (int)(cf.x + cf.y);
             }
+        } else if (TWOI && task.nib >= 2) {
+            // SP task of a group with nib >= 2 i-blocks: every warp takes TWO blocks (b0 and b0 + nib/2, one particle of each
+            // per lane) and 1/(2 jsplit) of every j tile, instead of one block and 1/jsplit of the tile
+            const int npair = task.nib >> 1, jsp = 2 * task.jsplit;
+            const int b0 = warp % npair, js2 = warp / npair;
+            const int ia = task.i_first + b0 * 32 + lane, ib2 = ia + npair * 32;
+            float xi[2] = {0.f, 0.f}, yi[2] = {0.f, 0.f}, zi[2] = {0.f, 0.f};
+            if (ia < w.ni)  { const float4 q = __ldg(epi + (size_t)prm.i_f4 * (size_t)(w.i_off + ia));  xi[0] = q.x; yi[0] = q.y; zi[0] = q.z; }
+            if (ib2 < w.ni) { const float4 q = __ldg(epi + (size_t)prm.i_f4 * (size_t)(w.i_off + ib2)); xi[1] = q.x; yi[1] = q.y; zi[1] = q.z; }
+            KSum k2x, k2y, k2z, k2p;
+            k2x.init(); k2y.init(); k2z.init(); k2p.init();
+            for (int k = 0; k < n_tiles; ++k, ++g) {
+                const int s = g % kWsStages;
+                mbar_wait(&ctl.full[s], (g / kWsStages) & 1);
+                const SpTile& T = *reinterpret_cast<const SpTile*>(tiles + (size_t)s * kTileBytes);
+                const int nv  = min(kTileJ, task.j_count - k * kTileJ);
+                const int npu = ((nv + 1) >> 1);
+                const int ppk = (nv == kTileJ) ? kTilePairs / jsp : (npu + jsp - 1) / jsp;
+                const int p0  = js2 * ppk, p1 = min(p0 + ppk, npu);
+                float2 ax[2] = {bc(0.f), bc(0.f)}, ay[2] = {bc(0.f), bc(0.f)}, az[2] = {bc(0.f), bc(0.f)}, pt[2] = {bc(0.f), bc(0.f)};
+                sp_pairs_2i<NR>(T, p0, p1, xi, yi, zi, prm.eps2, ax, ay, az, pt);
+                mbar_arrive(&ctl.empty[s]);
+                kx.add(ax[0].x + ax[0].y); ky.add(ay[0].x + ay[0].y); kz.add(az[0].x + az[0].y); kp.add(pt[0].x + pt[0].y);
+                k2x.add(ax[1].x + ax[1].y); k2y.add(ay[1].x + ay[1].y); k2z.add(az[1].x + az[1].y); k2p.add(pt[1].x + pt[1].y);
+            }
+            double d0x = kx.value(), d0y = ky.value(), d0z = kz.value(), d0p = kp.value();
+            double d1x = k2x.value(), d1y = k2y.value(), d1z = k2z.value(), d1p = k2p.value();
+            // combine the warps that share a block pair in fixed order js2 = 0,1,...; warp b0 writes both blocks
+            ctl.red[warp][0][lane] = d0x; ctl.red[warp][1][lane] = d0y; ctl.red[warp][2][lane] = d0z; ctl.red[warp][3][lane] = d0p;
+            ctl.red2[warp][0][lane] = d1x; ctl.red2[warp][1][lane] = d1y; ctl.red2[warp][2][lane] = d1z; ctl.red2[warp][3][lane] = d1p;
+            compute_bar();
+            if (js2 == 0) {
+                for (int s = 1; s < jsp; ++s) {
+                    const int ww = s * npair + b0;
+                    d0x += ctl.red[ww][0][lane]; d0y += ctl.red[ww][1][lane]; d0z += ctl.red[ww][2][lane]; d0p += ctl.red[ww][3][lane];
+                    d1x += ctl.red2[ww][0][lane]; d1y += ctl.red2[ww][1][lane]; d1z += ctl.red2[ww][2][lane]; d1p += ctl.red2[ww][3][lane];
+                }
+                const int slot = task.part_base + b0 * 32 + lane;
+                part4[slot] = make_double4(d0x, d0y, d0z, d0p);
+                partn[slot] = 0;
+                part4[slot + npair * 32] = make_double4(d1x, d1y, d1z, d1p);
+                partn[slot + npair * 32] = 0;
+            }
+            compute_bar();                                  // scratch free for the next task
+            continue;
         } else {
             for (int k = 0; k < n_tiles; ++k, ++g) {
                 const int s = g % kWsStages;
@@ -289,19 +335,24 @@ size_t ws_smem_bytes() { return (size_t)kWsStages * kTileBytes + sizeof(WsCtl); 
 
 cudaError_t launch_force_ws(cudaStream_t s, int n_ctas, int nr_steps,
                             const Walk* walks, const Task* tasks, const float4* epi, const int* id_epj, const int* id_spj,
-                            const float4* epj, const float4* spj, double4* part4, int* partn, Params p)
+                            const float4* epj, const float4* spj, double4* part4, int* partn, Params p, bool two_i)
 {
     if (n_ctas <= 0) return cudaSuccess;
     static bool configured = false;
     const size_t smem = ws_smem_bytes();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(force_kernel_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(force_kernel_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaSuccess;
+        const void* fns[] = {(const void*)force_kernel_ws<0, 0>, (const void*)force_kernel_ws<1, 0>, (const void*)force_kernel_ws<0, 1>, (const void*)force_kernel_ws<1, 1>};
+        for (const void* f : fns)
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (nr_steps >= 1) force_kernel_ws<1><<<n_ctas, kWsThreads, smem, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
-    else               force_kernel_ws<0><<<n_ctas, kWsThreads, smem, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p);
+#define PB_WS_LAUNCH(NR_, TI_) force_kernel_ws<NR_, TI_><<<n_ctas, kWsThreads, smem, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p)
+    const int nr = nr_steps >= 1 ? 1 : 0;
+    if (two_i) { if (nr) PB_WS_LAUNCH(1, 1); else PB_WS_LAUNCH(0, 1); }
+    else       { if (nr) PB_WS_LAUNCH(1, 0); else PB_WS_LAUNCH(0, 0); }
+#undef PB_WS_LAUNCH
     return cudaGetLastError();
 }
 

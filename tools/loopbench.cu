@@ -13,69 +13,7 @@ using namespace pb;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 
 // ---- alternative formulations under test ---------------------------------------------------------------------------
-// (A) two i-particles per lane, j packed in pairs as shipped: every j operand register feeds two consecutive
-//     instructions (operand-reuse cache), every LDS feeds four interactions
-template <int NR>
-__device__ __forceinline__ void sp_pairs_2i(const SpTile& t, int p0, int p1, const float (&xi)[2], const float (&yi)[2], const float (&zi)[2],
-                                            float eps2, float2 (&ax)[2], float2 (&ay)[2], float2 (&az)[2], float2 (&pt)[2]) {
-    const float2 e2 = bc(eps2);
-#pragma unroll 1
-    for (int p = p0; p < p1; ++p) {
-        const float4 Q0 = t.q0[p], Q1 = t.q1[p], Q2 = t.q2[p], Q3 = t.q3[p], Q4 = t.q4[p];
-        const float2 mtr = t.q5[p];
-        const float2 nxj = make_float2(-Q0.x, -Q0.y), nyj = make_float2(-Q0.z, -Q0.w), nzj = make_float2(-Q1.x, -Q1.y);
-        const float2 mj = make_float2(Q1.z, Q1.w);
-        const float2 qxx = make_float2(Q2.x, Q2.y), qyy = make_float2(Q2.z, Q2.w);
-        const float2 qzz = make_float2(Q3.x, Q3.y), qxy = make_float2(Q3.z, Q3.w);
-        const float2 qxz = make_float2(Q4.x, Q4.y), qyz = make_float2(Q4.z, Q4.w);
-        float2 dx[2], dy[2], dz[2], r2[2], rinv[2], qrx[2], qry[2], qrz[2], S[2];
-#pragma unroll
-        for (int s = 0; s < 2; s++) { dx[s] = __fadd2_rn(bc(xi[s]), nxj); }
-#pragma unroll
-        for (int s = 0; s < 2; s++) { dy[s] = __fadd2_rn(bc(yi[s]), nyj); }
-#pragma unroll
-        for (int s = 0; s < 2; s++) { dz[s] = __fadd2_rn(bc(zi[s]), nzj); }
-#pragma unroll
-        for (int s = 0; s < 2; s++) { r2[s] = __ffma2_rn(dx[s], dx[s], e2); r2[s] = __ffma2_rn(dy[s], dy[s], r2[s]); r2[s] = __ffma2_rn(dz[s], dz[s], r2[s]); }
-#pragma unroll
-        for (int s = 0; s < 2; s++) rinv[s] = rsqrt2<NR>(r2[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) qrx[s] = __fmul2_rn(qxx, dx[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) qry[s] = __fmul2_rn(qxy, dx[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) qrz[s] = __fmul2_rn(qxz, dx[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) qrx[s] = __ffma2_rn(qxy, dy[s], qrx[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) qry[s] = __ffma2_rn(qyy, dy[s], qry[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) qrz[s] = __ffma2_rn(qyz, dy[s], qrz[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) qrx[s] = __ffma2_rn(qxz, dz[s], qrx[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) qry[s] = __ffma2_rn(qyz, dz[s], qry[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) qrz[s] = __ffma2_rn(qzz, dz[s], qrz[s]);
-#pragma unroll
-        for (int s = 0; s < 2; s++) { S[s] = __ffma2_rn(qrx[s], dx[s], mtr); S[s] = __ffma2_rn(qry[s], dy[s], S[s]); S[s] = __ffma2_rn(qrz[s], dz[s], S[s]); }
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const float2 rinv2 = __fmul2_rn(rinv[s], rinv[s]);
-            const float2 rinv3 = __fmul2_rn(rinv2, rinv[s]);
-            const float2 rinv5 = __fmul2_rn(rinv3, rinv2);
-            const float2 mr3   = __fmul2_rn(mj, rinv3);
-            const float2 S5    = __fmul2_rn(rinv5, S[s]);
-            const float2 S7    = __fmul2_rn(S5, rinv2);
-            const float2 A     = __ffma2_rn(bc(2.5f), S7, mr3);
-            const float2 nA    = make_float2(-A.x, -A.y);
-            ax[s] = __ffma2_rn(nA, dx[s], ax[s]); ay[s] = __ffma2_rn(nA, dy[s], ay[s]); az[s] = __ffma2_rn(nA, dz[s], az[s]);
-            ax[s] = __ffma2_rn(rinv5, qrx[s], ax[s]); ay[s] = __ffma2_rn(rinv5, qry[s], ay[s]); az[s] = __ffma2_rn(rinv5, qrz[s], az[s]);
-            pt[s] = __ffma2_rn(bc(0.5f), S5, pt[s]);
-            pt[s] = __ffma2_rn(mj, rinv[s], pt[s]);
-        }
-    }
-}
+// (A) two i-particles per lane, j packed in pairs as shipped: pb::sp_pairs_2i (pb_pairs.cuh; shipped in the warp-specialised kernel)
 
 // (B) i-packed: each lane holds TWO i-particles as one float2, every j enters as a scalar-broadcast (.F32) operand:
 //     the j operands are 32-bit register reads instead of 64-bit ones.  j come from the same tile, one at a time.

@@ -10,9 +10,12 @@ f = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G
 g = engine.tree_neighbor_search(batch, n_walk_limit=16)
 cells, groups = batch.tree.export_tree()
 h = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"])
-for _ in range(2):      # device-resident step: first exact, then speculative
-    hr = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], resident=True)
-assert np.array_equal(hr["n_ngb"], h["n_ngb"])
+for ws, sp2i in ((0, 0), (0, 1), (1, 0), (1, 1)):  # device-resident step with every persistent kernel variant: first exact, then speculative
+    engine.set_option("ws", ws); engine.set_option("sp2i", sp2i)
+    for _ in range(2):
+        hr = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], resident=True)
+    assert np.array_equal(hr["n_ngb"], h["n_ngb"])
+    assert np.abs(hr["acc"] - h["acc"]).max() <= 1e-5 * np.abs(h["acc"]).max()
 part = np.zeros(len(batch.epj), dtype=EPJSoft)
 part["pos"], part["mass"] = batch.epj["pos"], batch.epj["mass"]
 pts = np.random.default_rng(0).normal(size=(100, 3))
