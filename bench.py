@@ -552,6 +552,8 @@ def main():
                            "the functor path is handed for free"}
             if stepper is not None and stepper.n_dw:
                 tree["rank0_host_phases_ms"] = {k: v * 1e3 / stepper.n_dw for k, v in stepper.host_dw.items()}
+                if stepper.trace:
+                    tree["rank0_let_enqueue_trace_ms"] = {k: v * 1e3 / stepper.trace["n"] for k, v in stepper.trace.items() if k != "n"}
         e2e, other, other_key = (dict(tree), fun, "e2e_functors") if args.e2e == "tree" else (dict(fun), tree, "e2e_tree_step")
         fp = fp32_peak()
         line = {

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 5
+#define PB_ABI_VERSION 6
 
 typedef enum pb_status {
     PB_OK = 0,
@@ -332,8 +332,16 @@ int  pb_publish_j(void* cuda_stream);
 /* LET send rows gathered ON THE DEVICE: d_out32[k] = EP store row idx[k] (device j format, 32 B), k < n.  `idx` is a
  * host array of EP store slots (the local particles a peer's domain needs, as FDPS's LET selection names them);
  * `d_out32` a device buffer (e.g. the send buffer of the NCCL all-to-all).  Queued on the library's upload stream,
- * behind pb_upload_j_range's copy of those particles: 4 B per row cross PCIe instead of a host-packed 32 B row. */
+ * behind pb_upload_j_range's copy of those particles: 4 B per row cross PCIe instead of a host-packed 32 B row.
+ * With option raw_upload the list is copied from where it lies (page-locked once; it must stay unchanged until the
+ * step's forces are back) and the indices are checked by the gather kernel: an index outside the store makes the next
+ * call that synchronises with the device (pb_tree_force_resident, pb_retrieve, the next pb_let_gather_epj) fail with
+ * PB_ERR_ARG; otherwise they are checked here. */
 int  pb_let_gather_epj(const int* idx, int n, void* d_out32);
+/* LET send rows of the other kind: d_out64[k] = pack(spj[k]) (device j format, 64 B), k < n, from a HOST array of
+ * superparticles (the local tree's multipoles a peer's domain needs) into a DEVICE buffer, on the upload stream.
+ * Option raw_upload: the array is copied as it is and packed on the device; otherwise packed here into pinned staging. */
+int  pb_let_pack_spj(const void* spj, int n, const pb_layout_spj* l, void* d_out64);
 /* Make `cuda_stream` (a cudaStream_t, e.g. the stream the collective is enqueued on) wait for everything queued so
  * far on the library's upload stream (pb_upload_j_range, pb_let_gather_epj). */
 int  pb_stream_wait_upload(void* cuda_stream);

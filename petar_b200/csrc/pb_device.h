@@ -119,7 +119,7 @@ cudaError_t launch_devplan(cudaStream_t s, const void* groups, int n_groups, con
 // device-side packing of raw host arrays (pb_pack.cu, option "raw_upload")
 cudaError_t launch_pack_epj(cudaStream_t s, const void* raw, size_t stride, size_t off_pos, size_t off_mass, size_t off_rs, int n, float4* out);
 cudaError_t launch_pack_spj(cudaStream_t s, const void* raw, size_t stride, size_t off_pos, size_t off_mass, size_t off_quad, int has_quad, int n, float4* out);
-cudaError_t launch_gather_epj(cudaStream_t s, const float4* epj, const int* idx, int n, float4* out);
+cudaError_t launch_gather_epj(cudaStream_t s, const float4* epj, int n_epj, const int* idx, int n, float4* out, int* err);
 cudaError_t launch_expand_runs(cudaStream_t s, const int2* runtab, const int2* runs, const Walk* walks, int n_walk, int* out);
 void plan_sizes_host(const int* ni, const int2* counts, int n_groups, int U, int Us, long long* n_tasks, long long* n_part, long long* n_iblk);
 

@@ -177,6 +177,9 @@ struct Engine {
     long long r_prev_tasks = 0, r_prev_part = 0;
     cudaEvent_t ev_tl[8] = {nullptr}; bool tl_valid = false; float tl_ms[8] = {0};
     int* d_let_idx = nullptr; int* h_let_idx = nullptr; size_t cap_let_idx = 0;      // LET send lists (EP store slots)
+    int* d_let_err = nullptr; int* h_let_err = nullptr;                              // an index outside the store, found by the gather kernel
+    char* d_raw_let = nullptr; size_t cap_raw_let = 0;                               // raw LET SP rows (option raw_upload)
+    float4* h_let_sp = nullptr; size_t cap_let_sp = 0;                               // host-packed LET SP rows (pinned)
 
     pb_profile prof;
 };
@@ -953,7 +956,7 @@ void pb_finalize(void) {
     cudaFreeHost(E.h_counts_p); cudaFreeHost(E.h_over_p);
     cudaFree(E.d_ifirst); cudaFreeHost(E.h_ifirst); cudaFree(E.d_r_walks); cudaFree(E.d_r_goff); cudaFree(E.d_r_epi); cudaFree(E.d_r_out);
     cudaFreeHost(E.h_r_out); cudaFree(E.d_r_iblocks); cudaFree(E.d_r_tasks); cudaFree(E.d_r_part4); cudaFree(E.d_r_partn);
-    cudaFree(E.d_r_meta); cudaFreeHost(E.h_r_meta); cudaFree(E.d_let_idx); cudaFreeHost(E.h_let_idx);
+    cudaFree(E.d_r_meta); cudaFreeHost(E.h_r_meta); cudaFree(E.d_let_idx); cudaFreeHost(E.h_let_idx); cudaFree(E.d_let_err); cudaFreeHost(E.h_let_err); cudaFree(E.d_raw_let); cudaFreeHost(E.h_let_sp);
     for (int k = 0; k < 8; k++) if (E.ev_tl[k]) cudaEventDestroy(E.ev_tl[k]);
     if (E.ev_count) cudaEventDestroy(E.ev_count);
     if (E.ev_fill) cudaEventDestroy(E.ev_fill);
@@ -1039,6 +1042,17 @@ bool ensure_registered(const void* ptr, size_t bytes) {
     if (cudaHostRegister((void*)p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return false; }
     E.registered.push_back({p, bytes});
     return true;
+}
+
+// the gather kernel of pb_let_gather_epj found an index outside the store (option raw_upload: the list is not read on
+// the host): reported by the first call that has synchronised with the device since
+int check_let_error() {
+    if (E.h_let_err && *E.h_let_err) {
+        *E.h_let_err = 0;
+        cudaMemset(E.d_let_err, 0, sizeof(int));
+        return fail(PB_ERR_ARG, "pb_let_gather_epj: an index was outside the EP store (found on the device)");
+    }
+    return PB_OK;
 }
 } // namespace
 
@@ -1153,14 +1167,61 @@ int pb_let_gather_epj(const int* idx, int n, void* d_out32) {
         CU(cudaMalloc(&E.d_let_idx, sizeof(int) * E.cap_let_idx));
         CU(cudaMallocHost(&E.h_let_idx, sizeof(int) * E.cap_let_idx));
     }
-    for (int k = 0; k < n; k++)
-        if (idx[k] < 0 || idx[k] >= E.n_epj) return fail(PB_ERR_ARG, "pb_let_gather_epj: index %d outside the EP store (%d entries)", idx[k], E.n_epj);
-    memcpy(E.h_let_idx, idx, sizeof(int) * (size_t)n);
+    if (!E.d_let_err) {
+        CU(cudaMalloc(&E.d_let_err, sizeof(int)));
+        CU(cudaMallocHost(&E.h_let_err, sizeof(int)));
+        CU(cudaMemset(E.d_let_err, 0, sizeof(int)));
+        *E.h_let_err = 0;
+    }
+    if ((rc = check_let_error()) != PB_OK) return rc;
     // on the upload stream: behind the local particles' copy, ahead of whatever the caller orders after pb_stream_wait_upload
-    CU(cudaMemcpyAsync(E.d_let_idx, E.h_let_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, E.s_upload));
-    CU(launch_gather_epj(E.s_upload, E.d_epj, E.d_let_idx, n, (float4*)d_out32));
+    if (E.opt_raw_upload && ensure_registered(idx, sizeof(int) * (size_t)n)) {
+        // the list travels from where it lies (page-locked once); the gather kernel checks the indices
+        CU(cudaMemcpyAsync(E.d_let_idx, idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, E.s_upload));
+    } else {
+        for (int k = 0; k < n; k++)
+            if (idx[k] < 0 || idx[k] >= E.n_epj) return fail(PB_ERR_ARG, "pb_let_gather_epj: index %d outside the EP store (%d entries)", idx[k], E.n_epj);
+        CU(cudaStreamSynchronize(E.s_upload));             // the staging copy of the previous call has been read
+        memcpy(E.h_let_idx, idx, sizeof(int) * (size_t)n);
+        CU(cudaMemcpyAsync(E.d_let_idx, E.h_let_idx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, E.s_upload));
+    }
+    CU(launch_gather_epj(E.s_upload, E.d_epj, E.n_epj, E.d_let_idx, n, (float4*)d_out32, E.d_let_err));
+    CU(cudaMemcpyAsync(E.h_let_err, E.d_let_err, sizeof(int), cudaMemcpyDeviceToHost, E.s_upload));
     E.prof.h2d_bytes += (long long)(sizeof(int) * (size_t)n);
     E.prof.n_kernel_launch += 1;
+    return PB_OK;
+}
+
+int pb_let_pack_spj(const void* spj, int n, const pb_layout_spj* l, void* d_out64) {
+    int rc = ensure_init();
+    if (rc != PB_OK) return rc;
+    if (n < 0 || (n && (!spj || !l || !d_out64))) return fail(PB_ERR_ARG, "pb_let_pack_spj: bad argument");
+    if (n == 0) return PB_OK;
+    const size_t bs = (size_t)n * l->stride;
+    if (E.opt_raw_upload && ensure_registered(spj, bs)) {
+        if (bs > E.cap_raw_let) {
+            CU(cudaStreamSynchronize(E.s_upload));
+            if (E.d_raw_let) CU(cudaFree(E.d_raw_let));
+            E.d_raw_let = nullptr; E.cap_raw_let = 0;
+            const size_t cap = align_up(bs + bs / 4, 1 << 20);
+            CU(cudaMalloc(&E.d_raw_let, cap));
+            E.cap_raw_let = cap;
+        }
+        CU(cudaMemcpyAsync(E.d_raw_let, spj, bs, cudaMemcpyHostToDevice, E.s_upload));
+        CU(launch_pack_spj(E.s_upload, E.d_raw_let, l->stride, l->off_pos, l->off_mass, l->off_quad, l->has_quad, n, (float4*)d_out64));
+        E.prof.h2d_bytes += (long long)bs;
+        E.prof.n_kernel_launch += 1;
+        return PB_OK;
+    }
+    CU(cudaStreamSynchronize(E.s_upload));                 // the staging buffer's previous content has been read
+    if ((size_t)n > E.cap_let_sp) {
+        if (E.h_let_sp) CU(cudaFreeHost(E.h_let_sp));
+        E.cap_let_sp = (size_t)n + n / 4 + 1024;
+        CU(cudaMallocHost(&E.h_let_sp, 64 * E.cap_let_sp));
+    }
+    pack_spj(spj, n, *l, E.h_let_sp);
+    CU(cudaMemcpyAsync(d_out64, E.h_let_sp, 64 * (size_t)n, cudaMemcpyHostToDevice, E.s_upload));
+    E.prof.h2d_bytes += (long long)(64 * (size_t)n);
     return PB_OK;
 }
 
@@ -1324,7 +1385,7 @@ int pb_retrieve(int n_walk, const int* ni, void* const* force, const pb_layout_f
         E.end_cur ^= 1;
     }
     E.outstanding = false;
-    return PB_OK;
+    return check_let_error();
 }
 
 // ---- direct-sum field query ---------------------------------------------------
@@ -1623,7 +1684,12 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
     if (elem_map && n_cells && (long long)cells[0].first + cells[0].n > n_elem)
         return fail(PB_ERR_ARG, "pb_tree_upload_let: the root cell spans %lld elements, elem_map has %d", (long long)cells[0].first + cells[0].n, n_elem);
     if (E.outstanding) return fail(PB_ERR_PROTOCOL, "pb_tree_upload while a dispatch is outstanding");
+    static const bool trace = getenv("PETAR_B200_TRACE") != nullptr;      // host time of this call's phases, printed once (8th call)
+    static int trace_calls = 0;
+    double tt[8]; int nt_ = 0;
+    tt[nt_++] = now_s();
     CU(cudaDeviceSynchronize());
+    tt[nt_++] = now_s();
     if ((size_t)n_cells > E.cap_cells) {
         if (E.d_cells) CU(cudaFree(E.d_cells));
         E.cap_cells = (size_t)n_cells + n_cells / 4 + 1024;
@@ -1659,6 +1725,7 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
     }
     CU(cudaMemcpyAsync(E.d_cells, E.h_tstage, bc, cudaMemcpyHostToDevice, E.s_upload));
     CU(cudaMemcpyAsync(E.d_groups, E.h_tstage + bc, bg, cudaMemcpyHostToDevice, E.s_upload));
+    tt[nt_++] = now_s();
     E.has_elem_map = elem_map != nullptr && n_elem > 0;
     if (E.has_elem_map) {
         if ((size_t)n_elem > E.cap_elem_map) {
@@ -1668,10 +1735,15 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
             CU(cudaMalloc(&E.d_elem_map, sizeof(int) * E.cap_elem_map));
             CU(cudaMallocHost(&E.h_elem_map, sizeof(int) * E.cap_elem_map));
         }
-        memcpy(E.h_elem_map, elem_map, sizeof(int) * (size_t)n_elem);
-        CU(cudaMemcpyAsync(E.d_elem_map, E.h_elem_map, sizeof(int) * (size_t)n_elem, cudaMemcpyHostToDevice, E.s_upload));
+        if (E.opt_raw_upload && ensure_registered(elem_map, sizeof(int) * (size_t)n_elem))
+            CU(cudaMemcpyAsync(E.d_elem_map, elem_map, sizeof(int) * (size_t)n_elem, cudaMemcpyHostToDevice, E.s_upload));   // from where it lies
+        else {
+            memcpy(E.h_elem_map, elem_map, sizeof(int) * (size_t)n_elem);
+            CU(cudaMemcpyAsync(E.d_elem_map, E.h_elem_map, sizeof(int) * (size_t)n_elem, cudaMemcpyHostToDevice, E.s_upload));
+        }
         E.prof.h2d_bytes += (long long)(sizeof(int) * (size_t)n_elem);
     }
+    tt[nt_++] = now_s();
     E.n_cells = n_cells; E.n_groups = n_groups; E.theta = theta;
     E.grp_n.resize(n_groups);
     for (int g = 0; g < n_groups; g++) E.grp_n[g] = groups[g].n;
@@ -1689,6 +1761,7 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
         E.r_n_i = acc; E.r_n_iblk = nblk;
         if (n_groups) CU(cudaMemcpyAsync(E.d_ifirst, E.h_ifirst, sizeof(int) * (size_t)n_groups, cudaMemcpyHostToDevice, E.s_upload));
     }
+    tt[nt_++] = now_s();
     CU(cudaEventRecord(E.ev_j_ready, E.s_upload)); E.j_epoch++;        // dispatch streams wait for j AND tree
     E.prof.h2d_bytes += (long long)(sizeof(pb_tree_cell) * (size_t)n_cells + sizeof(pb_tree_group) * (size_t)n_groups + sizeof(int) * (size_t)n_groups);
     // pass 1 of the device walk starts right away — it needs the tree only, so it runs while the
@@ -1771,6 +1844,10 @@ int pb_tree_upload_let(const pb_tree_cell* cells, int n_cells, const pb_tree_gro
         E.prof.n_kernel_launch += 1;
         E.prof.d2h_bytes += (long long)(sizeof(int2) * (size_t)n_groups);
     }
+    tt[nt_++] = now_s();
+    if (trace && ++trace_calls == 8)
+        fprintf(stderr, "petar_b200 trace: pb_tree_upload_let rank %d [ms]: device_sync %.3f, tree copies enqueued %.3f, elem_map %.3f, group sizes %.3f, walk enqueue %.3f (cells %d groups %d elems %d)\n",
+                E.rank, 1e3 * (tt[1] - tt[0]), 1e3 * (tt[2] - tt[1]), 1e3 * (tt[3] - tt[2]), 1e3 * (tt[4] - tt[3]), 1e3 * (tt[5] - tt[4]), n_cells, n_groups, n_elem);
     return PB_OK;
 }
 
@@ -2011,6 +2088,7 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
     CU(cudaEventSynchronize(E.ev_tl[6]));
 
     if (E.h_over_p[0]) return fail(PB_ERR_ARG, "pb_tree_force_resident: tree-walk frontier exceeded %d cells per level", kWalkCap);
+    if ((rc = check_let_error()) != PB_OK) return rc;
     const bool retry = (!exact && E.h_over_p[1] != 0) || E.h_r_meta[3] != 0;
     E.h_counts.assign(E.h_counts_p, E.h_counts_p + ng);    // true list lengths of this step, whatever happened
     if (retry) {

@@ -228,15 +228,21 @@ cudaError_t launch_devplan(cudaStream_t s, const void* groups, int n_groups, con
 // LET send rows gathered on the device: out[k] = EP store row idx[k] (32 B rows as two float4)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gather_epj_kernel(const float4* __restrict__ epj, const int* __restrict__ idx, int n, float4* __restrict__ out) {
+gather_epj_kernel(const float4* __restrict__ epj, int n_epj, const int* __restrict__ idx, int n, float4* __restrict__ out, int* __restrict__ err) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * n) return;
-    out[t] = __ldg(epj + 2 * (size_t)idx[t >> 1] + (t & 1));
+    const int id = idx[t >> 1];
+    if ((unsigned)id >= (unsigned)n_epj) {                // reported by the next call that synchronises with the device
+        if (err) atomicExch(err, 1);
+        out[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    out[t] = __ldg(epj + 2 * (size_t)id + (t & 1));
 }
 
-cudaError_t launch_gather_epj(cudaStream_t s, const float4* epj, const int* idx, int n, float4* out) {
+cudaError_t launch_gather_epj(cudaStream_t s, const float4* epj, int n_epj, const int* idx, int n, float4* out, int* err) {
     if (n <= 0) return cudaSuccess;
-    gather_epj_kernel<<<(2 * n + 255) / 256, 256, 0, s>>>(epj, idx, n, out);
+    gather_epj_kernel<<<(2 * n + 255) / 256, 256, 0, s>>>(epj, n_epj, idx, n, out, err);
     return cudaGetLastError();
 }
 

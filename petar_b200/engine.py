@@ -79,7 +79,7 @@ LAYOUT_EPJ = LayoutEpj(EPJSoft.itemsize, _off(EPJSoft, "pos"), _off(EPJSoft, "ma
 LAYOUT_SPJ = LayoutSpj(SPJQuad.itemsize, _off(SPJQuad, "pos"), _off(SPJQuad, "mass"), _off(SPJQuad, "quad"), 1)
 LAYOUT_FORCE = LayoutForce(ForceSoft.itemsize, _off(ForceSoft, "acc"), _off(ForceSoft, "pot"), _off(ForceSoft, "n_ngb"))
 
-ABI_VERSION = 5   # PB_ABI_VERSION of include/petar_b200.h this module binds
+ABI_VERSION = 6   # PB_ABI_VERSION of include/petar_b200.h this module binds
 
 # every symbol include/petar_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -89,7 +89,7 @@ ABI_SYMBOLS = [
     "pb_reserve_j", "pb_upload_j_range", "pb_publish_j", "pb_pack_epj_host", "pb_pack_epj_host_indexed", "pb_pack_spj_host",
     "pb_field_at_points", "pb_dispatch_count_index", "pb_tree_upload", "pb_tree_force", "pb_tree_lists",
     "pb_correct_changeover", "pb_retrieve_neighbors", "pb_tree_upload_let", "pb_debug_plan", "pb_tree_stage",
-    "pb_tree_force_resident", "pb_tree_timeline", "pb_let_gather_epj", "pb_stream_wait_upload",
+    "pb_tree_force_resident", "pb_tree_timeline", "pb_let_gather_epj", "pb_let_pack_spj", "pb_stream_wait_upload",
 ]
 
 _lib = None
@@ -129,6 +129,7 @@ def load():
     L.pb_upload_j_range.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(LayoutEpj), _vp, C.c_int, C.c_int, C.POINTER(LayoutSpj)]
     L.pb_publish_j.argtypes = [_vp]
     L.pb_let_gather_epj.argtypes = [_vp, C.c_int, _vp]
+    L.pb_let_pack_spj.argtypes = [_vp, C.c_int, C.POINTER(LayoutSpj), _vp]
     L.pb_stream_wait_upload.argtypes = [_vp]
     L.pb_pack_epj_host.argtypes = [_vp, C.c_int, C.POINTER(LayoutEpj), _vp]
     L.pb_pack_epj_host_indexed.argtypes = [_vp, _vp, C.c_int, C.POINTER(LayoutEpj), _vp]

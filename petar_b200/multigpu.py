@@ -164,6 +164,7 @@ class DomainStepper:
         self.nccl_bytes_per_step = 32 * len(self.send_idx) + 64 * len(self.send_sp)
         self.host_s, self.n_steps = {}, 0          # wall-clock of the step's host phases (seconds, accumulated)
         self.host_dw, self.n_dw = {}, 0
+        self.trace = {} if os.environ.get("PETAR_B200_TRACE_HOST") else None   # finer host timers of the LET exchange
         self.send_idx32 = self.send_idx.astype(np.int32)            # LET EP rows as store slots (local particles come first)
         self.L = engine.load()
         if device:
@@ -224,18 +225,32 @@ class DomainStepper:
     def exchange_device(self):
         """The LET exchange of the GPU steps.  EP rows are gathered ON THE DEVICE from the local part of the j store
         (the host ships 4-byte store slots, not packed 32-byte rows); SP rows are the local tree's multipoles, which
-        exist on the host only, so they are packed there (64 B each) and copied.  One NCCL all-to-all per kind writes
-        straight into the peers' j stores behind their locally uploaded part."""
+        exist on the host only: pb_let_pack_spj copies them as they are and packs them on the device (raw_upload) or packs
+        them into pinned staging.  One NCCL all-to-all per kind writes straight into the peers' j stores behind their
+        locally uploaded part."""
+        import time
         torch, dist, L = self.torch, self.dist, self.L
+        tr = self.trace
+        t = [time.perf_counter()] if tr is not None else None
         if len(self.send_idx32):
             engine.check(L.pb_let_gather_epj(self.send_idx32.ctypes.data, len(self.send_idx32), self.d_send_ep.data_ptr()), "pb_let_gather_epj")
-        self.pack_send_sp()
-        self.d_send_sp.copy_(self.h_send_sp, non_blocking=True)
+        if t: t.append(time.perf_counter())
+        if len(self.send_sp):
+            engine.check(L.pb_let_pack_spj(self.send_sp.ctypes.data, len(self.send_sp), C.byref(engine.LAYOUT_SPJ), self.d_send_sp.data_ptr()), "pb_let_pack_spj")
+        if t: t.append(time.perf_counter())
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         engine.check(L.pb_stream_wait_upload(stream), "pb_stream_wait_upload")     # local j copied, EP rows gathered
+        if t: t.append(time.perf_counter())
         dist.all_to_all_single(self.store_ep[self.n_loc:], self.d_send_ep, self.out_ep, self.in_ep)
+        if t: t.append(time.perf_counter())
         dist.all_to_all_single(self.store_sp[self.n_nodes:], self.d_send_sp, self.out_sp, self.in_sp)
+        if t: t.append(time.perf_counter())
         engine.check(L.pb_publish_j(stream), "pb_publish_j")
+        if t:
+            t.append(time.perf_counter())
+            for k, name in enumerate(("gather_ep", "pack_sp", "wait_upload", "all_to_all_ep", "all_to_all_sp", "publish")):
+                tr[name] = tr.get(name, 0.0) + t[k + 1] - t[k]
+            tr["n"] = tr.get("n", 0) + 1
 
     def _stage_tree(self):
         wl = self.wl

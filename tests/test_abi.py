@@ -27,7 +27,7 @@ def test_header_symbols_all_exported():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/petar_b200.h but not exported"
     assert sorted(engine.ABI_SYMBOLS) == names
-    assert L.pb_abi_version() == engine.ABI_VERSION == 5
+    assert L.pb_abi_version() == engine.ABI_VERSION == 6
 
 
 def test_shim_defines_petar_symbols():

@@ -144,3 +144,49 @@ def test_ep_lists_as_runs_are_bitwise_equivalent():
     engine.check(L.pb_replay(2, C.byref(ms), None), "replay")
     engine.set_option("ep_runs", 0)
     assert ms.value > 0
+
+
+def test_let_send_rows_made_on_the_device():
+    """pb_let_gather_epj / pb_let_pack_spj (the LET send rows of a multi-GPU step), with and without raw_upload: the rows
+    equal the host packers' bit for bit; with raw_upload a bad index is found by the gather kernel and reported by the
+    next call that has synchronised with the device."""
+    import torch
+    L = engine.load()
+    batch, _, prm, _ = hz.kroupa_binary_case(4000)
+    n_e, n_s = len(batch.epj), len(batch.spj)
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, n_e, size=5000).astype(np.int32)
+    sp_rows = batch.spj[rng.integers(0, n_s, size=3000)].copy()
+    ref_e = np.zeros((len(idx), 8), dtype=np.float32)
+    ref_s = np.zeros((len(sp_rows), 16), dtype=np.float32)
+    idx64 = idx.astype(np.int64)
+    engine.check(L.pb_pack_epj_host_indexed(batch.epj.ctypes.data, idx64.ctypes.data, len(idx), C.byref(engine.LAYOUT_EPJ), ref_e.ctypes.data), "pack")
+    engine.check(L.pb_pack_spj_host(sp_rows.ctypes.data, len(sp_rows), C.byref(engine.LAYOUT_SPJ), ref_s.ctypes.data), "pack")
+    d_e = torch.zeros((len(idx), 8), dtype=torch.float32, device="cuda")
+    d_s = torch.zeros((len(sp_rows), 16), dtype=torch.float32, device="cuda")
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for raw in (0, 1):
+        engine.set_option("raw_upload", raw)
+        try:
+            d_e.zero_(); d_s.zero_(); torch.cuda.synchronize()
+            engine.check(L.pb_upload_j(batch.epj.ctypes.data, n_e, C.byref(engine.LAYOUT_EPJ), batch.spj.ctypes.data, n_s, C.byref(engine.LAYOUT_SPJ)), "pb_upload_j")
+            engine.check(L.pb_let_gather_epj(idx.ctypes.data, len(idx), d_e.data_ptr()), "pb_let_gather_epj")
+            engine.check(L.pb_let_pack_spj(sp_rows.ctypes.data, len(sp_rows), C.byref(engine.LAYOUT_SPJ), d_s.data_ptr()), "pb_let_pack_spj")
+            engine.check(L.pb_stream_wait_upload(stream), "pb_stream_wait_upload")
+            torch.cuda.synchronize()
+            assert d_e.cpu().numpy().tobytes() == ref_e.tobytes(), raw
+            assert d_s.cpu().numpy().tobytes() == ref_s.tobytes(), raw
+            bad = idx.copy(); bad[17] = n_e + 5
+            if raw:
+                engine.check(L.pb_let_gather_epj(bad.ctypes.data, len(bad), d_e.data_ptr()), "pb_let_gather_epj")   # accepted: nobody reads it on the host
+                engine.check(L.pb_stream_wait_upload(stream), "pb_stream_wait_upload")
+                torch.cuda.synchronize()
+                with pytest.raises(engine.PbError):
+                    engine.check(L.pb_let_gather_epj(idx.ctypes.data, len(idx), d_e.data_ptr()), "pb_let_gather_epj")
+                engine.check(L.pb_let_gather_epj(idx.ctypes.data, len(idx), d_e.data_ptr()), "pb_let_gather_epj")   # reported once
+            else:
+                with pytest.raises(engine.PbError):
+                    engine.check(L.pb_let_gather_epj(bad.ctypes.data, len(bad), d_e.data_ptr()), "pb_let_gather_epj")
+            torch.cuda.synchronize()
+        finally:
+            engine.set_option("raw_upload", 0)
