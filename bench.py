@@ -400,6 +400,9 @@ def main():
     else:
         cells, groups = wl["tree_cells"], wl["tree_groups"]
         tree_step = lambda: stepper.step_device_walk(force_dw)
+    # the result array of the tree step persists from step to step (as FDPS's force array does): the library page-locks it
+    # once and the force kernel writes the reduced forces straight into it
+    engine.set_option("raw_result", int(os.environ.get("PETAR_B200_RAW_RESULT", "1")))
     run_tree = not args.no_device_walk
     if not run_tree:
         args.e2e = "functors"

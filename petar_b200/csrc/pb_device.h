@@ -35,7 +35,7 @@ struct __align__(16) Walk {
 
 // One CTA's work: a group of `nib` 32-wide i-blocks of one walk against a chunk of one of the
 // walk's two j lists; `jsplit` warps share each i-block and split every j tile between them
-// (nib * jsplit <= kWarpsPerCta).  32 B.
+// (nib * jsplit <= kWarpsPerCta).  48 B.
 struct __align__(16) Task {
     int walk;
     int i_first;          // first i of the group, relative to the walk (multiple of 32)
@@ -45,6 +45,9 @@ struct __align__(16) Task {
     int j_begin;          // chunk start within the walk's list
     int j_count;
     int part_base;        // partial-sum slot of (i-block 0, lane 0) for this task
+    int blk0;             // index of the group's first i-block in the IBlock table (fused reduction: its chunk counter)
+    int n_chunks;         // EP + SP chunks of the group = partial sums every one of its i-blocks receives
+    int pad1, pad2;
 };
 
 // One 32-wide i-block for the reduction kernel.  32 B.
@@ -78,6 +81,12 @@ struct Params {
     unsigned long long* pairs;
     unsigned int* pair_cursor;
     int* meta;            // persistent launches (device-made plan): [0] task count, [4] task cursor
+    // fused reduction (pb::force_kernel_ws, option "fuse_reduce"): the warp that delivers the LAST chunk of an i-block adds
+    // the block's partial sums in chunk order and writes the forces, straight into page-locked host memory
+    const IBlock* iblocks;
+    int*   done;          // chunks delivered per i-block (returns to 0)
+    ForceOut* out;        // device-visible address of the host result array
+    double G;
 };
 
 // Two-float position relative to the walk origin: hi + lo = (xh + xl) - (oh + ol) to ~2^-46,

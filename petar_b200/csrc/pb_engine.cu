@@ -162,6 +162,8 @@ struct Engine {
     char* d_raw = nullptr; size_t cap_raw = 0;             // device landing zone of the raw arrays
     std::vector<std::pair<const char*, size_t>> registered;   // host ranges page-locked by the library (cudaHostRegister)
     int opt_ws = 1;                                        // persistent launches use the warp-specialised kernel (pb_kernels_ws.cu)
+    int opt_raw_result = 0;                                // device-resident step: page-lock the caller's force array once and let the kernel write into it
+    int opt_fuse_reduce = 1;                               // device-resident step: the force kernel adds up finished i-blocks and writes the forces to host memory itself
     int opt_sp2i = 1;                                      // SP tasks of groups with >= 2 i-blocks keep two i-particles per lane (sp_pairs_2i)
     int opt_chunk_tile = 1;                                // j chunks are whole 256-entry tiles (0: multiples of 8 entries, the round-1 plan)
     std::vector<unsigned long long> nb_keys;               // (i << 32 | j) of the last retrieved count dispatch, sorted
@@ -170,7 +172,7 @@ struct Engine {
     // device-resident tree step (pb_tree_force_resident): i-particles, plan and forces never visit the host
     int* d_ifirst = nullptr; int* h_ifirst = nullptr; size_t cap_ifirst = 0; long long r_n_i = 0; int r_n_iblk = 0;
     Walk* d_r_walks = nullptr; int3* d_r_goff = nullptr; size_t cap_r_groups = 0;
-    float4* d_r_epi = nullptr; ForceOut* d_r_out = nullptr; ForceOut* h_r_out = nullptr; IBlock* d_r_iblocks = nullptr; size_t cap_r_i = 0;
+    float4* d_r_epi = nullptr; ForceOut* d_r_out = nullptr; ForceOut* h_r_out = nullptr; IBlock* d_r_iblocks = nullptr; int* d_r_done = nullptr; size_t cap_r_i = 0;
     Task* d_r_tasks = nullptr; size_t cap_r_tasks = 0;
     double4* d_r_part4 = nullptr; int* d_r_partn = nullptr; size_t cap_r_part = 0;
     int* d_r_meta = nullptr; int* h_r_meta = nullptr;
@@ -453,10 +455,12 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
                 t.walk = g.walk; t.i_first = g.i_first; t.nib = g.nib; t.jsplit = g.jsplit;
                 t.kind = (kind == 0 && E.count_only) ? 2 : kind; t.j_begin = jb; t.j_count = std::min(len, nj - jb);
                 t.part_base = part_base + chunk * stride;
+                t.blk0 = (int)hp.iblocks.size(); t.n_chunks = 0; t.pad1 = t.pad2 = 0;
                 hp.tasks.push_back(t);
                 chunk++;
             }
         }
+        for (int c = 0; c < chunk; c++) hp.tasks[hp.tasks.size() - 1 - c].n_chunks = chunk;
         for (int b = 0; b < g.nib; b++) {
             IBlock ib;
             ib.part_base = part_base + b * 32;
@@ -625,6 +629,7 @@ Params make_params(const Plan& p, const Slot* emit) {
     prm.pairs = emit ? emit->d_pairs : nullptr;
     prm.pair_cursor = emit ? emit->d_cursor : nullptr;
     prm.meta = nullptr;
+    prm.iblocks = nullptr; prm.done = nullptr; prm.out = nullptr; prm.G = E.G;
     return prm;
 }
 
@@ -955,7 +960,7 @@ void pb_finalize(void) {
     cudaFree(E.d_tree_ide); cudaFree(E.d_tree_ids); cudaFree(E.d_tree_off); cudaFree(E.d_tree_caps);
     cudaFreeHost(E.h_counts_p); cudaFreeHost(E.h_over_p);
     cudaFree(E.d_ifirst); cudaFreeHost(E.h_ifirst); cudaFree(E.d_r_walks); cudaFree(E.d_r_goff); cudaFree(E.d_r_epi); cudaFree(E.d_r_out);
-    cudaFreeHost(E.h_r_out); cudaFree(E.d_r_iblocks); cudaFree(E.d_r_tasks); cudaFree(E.d_r_part4); cudaFree(E.d_r_partn);
+    cudaFreeHost(E.h_r_out); cudaFree(E.d_r_iblocks); cudaFree(E.d_r_done); cudaFree(E.d_r_tasks); cudaFree(E.d_r_part4); cudaFree(E.d_r_partn);
     cudaFree(E.d_r_meta); cudaFreeHost(E.h_r_meta); cudaFree(E.d_let_idx); cudaFreeHost(E.h_let_idx); cudaFree(E.d_let_err); cudaFreeHost(E.h_let_err); cudaFree(E.d_raw_let); cudaFreeHost(E.h_let_sp);
     for (int k = 0; k < 8; k++) if (E.ev_tl[k]) cudaEventDestroy(E.ev_tl[k]);
     if (E.ev_count) cudaEventDestroy(E.ev_count);
@@ -991,6 +996,8 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "walk_compact")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "walk_compact must be 0 or 1"); E.opt_walk_compact = (int)v; return PB_OK; }
     if (!strcmp(key, "raw_upload")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "raw_upload must be 0 or 1"); E.opt_raw_upload = (int)v; return PB_OK; }
     if (!strcmp(key, "ws")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "ws must be 0 or 1"); E.opt_ws = (int)v; return PB_OK; }
+    if (!strcmp(key, "raw_result")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "raw_result must be 0 or 1"); E.opt_raw_result = (int)v; return PB_OK; }
+    if (!strcmp(key, "fuse_reduce")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "fuse_reduce must be 0 or 1"); E.opt_fuse_reduce = (int)v; return PB_OK; }
     if (!strcmp(key, "sp2i")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "sp2i must be 0 or 1"); E.opt_sp2i = (int)v; return PB_OK; }
     if (!strcmp(key, "chunk_tile")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "chunk_tile must be 0 or 1"); E.opt_chunk_tile = (int)v; return PB_OK; }
     if (!strcmp(key, "nb_lists")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "nb_lists must be 0 or 1"); E.opt_nb_lists = (int)v; return PB_OK; }
@@ -1007,7 +1014,7 @@ int pb_get_option(const char* key, long long* v) {
         {"coords", E.opt_coords}, {"streams", E.opt_streams}, {"jchunk", E.opt_jchunk}, {"cull", E.opt_cull},
         {"tree_fill", E.opt_tree_fill}, {"min_slot_work", E.opt_min_slot_work}, {"tree_streams", E.opt_tree_streams},
         {"tree_spec", E.opt_tree_spec}, {"walk_ctas", E.opt_walk_ctas}, {"nb_lists", E.opt_nb_lists},
-        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"ws", E.opt_ws}, {"sp2i", E.opt_sp2i}, {"raw_upload", E.opt_raw_upload}, {"walk_compact", E.opt_walk_compact}, {"ep_runs", E.opt_ep_runs}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
+        {"tree_batch", E.opt_tree_batch}, {"chunk_tile", E.opt_chunk_tile}, {"ws", E.opt_ws}, {"sp2i", E.opt_sp2i}, {"fuse_reduce", E.opt_fuse_reduce}, {"raw_result", E.opt_raw_result}, {"raw_upload", E.opt_raw_upload}, {"walk_compact", E.opt_walk_compact}, {"ep_runs", E.opt_ep_runs}, {"lead", E.opt_lead}, {"occupancy", E.opt_occ}, {"nr", E.opt_nr}};
     for (const auto& t : tab)
         if (!strcmp(key, t.k)) { *v = t.val; return PB_OK; }
     return fail(PB_ERR_ARG, "pb_get_option: unknown key '%s'", key);
@@ -2013,6 +2020,8 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
         CU(cudaMalloc(&E.d_r_out, sizeof(ForceOut) * E.cap_r_i));
         CU(cudaMallocHost(&E.h_r_out, sizeof(ForceOut) * E.cap_r_i));
         CU(cudaMalloc(&E.d_r_iblocks, sizeof(IBlock) * (E.cap_r_i / 32 + E.cap_r_groups + 1024)));
+        if (E.d_r_done) CU(cudaFree(E.d_r_done));
+        CU(cudaMalloc(&E.d_r_done, sizeof(int) * (E.cap_r_i / 32 + E.cap_r_groups + 1024)));
     }
     if ((size_t)E.r_n_iblk > E.cap_r_i / 32 + E.cap_r_groups + 1024) return fail(PB_ERR_ARG, "pb_tree_force_resident: i-block table too small");
     if (!E.d_r_meta) { CU(cudaMalloc(&E.d_r_meta, 8 * sizeof(int))); CU(cudaMallocHost(&E.h_r_meta, 8 * sizeof(int))); }
@@ -2069,6 +2078,18 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
     Plan pl; pl.coords = coords; pl.i_f4 = i_f4; pl.count_only = 0;
     Params prm = make_params(pl, nullptr);
     prm.meta = E.d_r_meta;
+    const bool fuse = E.opt_ws && E.opt_fuse_reduce;       // the force kernel reduces and writes the forces into h_r_out itself
+    const bool plain = L.stride == sizeof(ForceOut) && L.off_acc == 0 && L.off_pot == 24 && L.off_nngb == 32;
+    bool direct = false;                                   // the kernel writes into the caller's array (option raw_result)
+    if (fuse) {
+        CU(cudaMemsetAsync(E.d_r_done, 0, sizeof(int) * (size_t)E.r_n_iblk, s0));
+        prm.iblocks = E.d_r_iblocks; prm.done = E.d_r_done; prm.out = E.h_r_out; prm.G = E.G;
+        if (E.opt_raw_result && plain && ensure_registered(force, sizeof(ForceOut) * (size_t)E.r_n_i)) {
+            void* dp = nullptr;
+            if (cudaHostGetDevicePointer(&dp, force, 0) == cudaSuccess && dp) { prm.out = (ForceOut*)dp; direct = true; }
+            else cudaGetLastError();
+        }
+    }
     if (E.opt_ws)
         CU(launch_force_ws(s0, 2 * 148, E.opt_nr, E.d_r_walks, E.d_r_tasks, E.d_r_epi, E.d_tree_ide, E.d_tree_ids, E.d_epj, E.d_spj,
                            E.d_r_part4, E.d_r_partn, prm, E.opt_sp2i != 0));
@@ -2076,9 +2097,9 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
         CU(launch_force_persistent(s0, 2 * 148, E.opt_nr, E.d_r_walks, E.d_r_tasks, E.d_r_epi, E.d_tree_ide, E.d_tree_ids, E.d_epj, E.d_spj,
                                    E.d_r_part4, E.d_r_partn, prm, E.opt_sp2i != 0));
     CU(cudaEventRecord(E.ev_tl[4], s0));
-    CU(launch_reduce(s0, E.r_n_iblk, E.d_r_iblocks, E.d_r_part4, E.d_r_partn, E.d_r_out, E.G, E.d_r_meta));
+    if (!fuse) CU(launch_reduce(s0, E.r_n_iblk, E.d_r_iblocks, E.d_r_part4, E.d_r_partn, E.d_r_out, E.G, E.d_r_meta));
     CU(cudaEventRecord(E.ev_tl[5], s0));
-    CU(cudaMemcpyAsync(E.h_r_out, E.d_r_out, sizeof(ForceOut) * (size_t)E.r_n_i, cudaMemcpyDeviceToHost, s0));
+    if (!fuse) CU(cudaMemcpyAsync(E.h_r_out, E.d_r_out, sizeof(ForceOut) * (size_t)E.r_n_i, cudaMemcpyDeviceToHost, s0));
     CU(cudaMemcpyAsync(E.h_r_meta, E.d_r_meta, 8 * sizeof(int), cudaMemcpyDeviceToHost, s0));
     CU(cudaMemcpyAsync(E.h_counts_p, E.d_counts, sizeof(int2) * (size_t)ng, cudaMemcpyDeviceToHost, s0));
     CU(cudaMemcpyAsync(E.h_over_p, E.d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, s0));
@@ -2104,10 +2125,11 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
 
     // forces back to the caller's array (group order)
     const double t0 = now_s();
-    const bool plain = L.stride == sizeof(ForceOut) && L.off_acc == 0 && L.off_pot == 24 && L.off_nngb == 32;
     const long long n = E.r_n_i;
     char* dst = (char*)force;
-    if (plain) {
+    if (direct) {
+        // already there
+    } else if (plain) {
         const long long chunk = 1 << 15;
 #pragma omp parallel for schedule(static)
         for (long long c = 0; c < (n + chunk - 1) / chunk; c++)

@@ -61,9 +61,50 @@ __device__ __forceinline__ void producer_bar() {           // the producer warps
     asm volatile("bar.sync 2, %0;" :: "n"(kWsProducers * 32) : "memory");
 }
 
+// Fused reduction.  The warp that has just written the partial sums of an i-block for one chunk counts the chunk in (one
+// release-acquire atomic by lane 0).  The warp that delivered the block's LAST chunk adds all of them in chunk order (fixed
+// order: bitwise reproducible whoever comes last), applies G and writes the 32 ForceSoft-shaped records — into page-locked
+// host memory, so no reduction kernel and no D2H copy follow the force kernel.  The 40-byte records leave as five coalesced
+// 256-byte stores.  reduce_block is a real call: its registers must not weigh on the pair loops.
+__device__ __noinline__ void reduce_block(int bi, int lane, const double4* part4, const int* partn, const IBlock* iblocks, ForceOut* out, int* done, double G) {
+    const IBlock B = iblocks[bi];
+    double ax = 0.0, ay = 0.0, az = 0.0, pt = 0.0;
+    long long n = 0;
+#pragma unroll 4
+    for (int c = 0; c < B.n_chunks; ++c) {
+        const int slot = B.part_base + c * B.stride + lane;
+        const double2* q = reinterpret_cast<const double2*>(part4 + slot);
+        const double2 v0 = __ldcg(q), v1 = __ldcg(q + 1);
+        ax += v0.x; ay += v0.y; az += v1.x; pt += v1.y;
+        n += __ldcg(partn + slot);
+    }
+    const double f[5] = {G * ax, G * ay, G * az, -(G * pt), __longlong_as_double(n)};
+    double* o = reinterpret_cast<double*>(out + B.out_off);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int k = lane + 32 * j, src = k / 5, fld = k - 5 * src;   // 8-byte word k of the block's 160: particle src, field fld
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const double t = __shfl_sync(0xffffffffu, f[q], src);
+            if (q == fld) v = t;
+        }
+        if (src < B.n_valid) o[k] = v;
+    }
+    if (lane == 0) done[bi] = 0;                              // ready for the next step
+}
+
+__device__ __forceinline__ void finish_block(int bi, int nch, int lane, const double4* part4, const int* partn, const Params& prm) {
+    __syncwarp();                                             // the lanes' partial-sum stores are ordered before lane 0's release
+    int old = 0;
+    if (lane == 0) asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(prm.done + bi) : "memory");
+    const int last = __shfl_sync(0xffffffffu, (int)(old + 1 == nch), 0);      // ... and lane 0's acquire before the other lanes' loads
+    if (last) reduce_block(bi, lane, part4, partn, prm.iblocks, prm.out, prm.done, prm.G);
+}
+
 } // namespace
 
-template <int NR, int TWOI>
+template <int NR, int TWOI, int FUSE>
 __global__ void __maxnreg__(96)
 force_kernel_ws(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 const float4* __restrict__ epi,
@@ -101,7 +142,7 @@ force_kernel_ws(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             producer_bar();                                                    // task number visible to every producer warp
             const int t = ctl.next_task[ts];
             Task task;
-            if (t < n_tasks) task = tasks[t]; else { task.kind = -1; task.walk = 0; task.j_count = 0; task.j_begin = 0; task.nib = 1; task.jsplit = 8; task.i_first = 0; task.part_base = 0; }
+            if (t < n_tasks) task = tasks[t]; else { task.kind = -1; task.walk = 0; task.j_count = 0; task.j_begin = 0; task.nib = 1; task.jsplit = 8; task.i_first = 0; task.part_base = 0; task.blk0 = 0; }
             Walk w;
             if (t < n_tasks) w = walks[task.walk];
             if (pw == 0) {
@@ -281,6 +322,10 @@ force_kernel_ws(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 partn[slot + npair * 32] = 0;
             }
             compute_bar();                                  // scratch free for the next task
+            if (FUSE && js2 == 0) {
+                finish_block(task.blk0 + b0, task.n_chunks, lane, part4, partn, prm);
+                finish_block(task.blk0 + b0 + npair, task.n_chunks, lane, part4, partn, prm);
+            }
             continue;
         } else {
             for (int k = 0; k < n_tiles; ++k, ++g) {
@@ -328,6 +373,7 @@ force_kernel_ws(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
             part4[slot] = make_double4(dax, day, daz, dpt);
             partn[slot] = cnt;
         }
+        if (FUSE && js == 0) finish_block(task.blk0 + ib, task.n_chunks, lane, part4, partn, prm);
     }
 }
 
@@ -342,16 +388,23 @@ cudaError_t launch_force_ws(cudaStream_t s, int n_ctas, int nr_steps,
     const size_t smem = ws_smem_bytes();
     if (!configured) {
         cudaError_t e = cudaSuccess;
-        const void* fns[] = {(const void*)force_kernel_ws<0, 0>, (const void*)force_kernel_ws<1, 0>, (const void*)force_kernel_ws<0, 1>, (const void*)force_kernel_ws<1, 1>};
+        const void* fns[] = {(const void*)force_kernel_ws<0, 0, 0>, (const void*)force_kernel_ws<1, 0, 0>, (const void*)force_kernel_ws<0, 1, 0>, (const void*)force_kernel_ws<1, 1, 0>,
+                             (const void*)force_kernel_ws<0, 0, 1>, (const void*)force_kernel_ws<1, 0, 1>, (const void*)force_kernel_ws<0, 1, 1>, (const void*)force_kernel_ws<1, 1, 1>};
         for (const void* f : fns)
             if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-#define PB_WS_LAUNCH(NR_, TI_) force_kernel_ws<NR_, TI_><<<n_ctas, kWsThreads, smem, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p)
+#define PB_WS_LAUNCH(NR_, TI_, FU_) force_kernel_ws<NR_, TI_, FU_><<<n_ctas, kWsThreads, smem, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p)
     const int nr = nr_steps >= 1 ? 1 : 0;
-    if (two_i) { if (nr) PB_WS_LAUNCH(1, 1); else PB_WS_LAUNCH(0, 1); }
-    else       { if (nr) PB_WS_LAUNCH(1, 0); else PB_WS_LAUNCH(0, 0); }
+    const bool fuse = p.out != nullptr;                   // fused reduction: Params carries the i-block table, counters and the result array
+    if (fuse) {
+        if (two_i) { if (nr) PB_WS_LAUNCH(1, 1, 1); else PB_WS_LAUNCH(0, 1, 1); }
+        else       { if (nr) PB_WS_LAUNCH(1, 0, 1); else PB_WS_LAUNCH(0, 0, 1); }
+    } else {
+        if (two_i) { if (nr) PB_WS_LAUNCH(1, 1, 0); else PB_WS_LAUNCH(0, 1, 0); }
+        else       { if (nr) PB_WS_LAUNCH(1, 0, 0); else PB_WS_LAUNCH(0, 0, 0); }
+    }
 #undef PB_WS_LAUNCH
     return cudaGetLastError();
 }

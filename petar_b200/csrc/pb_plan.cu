@@ -184,6 +184,8 @@ emit_kernel(const pb_tree_group* __restrict__ groups, int n_groups, const int* _
         if (nib_left >= kWarpsPerCta) nib = kWarpsPerCta;
         else { nib = kWarpsPerCta / 2; while (!(nib_left & nib)) nib >>= 1; }
         const int jsplit = kWarpsPerCta / nib, stride = nib * 32, part_base = part;
+        int n_chunks_grp;
+        { int ce, cs, l; chunking(nej, U, jsplit, ce, l); chunking(nsj, Us, jsplit, cs, l); n_chunks_grp = ce + cs; }
         int chunk = 0;
         for (int kind = 0; kind < 2; kind++) {
             const int nj = kind == 0 ? nej : nsj;
@@ -193,6 +195,7 @@ emit_kernel(const pb_tree_group* __restrict__ groups, int n_groups, const int* _
                 Task T;
                 T.walk = g; T.i_first = ib * 32; T.nib = nib; T.jsplit = jsplit; T.kind = kind;
                 T.j_begin = c * len; T.j_count = min(len, nj - c * len); T.part_base = part_base + chunk * stride;
+                T.blk0 = ib_out; T.n_chunks = n_chunks_grp; T.pad1 = T.pad2 = 0;
                 tasks[t++] = T;
                 chunk++;
             }

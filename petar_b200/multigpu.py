@@ -170,6 +170,7 @@ class DomainStepper:
         if device:
             # several ranks share the node's host cores: this rank's own j-particles travel raw and are packed on the GPU
             engine.set_option("raw_upload", int(os.environ.get("PETAR_B200_RAW_UPLOAD", "1")))
+            engine.set_option("raw_result", int(os.environ.get("PETAR_B200_RAW_RESULT", "1")))
         pin = device
         self.h_send_ep = torch.empty((len(self.send_idx), 8), dtype=torch.float32, pin_memory=pin)
         self.h_send_sp = torch.empty((len(self.send_sp), 16), dtype=torch.float32, pin_memory=pin)

@@ -10,8 +10,8 @@ f = engine.calc_force_all_and_write_back(batch, prm["eps"], prm["r_out"], prm["G
 g = engine.tree_neighbor_search(batch, n_walk_limit=16)
 cells, groups = batch.tree.export_tree()
 h = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"])
-for ws, sp2i in ((0, 0), (0, 1), (1, 0), (1, 1)):  # device-resident step with every persistent kernel variant: first exact, then speculative
-    engine.set_option("ws", ws); engine.set_option("sp2i", sp2i)
+for ws, sp2i, fuse in ((0, 0, 0), (0, 1, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1)):  # device-resident step with every persistent kernel variant: first exact, then speculative
+    engine.set_option("ws", ws); engine.set_option("sp2i", sp2i); engine.set_option("fuse_reduce", fuse)
     for _ in range(2):
         hr = engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], resident=True)
     assert np.array_equal(hr["n_ngb"], h["n_ngb"])
