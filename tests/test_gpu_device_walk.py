@@ -269,3 +269,31 @@ def test_compact_walk_records_give_identical_lists_in_identical_order():
             assert np.array_equal(a, b), name
         assert f0.tobytes() == f1.tobytes(), name
         print(f"[compact walk, {name}] {len(groups)} groups, {int(l1[0].sum())} EP + {int(l1[1].sum())} SP list entries identical")
+
+
+def test_fused_reduction_and_direct_result_write_are_bitwise_equivalent():
+    """Options fuse_reduce (the force kernel adds up finished i-blocks and writes the forces into page-locked host memory) and
+    raw_result (... into the caller's own array): the same partial sums are added in the same chunk order whoever delivers
+    the last one, so every combination returns the same bytes as reduction kernel + D2H copy; both kernel variants; ragged
+    walks; repeated steps (the chunk counters return to zero)."""
+    batch, prm, cells, groups = _case("kroupa_binaries", 20000)
+    out = {}
+    f = np.zeros(batch.n_epi_total, dtype=engine.ForceSoft)
+    try:
+        for ws, sp2i in ((1, 1), (1, 0)):
+            for fuse, raw in ((0, 0), (1, 0), (1, 1)):
+                engine.set_option("ws", ws); engine.set_option("sp2i", sp2i)
+                engine.set_option("fuse_reduce", fuse); engine.set_option("raw_result", raw)
+                for _ in range(3):                                  # exact first step, then speculative ones
+                    f[:] = 0
+                    engine.tree_force(batch, cells, groups, prm["eps"], prm["r_out"], prm["G"], force=f, resident=True)
+                out[(ws, sp2i, fuse, raw)] = f.copy()
+    finally:
+        engine.set_option("ws", 1); engine.set_option("sp2i", 1); engine.set_option("fuse_reduce", 1); engine.set_option("raw_result", 0)
+    for ws, sp2i in ((1, 1), (1, 0)):
+        base = out[(ws, sp2i, 0, 0)]
+        assert np.abs(base["acc"]).max() > 0
+        assert out[(ws, sp2i, 1, 0)].tobytes() == base.tobytes()
+        assert out[(ws, sp2i, 1, 1)].tobytes() == base.tobytes()
+    ref = ob.walks_index(batch, prm["eps"], prm["r_out"], prm["G"])
+    assert np.array_equal(out[(1, 1, 1, 1)]["n_ngb"], ref["n_ngb"])
