@@ -73,12 +73,12 @@ summary = ["# Round-2 ncu summary (B200, `--clock-control none`; per-launch time
 t = raw_table("z_prof_force.ncu-rep", "r2_ncu_force_kernel_N1e6.csv")
 if t:
     rd, wr = col(t, "dram__bytes_read.sum"), col(t, "dram__bytes_write.sum")
-    traffic = {"kernel": "pb::force_kernel<0,2,false,false>",
+    traffic = {"kernel": "pb::force_kernel<0,2,false,false,true>",
                "source": f"ncu --set full --clock-control none, {len(rd)} launches of `bench.py --steps 1 --warmup 1 --no-device-walk` (default workload: N=1e6 Kroupa Plummer, "
                          "10% binaries; 8 streams, so one launch = one of the 8 sub-batches of a 200-walk dispatch); summary in profiles/r2_ncu_force_kernel_N1e6.csv",
                "dram_bytes_per_launch": int((sum(rd) + sum(wr)) / len(rd)), "dram_bytes_read_per_launch": int(sum(rd) / len(rd)), "dram_bytes_write_per_launch": int(sum(wr) / len(wr)),
                "note": "cold-L2 figure of an isolated, profiled launch: the j store (71 MB for the whole step) and the index lists of the launch's walks are fetched from DRAM "
-                       "again for every profiled launch, partial sums stay in L2. The algorithmic input of one launch is ~1.2 MB (0.55 GB H2D per step / 448 launches), so the "
+                       "again for every profiled launch, partial sums stay in L2. The algorithmic input of one launch is ~1.7 MB (0.76 GB H2D per step / 448 launches), so the "
                        "profiled traffic is ~3x that; at < 1 % of DRAM throughput it has no bearing on the bound."}
     json.dump(traffic, open(os.path.join(P, "r2_force_kernel_traffic.json"), "w"), indent=1)
     st = stalls("z_prof_force.ncu-rep")
@@ -122,8 +122,10 @@ if os.path.exists(src):
         agg[n][0] += 1; agg[n][1] += v
     tot = sum(v[1] for v in agg.values())
     summary.append("## Launch list of `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity` (ncu --metrics gpu__time_duration.sum, -c 6000)\n")
-    summary.append("The command runs, per warm-up / timed iteration, one device-resident replay (448 force + 448 reduce launches), its force-only timing pass (448), one functor step "
-                   "(448 + 448 + 448 run-expansion launches) and one device-resident tree step (walk, compact, i-prep, plan, emit, ONE persistent force launch, reduce), plus the recording step.\n")
+    summary.append("The command runs, per warm-up / timed iteration, one replay of the recorded functor step (448 force + 448 reduce launches), its force-only timing pass (448), one functor step "
+                   "(448 + 448) and one device-resident tree step (compact, walk, i-prep, plan, emit and ONE persistent force launch that also reduces and writes the forces to host memory), "
+                   "plus the recording step: 7 x 448 force, 5 x 448 reduce, 2 persistent launches.  In one tree step of the product path the force kernel is > 99 % of the kernel time "
+                   "either way (`value`: 448 launches, 26.0 ms of 26.1; `e2e`: one launch, 25.3 ms beside 2.6 ms of walk).\n")
     summary.append("| kernel | launches | total ms (under ncu) | share |\n|---|---|---|---|")
     for n, (c, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         summary.append(f"| `{n}` | {c} | {tt / 1e6:.3f} | {100 * tt / tot:.1f} % |")
