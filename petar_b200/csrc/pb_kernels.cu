@@ -29,7 +29,7 @@ namespace pb {
 // ------------------------------------------------------------------------------------------
 // Index tiles through TMA: a chunk's index list is contiguous and 16-byte aligned, so each 1 KB
 // tile of it is one `cp.async.bulk` (1-D TMA bulk copy, SASS UBLKCP) into a 3-deep shared-memory
-// ring, completion signalled on an mbarrier — issued by one thread three tiles ahead, no
+// ring, completion signalled on an mbarrier — issued by one thread up to four tiles ahead of the tile being computed, no
 // registers held, no per-thread global loads.  (The j records themselves are an indexed gather
 // and stay 16-byte loads from L2.)  PB_TMA_IDS=0 builds the plain-load variant.
 // ------------------------------------------------------------------------------------------
