@@ -124,7 +124,7 @@ cudaError_t launch_force_ws(cudaStream_t s, int n_ctas, int nr_steps,
 cudaError_t launch_iprep(cudaStream_t s, const void* groups, int n_groups, const int* i_first, const int2* counts, const int2* offs,
                          const float4* epj, Walk* walks, float4* epi, int i_f4, int coords, int cull);
 cudaError_t launch_devplan(cudaStream_t s, const void* groups, int n_groups, const int* i_first, const int2* counts, int U, int Us,
-                           int3* goff, int* meta, int cap_tasks, long long cap_part, Task* tasks, IBlock* iblocks, const int2* caps);
+                           int3* goff, int* meta, int cap_tasks, long long cap_part, Task* tasks, IBlock* iblocks, const int2* caps, ForceOut* out_fused);
 // device-side packing of raw host arrays (pb_pack.cu, option "raw_upload")
 cudaError_t launch_pack_epj(cudaStream_t s, const void* raw, size_t stride, size_t off_pos, size_t off_mass, size_t off_rs, int n, float4* out);
 cudaError_t launch_pack_spj(cudaStream_t s, const void* raw, size_t stride, size_t off_pos, size_t off_mass, size_t off_quad, int has_quad, int n, float4* out);

@@ -2069,26 +2069,32 @@ int resident_run(void* force, const pb_layout_force& L, bool exact) {
         CU(cudaMalloc(&E.d_r_partn, sizeof(int) * E.cap_r_part));
     }
 
+    // fused reduction: the force kernel reduces finished i-blocks and writes the forces into page-locked host memory itself
+    const bool fuse = E.opt_ws && E.opt_fuse_reduce;
+    const bool plain = L.stride == sizeof(ForceOut) && L.off_acc == 0 && L.off_pot == 24 && L.off_nngb == 32;
+    bool direct = false;                                   // ... into the caller's own array (option raw_result)
+    ForceOut* out_fused = nullptr;
+    if (fuse) {
+        out_fused = E.h_r_out;
+        if (E.opt_raw_result && plain && ensure_registered(force, sizeof(ForceOut) * (size_t)E.r_n_i)) {
+            void* dp = nullptr;
+            if (cudaHostGetDevicePointer(&dp, force, 0) == cudaSuccess && dp) { out_fused = (ForceOut*)dp; direct = true; }
+            else cudaGetLastError();
+        }
+    }
+
     CU(cudaStreamWaitEvent(s0, E.ev_j_ready, 0));          // this step's j (local upload + whatever a collective wrote) is in place
     CU(cudaEventRecord(E.ev_tl[2], s0));
     CU(launch_iprep(s0, E.d_groups, ng, E.d_ifirst, E.d_counts, E.d_tree_off, E.d_epj, E.d_r_walks, E.d_r_epi, i_f4, coords, E.opt_cull));
     CU(launch_devplan(s0, E.d_groups, ng, E.d_ifirst, E.d_counts, U, Us, E.d_r_goff, E.d_r_meta,
-                   (int)std::min<size_t>(E.cap_r_tasks, 0x7fffffff), (long long)E.cap_r_part, E.d_r_tasks, E.d_r_iblocks, d_caps));
+                   (int)std::min<size_t>(E.cap_r_tasks, 0x7fffffff), (long long)E.cap_r_part, E.d_r_tasks, E.d_r_iblocks, d_caps, out_fused));
     CU(cudaEventRecord(E.ev_tl[3], s0));
     Plan pl; pl.coords = coords; pl.i_f4 = i_f4; pl.count_only = 0;
     Params prm = make_params(pl, nullptr);
     prm.meta = E.d_r_meta;
-    const bool fuse = E.opt_ws && E.opt_fuse_reduce;       // the force kernel reduces and writes the forces into h_r_out itself
-    const bool plain = L.stride == sizeof(ForceOut) && L.off_acc == 0 && L.off_pot == 24 && L.off_nngb == 32;
-    bool direct = false;                                   // the kernel writes into the caller's array (option raw_result)
     if (fuse) {
         CU(cudaMemsetAsync(E.d_r_done, 0, sizeof(int) * (size_t)E.r_n_iblk, s0));
-        prm.iblocks = E.d_r_iblocks; prm.done = E.d_r_done; prm.out = E.h_r_out; prm.G = E.G;
-        if (E.opt_raw_result && plain && ensure_registered(force, sizeof(ForceOut) * (size_t)E.r_n_i)) {
-            void* dp = nullptr;
-            if (cudaHostGetDevicePointer(&dp, force, 0) == cudaSuccess && dp) { prm.out = (ForceOut*)dp; direct = true; }
-            else cudaGetLastError();
-        }
+        prm.iblocks = E.d_r_iblocks; prm.done = E.d_r_done; prm.out = out_fused; prm.G = E.G;
     }
     if (E.opt_ws)
         CU(launch_force_ws(s0, 2 * 148, E.opt_nr, E.d_r_walks, E.d_r_tasks, E.d_r_epi, E.d_tree_ide, E.d_tree_ids, E.d_epj, E.d_spj,

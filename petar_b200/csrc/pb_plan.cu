@@ -171,7 +171,7 @@ plan_kernel(const pb_tree_group* __restrict__ groups, int n_groups, const int2* 
 __global__ void __launch_bounds__(128)
 emit_kernel(const pb_tree_group* __restrict__ groups, int n_groups, const int* __restrict__ i_first,
             const int2* __restrict__ counts, const int3* __restrict__ goff, const int* __restrict__ meta,
-            int U, int Us, Task* __restrict__ tasks, IBlock* __restrict__ iblocks)
+            int U, int Us, Task* __restrict__ tasks, IBlock* __restrict__ iblocks, ForceOut* __restrict__ out_fused)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups || meta[3] != 0) return;
@@ -206,6 +206,10 @@ emit_kernel(const pb_tree_group* __restrict__ groups, int n_groups, const int* _
             B.out_off = i0 + (ib + b) * 32; B.n_valid = min(32, ni - (ib + b) * 32);
             B.pad0 = B.pad1 = B.pad2 = 0;
             iblocks[ib_out++] = B;
+            if (chunk == 0 && out_fused) {                 // a group without any list entry: nobody will deliver a last chunk (fused reduction)
+                ForceOut z; z.ax = z.ay = z.az = z.pot = 0.0; z.n_ngb = 0;
+                for (int l = 0; l < B.n_valid; l++) out_fused[B.out_off + l] = z;
+            }
         }
         part += chunk * stride;
         ib += nib; nib_left -= nib;
@@ -220,10 +224,10 @@ cudaError_t launch_iprep(cudaStream_t s, const void* groups, int n_groups, const
 }
 
 cudaError_t launch_devplan(cudaStream_t s, const void* groups, int n_groups, const int* i_first, const int2* counts, int U, int Us,
-                           int3* goff, int* meta, int cap_tasks, long long cap_part, Task* tasks, IBlock* iblocks, const int2* caps) {
+                           int3* goff, int* meta, int cap_tasks, long long cap_part, Task* tasks, IBlock* iblocks, const int2* caps, ForceOut* out_fused) {
     if (n_groups <= 0) return cudaSuccess;
     plan_kernel<<<1, 1024, 0, s>>>((const pb_tree_group*)groups, n_groups, counts, U, Us, goff, meta, cap_tasks, cap_part, caps);
-    emit_kernel<<<(n_groups + 127) / 128, 128, 0, s>>>((const pb_tree_group*)groups, n_groups, i_first, counts, goff, meta, U, Us, tasks, iblocks);
+    emit_kernel<<<(n_groups + 127) / 128, 128, 0, s>>>((const pb_tree_group*)groups, n_groups, i_first, counts, goff, meta, U, Us, tasks, iblocks, out_fused);
     return cudaGetLastError();
 }
 
