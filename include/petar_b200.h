@@ -162,10 +162,12 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *   "ws"         1 (default): persistent force launches (the device-resident tree step) run the warp-specialised kernel —
  *                8 compute warps that only wait for tiles and run the pair loops, 2 producer warps that fetch tasks and
  *                stage j tiles four deep (pb_kernels_ws.cu); 0: every warp stages and computes (pb::force_kernel).
- *   "fuse_reduce" 1 (default): in the device-resident tree step the warp that delivers the last partial sum of a 32-particle
- *                block adds the block's partial sums (fixed chunk order: bitwise equal to the separate reduction kernel) and
- *                writes the 32 force records itself — into page-locked HOST memory, so neither a reduction kernel nor a D2H
- *                copy follows the force kernel (-0.9 ms per tree step at N = 1e6).  0: reduction kernel + D2H copy.
+ *   "fuse_reduce" 1 (default): the warp that delivers the last partial sum of a 32-particle block adds the block's partial sums
+ *                (fixed chunk order: bitwise equal to the separate reduction kernel) and writes the 32 force records itself —
+ *                into page-locked HOST memory, so neither a reduction kernel nor a D2H copy follows the force kernel.
+ *                Device-resident tree step: -0.9 ms per step at N = 1e6; functor path (force dispatches, not the neighbour
+ *                search): 46.0 -> 43.2 ms per tree step (two launches / copies fewer per stream and dispatch), at +0.7 %
+ *                kernel time.  0: reduction kernel + D2H copy.
  *   "raw_result" 1: pb_tree_force_resident page-locks the caller's force array once (it must be the same array from step to
  *                step, as FDPS's is, and in the plain ForceSoft layout) and the kernel writes into it directly; 0
  *                (default): into the library's pinned buffer, copied to the caller's array by the host threads.

@@ -69,7 +69,7 @@ struct Plan {                // layout of one sub-batch inside an arena
     int    n_walk = 0, n_tasks = 0, n_iblocks = 0;
     size_t n_i = 0, n_ide = 0, n_ids = 0, n_part = 0;
     size_t n_lepj = 0, n_lspj = 0;            // direct mode: dispatch-local j store entries
-    size_t off_walks = 0, off_tasks = 0, off_iblocks = 0, off_epi = 0, off_ide = 0, off_ids = 0;
+    size_t off_walks = 0, off_tasks = 0, off_iblocks = 0, off_done = 0, off_epi = 0, off_ide = 0, off_ids = 0;
     size_t off_lepj = 0, off_lspj = 0, bytes = 0;
     int    count_only = 0;                    // neighbour search only: EP lists as kind-2 tasks, no SP, eps2 = 0
     int    coords = 0, i_f4 = 2;              // option "coords" the sub-batch was packed for; float4 per packed i-particle
@@ -392,11 +392,12 @@ struct HostPlan {
     bool use_runs = false;                    // index mode: the EP lists travel run-length coded
     long long run_cursor = 0;                 // runs appended so far to the arena's run section (walks are packed concurrently: atomic adds)
     std::vector<int2> runtab;                 // per walk {first run, number of runs}
+    std::vector<std::pair<size_t, int>> zero_blocks;   // {first i, count} of block groups without any chunk (fused reduction: zeroed on the host)
 };
 
 void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active, HostPlan& hp, const int2* ext_off = nullptr) {
     hp.walks.resize(n_walk);
-    hp.tasks.clear(); hp.iblocks.clear();
+    hp.tasks.clear(); hp.iblocks.clear(); hp.zero_blocks.clear();
     hp.lepj_off.assign(n_walk, 0); hp.lspj_off.assign(n_walk, 0);
     std::vector<Group> groups;
     size_t i_off = 0, ide = 0, ids = 0, lepj = 0, lspj = 0;
@@ -461,6 +462,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
             }
         }
         for (int c = 0; c < chunk; c++) hp.tasks[hp.tasks.size() - 1 - c].n_chunks = chunk;
+        if (chunk == 0) hp.zero_blocks.push_back({(size_t)W.i_off + g.i_first, std::min(g.nib * 32, W.ni - g.i_first)});
         for (int b = 0; b < g.nib; b++) {
             IBlock ib;
             ib.part_base = part_base + b * 32;
@@ -492,6 +494,7 @@ void plan_batch(const WalkIn* win, int n_walk, bool direct, int n_streams_active
     p.off_walks = o;   o = align_up(o + sizeof(Walk) * n_walk, 256);
     p.off_tasks = o;   o = align_up(o + sizeof(Task) * p.n_tasks, 256);
     p.off_iblocks = o; o = align_up(o + sizeof(IBlock) * p.n_iblocks, 256);
+    p.off_done = o;    o = align_up(o + sizeof(int) * p.n_iblocks, 256);     // chunk counters of the fused reduction: travel as zeros, return to zero
     p.off_runtab = o;  o = align_up(o + (hp.use_runs ? sizeof(int2) * (size_t)n_walk : 0), 256);
     p.off_epi = o;     o = align_up(o + (size_t)p.i_f4 * sizeof(float4) * p.n_i, 256);
     p.off_ide = o;     o = align_up(o + sizeof(int) * p.n_ide, 256);
@@ -601,6 +604,7 @@ void pack_tail(const WalkIn* win, bool direct, const pb_layout_epj* Lj, const pb
     memcpy(arena + p.off_walks, hp.walks.data(), sizeof(Walk) * hp.walks.size());
     memcpy(arena + p.off_tasks, hp.tasks.data(), sizeof(Task) * hp.tasks.size());
     memcpy(arena + p.off_iblocks, hp.iblocks.data(), sizeof(IBlock) * hp.iblocks.size());
+    memset(arena + p.off_done, 0, sizeof(int) * hp.iblocks.size());
     if (hp.use_runs) memcpy(arena + p.off_runtab, hp.runtab.data(), sizeof(int2) * hp.runtab.size());
 }
 
@@ -633,9 +637,16 @@ Params make_params(const Plan& p, const Slot* emit) {
     return prm;
 }
 
-cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, bool direct,
-                        double4* part4, int* partn, ForceOut* out, bool force_only = false, const Slot* emit = nullptr) {
+// the force kernel reduces finished i-blocks itself and writes the forces to `out_host` (page-locked, device-visible)
+bool plan_fused(const Plan& p, const Slot* emit) { return E.opt_fuse_reduce && !p.count_only && !emit && E.opt_occ < 3; }
+
+cudaError_t launch_plan(cudaStream_t st, const Plan& p, char* d_arena, bool direct,
+                        double4* part4, int* partn, ForceOut* out, ForceOut* out_host, bool force_only = false, const Slot* emit = nullptr) {
     Params prm = make_params(p, emit);
+    const bool fuse = plan_fused(p, emit) && out_host;
+    if (fuse) {
+        prm.iblocks = (const IBlock*)(d_arena + p.off_iblocks); prm.done = (int*)(d_arena + p.off_done); prm.out = out_host; prm.G = E.G;
+    }
     const float4* epj = direct ? (const float4*)(d_arena + p.off_lepj) : E.d_epj;
     const float4* spj = direct ? (const float4*)(d_arena + p.off_lspj) : E.d_spj;
     cudaError_t e = launch_force(st, p.n_tasks, E.opt_nr, E.opt_occ,
@@ -644,7 +655,7 @@ cudaError_t launch_plan(cudaStream_t st, const Plan& p, const char* d_arena, boo
                                  p.ext_ide ? p.ext_ide : (const int*)(d_arena + p.off_ide),
                                  p.ext_ids ? p.ext_ids : (const int*)(d_arena + p.off_ids),
                                  epj, spj, part4, partn, prm, emit != nullptr, E.opt_sp2i != 0);
-    if (e != cudaSuccess || force_only) return e;
+    if (e != cudaSuccess || force_only || fuse) return e;
     return launch_reduce(st, p.n_iblocks, (const IBlock*)(d_arena + p.off_iblocks), part4, partn, out, E.G);
 }
 
@@ -658,7 +669,7 @@ int collect_pairs_begin(Slot& S, size_t n_i_dispatch) {
         if (rc != PB_OK) return rc;
         CU(cudaMemsetAsync(S.d_cursor, 0, sizeof(unsigned int), S.stream));
         CU(cudaMemsetAsync(S.d_pairs, 0xff, sizeof(unsigned long long) * S.n_pairs_window, S.stream));
-        CU(launch_plan(S.stream, S.plan, S.d_arena, false, S.d_part4, S.d_partn, S.d_out, true, &S));
+        CU(launch_plan(S.stream, S.plan, S.d_arena, false, S.d_part4, S.d_partn, S.d_out, nullptr, true, &S));
         CU(sort_pairs(S, n_i_dispatch));
         CU(cudaMemcpyAsync(S.h_cursor, S.d_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
         CU(cudaStreamSynchronize(S.stream));
@@ -789,7 +800,10 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
             S.plan.ext_ide = S.d_ide_x;
             E.prof.n_kernel_launch += 1;
         }
-        CU(launch_plan(S.stream, S.plan, S.d_arena, direct, S.d_part4, S.d_partn, S.d_out, false, S.emit ? &S : nullptr));
+        const bool fused = plan_fused(S.plan, S.emit ? &S : nullptr);
+        if (fused)                                          // blocks nobody will deliver a chunk for (walks with two empty lists)
+            for (const auto& z : hp[s].zero_blocks) memset(S.h_out + z.first, 0, sizeof(ForceOut) * (size_t)z.second);
+        CU(launch_plan(S.stream, S.plan, S.d_arena, direct, S.d_part4, S.d_partn, S.d_out, S.h_out, false, S.emit ? &S : nullptr));
         CU(cudaEventRecord(S.ev[2], S.stream));
         if (s == last_active) CU(cudaEventRecord(E.ev_end[E.end_cur], S.stream));
         if (S.emit) {
@@ -797,11 +811,11 @@ int dispatch_common(int n_walk, const WalkIn* win, bool direct, const pb_layout_
             CU(cudaMemcpyAsync(S.h_cursor, S.d_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, S.stream));
             E.prof.n_kernel_launch += 1;
         }
-        CU(cudaMemcpyAsync(S.h_out, S.d_out, sizeof(ForceOut) * S.plan.n_i, cudaMemcpyDeviceToHost, S.stream));
+        if (!fused) CU(cudaMemcpyAsync(S.h_out, S.d_out, sizeof(ForceOut) * S.plan.n_i, cudaMemcpyDeviceToHost, S.stream));
         CU(cudaEventRecord(S.ev[3], S.stream));
         E.prof.h2d_bytes += (long long)S.plan.bytes;
         E.prof.d2h_bytes += (long long)(sizeof(ForceOut) * S.plan.n_i);
-        E.prof.n_kernel_launch += (S.plan.n_tasks > 0) + (S.plan.n_iblocks > 0);
+        E.prof.n_kernel_launch += (S.plan.n_tasks > 0) + (!fused && S.plan.n_iblocks > 0);
         if (E.recording) {
             Recorded r;
             r.plan = S.plan; r.direct = direct; r.slot = s;
@@ -1966,7 +1980,7 @@ int pb_tree_force(const void* epi, const pb_layout_epi* lepi, void* force, const
         CU(cudaEventRecord(S.ev[0], S.stream));
         CU(cudaMemcpyAsync(S.d_arena, S.h_arena, h2d, cudaMemcpyHostToDevice, S.stream));
         CU(cudaEventRecord(S.ev[1], S.stream));
-        CU(launch_plan(S.stream, S.plan, S.d_arena, false, S.d_part4, S.d_partn, S.d_out));
+        CU(launch_plan(S.stream, S.plan, S.d_arena, false, S.d_part4, S.d_partn, S.d_out, nullptr));
         CU(cudaEventRecord(S.ev[2], S.stream));
         CU(cudaMemcpyAsync(S.h_out, S.d_out, sizeof(ForceOut) * S.plan.n_i, cudaMemcpyDeviceToHost, S.stream));
         CU(cudaEventRecord(S.ev[3], S.stream));
@@ -2267,7 +2281,7 @@ int pb_replay(int n_iter, float* ms_total, float* ms_force) {
         for (int it = 0; it < n_iter; it++)
             for (auto& r : E.recs) {
                 Slot& S = E.slots[r.slot];
-                CU(launch_plan(S.stream, r.plan, r.d_arena, r.direct, S.d_part4, S.d_partn, S.d_out, force_only));
+                CU(launch_plan(S.stream, r.plan, r.d_arena, r.direct, S.d_part4, S.d_partn, S.d_out, S.h_out, force_only));
             }
         for (int s = 1; s < kMaxStreams; s++)
             if (used[s]) {

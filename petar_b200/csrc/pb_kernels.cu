@@ -115,7 +115,8 @@ struct IdPipe {
 // (pb_plan.cu), so no host round trip sits between the tree walk and the forces.
 // TWOI: SP tasks of groups with at least two i-blocks give every warp TWO blocks (one particle of each per lane) and half as
 // much of every j tile (sp_pairs_2i in pb_pairs.cuh: +6 % on the SP loop).
-template <int NR, int MINB, bool EMIT = false, bool PERSIST = false, bool TWOI = false>
+// FUSE: the warp that delivers an i-block's last partial sum reduces the block and writes the forces (finish_block, pb_pairs.cuh).
+template <int NR, int MINB, bool EMIT = false, bool PERSIST = false, bool TWOI = false, bool FUSE = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
              const float4* __restrict__ epi,
@@ -315,6 +316,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
                 const int slot = task.part_base + (b0 + set * npair) * 32 + lane;
                 part4[slot] = make_double4(d0, d1, d2, d3);
                 partn[slot] = 0;
+                if (FUSE) finish_block(task.blk0 + b0 + set * npair, task.n_chunks, lane, part4, partn, prm);
             }
             __syncthreads();
         }
@@ -355,6 +357,7 @@ force_kernel(const Walk* __restrict__ walks, const Task* __restrict__ tasks,
         part4[slot] = make_double4(dax, day, daz, dpt);
         partn[slot] = cnt;
     }
+    if (FUSE && busy && js == 0) finish_block(task.blk0 + ib, task.n_chunks, lane, part4, partn, prm);
     }
     if (!PERSIST) break;
     __syncthreads();                                   // everybody is done with this task's shared state
@@ -381,6 +384,10 @@ cudaError_t launch_force(cudaStream_t s, int n_tasks, int nr_steps, int min_bloc
 #define PB_LAUNCH(...) force_kernel<__VA_ARGS__><<<n_tasks, kThreads, 0, s>>>(walks, tasks, epi, id_epj, id_spj, epj, spj, part4, partn, p)
     if (emit_pairs)          PB_LAUNCH(0, 2, true);        // neighbour lists: count-only tasks, no rsqrt involved
     else if (min_blocks >= 3) { if (nr_steps >= 1) PB_LAUNCH(1, 3); else PB_LAUNCH(0, 3); }       // occupancy experiment: one i per lane only
+    else if (p.out != nullptr) {                           // fused reduction: Params carries the i-block table, the counters and the result array
+        if (two_i)          { if (nr_steps >= 1) PB_LAUNCH(1, 2, false, false, true, true); else PB_LAUNCH(0, 2, false, false, true, true); }
+        else                { if (nr_steps >= 1) PB_LAUNCH(1, 2, false, false, false, true); else PB_LAUNCH(0, 2, false, false, false, true); }
+    }
     else if (two_i)         { if (nr_steps >= 1) PB_LAUNCH(1, 2, false, false, true); else PB_LAUNCH(0, 2, false, false, true); }
     else                    { if (nr_steps >= 1) PB_LAUNCH(1, 2); else PB_LAUNCH(0, 2); }
 #undef PB_LAUNCH

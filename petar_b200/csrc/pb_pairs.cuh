@@ -445,4 +445,45 @@ __device__ __forceinline__ void sp_pairs_2i(const SpTile& t, int p0, int p1, con
     }
 }
 
+// Fused reduction.  The warp that has just written the partial sums of an i-block for one chunk counts the chunk in (one
+// release-acquire atomic by lane 0).  The warp that delivered the block's LAST chunk adds all of them in chunk order (fixed
+// order: bitwise reproducible whoever comes last), applies G and writes the 32 ForceSoft-shaped records — into page-locked
+// host memory, so no reduction kernel and no D2H copy follow the force kernel.  The 40-byte records leave as five coalesced
+// 256-byte stores.  reduce_block is a real call: its registers must not weigh on the pair loops.
+static __device__ __noinline__ void reduce_block(int bi, int lane, const double4* part4, const int* partn, const IBlock* iblocks, ForceOut* out, int* done, double G) {
+    const IBlock B = iblocks[bi];
+    double ax = 0.0, ay = 0.0, az = 0.0, pt = 0.0;
+    long long n = 0;
+#pragma unroll 4
+    for (int c = 0; c < B.n_chunks; ++c) {
+        const int slot = B.part_base + c * B.stride + lane;
+        const double2* q = reinterpret_cast<const double2*>(part4 + slot);
+        const double2 v0 = __ldcg(q), v1 = __ldcg(q + 1);
+        ax += v0.x; ay += v0.y; az += v1.x; pt += v1.y;
+        n += __ldcg(partn + slot);
+    }
+    const double f[5] = {G * ax, G * ay, G * az, -(G * pt), __longlong_as_double(n)};
+    double* o = reinterpret_cast<double*>(out + B.out_off);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int k = lane + 32 * j, src = k / 5, fld = k - 5 * src;   // 8-byte word k of the block's 160: particle src, field fld
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const double t = __shfl_sync(0xffffffffu, f[q], src);
+            if (q == fld) v = t;
+        }
+        if (src < B.n_valid) o[k] = v;
+    }
+    if (lane == 0) done[bi] = 0;                              // ready for the next step
+}
+
+__device__ __forceinline__ void finish_block(int bi, int nch, int lane, const double4* part4, const int* partn, const Params& prm) {
+    __syncwarp();                                             // the lanes' partial-sum stores are ordered before lane 0's release
+    int old = 0;
+    if (lane == 0) asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(prm.done + bi) : "memory");
+    const int last = __shfl_sync(0xffffffffu, (int)(old + 1 == nch), 0);      // ... and lane 0's acquire before the other lanes' loads
+    if (last) reduce_block(bi, lane, part4, partn, prm.iblocks, prm.out, prm.done, prm.G);
+}
+
 } // namespace pb
