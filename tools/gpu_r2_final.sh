@@ -9,7 +9,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')
 timeout 900 python bench.py > $O/z_bench.log 2>&1; tail -1 $O/z_bench.log | cut -c1-300
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/z_bench_ref.log 2>&1; tail -1 $O/z_bench_ref.log | cut -c1-300
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-parity --opt coords=0 > $O/z_bench_coords0.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/z_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/z_ncu_launch_run.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/z_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/z_ncu_launch_run.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'^force_kernel$' -s 60 -c 3 -f -o $O/z_prof_force python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --no-device-walk > $O/z_ncu_full_run.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:force_kernel_ws -s 1 -c 1 -f -o $O/z_prof_ws python tools/run_resident.py 1000000 1 > $O/z_ncu_ws_run.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"walk_kernel_c" -s 1 -c 1 -f -o $O/z_prof_walk python tools/run_resident.py 1000000 1 > $O/z_ncu_walk_run.log 2>&1

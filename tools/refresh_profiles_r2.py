@@ -121,11 +121,11 @@ if os.path.exists(src):
         n = r[ik].split("(")[0][:70]
         agg[n][0] += 1; agg[n][1] += v
     tot = sum(v[1] for v in agg.values())
-    summary.append("## Launch list of `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity` (ncu --metrics gpu__time_duration.sum, -c 6000)\n")
-    summary.append("The command runs, per warm-up / timed iteration, one replay of the recorded functor step (448 force + 448 reduce launches), its force-only timing pass (448), one functor step "
-                   "(448 + 448) and one device-resident tree step (compact, walk, i-prep, plan, emit and ONE persistent force launch that also reduces and writes the forces to host memory), "
-                   "plus the recording step: 7 x 448 force, 5 x 448 reduce, 2 persistent launches.  In one tree step of the product path the force kernel is > 99 % of the kernel time "
-                   "either way (`value`: 448 launches, 26.0 ms of 26.1; `e2e`: one launch, 25.3 ms beside 2.6 ms of walk).\n")
+    summary.append("## Launch list of `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity` (ncu --metrics gpu__time_duration.sum, first 3000 launches)\n")
+    summary.append("The command runs the recording functor step, then per warm-up / timed iteration one replay of the recorded step and its force-only timing pass, one functor step "
+                   "(448 force launches each: the reduction is fused into the force kernel, no `reduce_kernel` launches are left) and one device-resident tree step (compact, walk, i-prep, plan, emit "
+                   "and ONE persistent force launch that also reduces and writes the forces to host memory); the capture ends after 3000 launches, inside the second iteration.  In one tree step of "
+                   "the product path the force kernel is > 99 % of the kernel time either way (`value`: 448 launches, 26.2 ms; `e2e`: one launch, 25.3 ms beside 2.6 ms of walk).\n")
     summary.append("| kernel | launches | total ms (under ncu) | share |\n|---|---|---|---|")
     for n, (c, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         summary.append(f"| `{n}` | {c} | {tt / 1e6:.3f} | {100 * tt / tot:.1f} % |")
