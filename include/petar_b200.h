@@ -158,7 +158,9 @@ int  pb_set_params(double eps2, double rcut2, double G);
  *                are and pack them on the device (bit-identical to the host packing) — for several ranks per node, where the
  *                host cores (4 per rank on an 8-GPU box) are scarcer than PCIe bandwidth: 2.7 -> 0.3 ms of host time per
  *                tree step at 8 ranks.  The arrays must then stay unchanged until the step's forces are back.  0 (default):
- *                packed on the host into pinned staging; the arrays are consumed when the call returns.
+ *                packed on the host into pinned staging; the arrays are consumed when the call returns.  Setting raw_upload
+ *                or raw_result to 0 releases every page-lock taken so far: do that (or pb_finalize) before freeing or moving
+ *                an array the library has page-locked.
  *   "ws"         1 (default): persistent force launches (the device-resident tree step) run the warp-specialised kernel —
  *                8 compute warps that only wait for tiles and run the pair loops, 2 producer warps that fetch tasks and
  *                stage j tiles four deep (pb_kernels_ws.cu); 0: every warp stages and computes (pb::force_kernel).

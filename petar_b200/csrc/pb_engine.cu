@@ -995,6 +995,17 @@ int pb_set_params(double eps2, double rcut2, double G) {
     return PB_OK;
 }
 
+// Switching raw_upload / raw_result off releases every page-lock taken for them: a caller that wants to free or move a
+// registered array switches the option off first (a stale registration would make a later array at the same address look
+// page-locked while the driver still maps its old pages).
+static void release_registered() {
+    if (!E.inited || E.registered.empty()) return;
+    cudaDeviceSynchronize();
+    for (auto& r : E.registered) cudaHostUnregister((void*)r.first);
+    cudaGetLastError();
+    E.registered.clear();
+}
+
 int pb_set_option(const char* key, long long v) {
     if (!key) return fail(PB_ERR_ARG, "pb_set_option: null key");
     if (!strcmp(key, "coords"))  { if (v < 0 || v > 2) return fail(PB_ERR_ARG, "coords must be 0, 1 or 2"); E.opt_coords = (int)v; return PB_OK; }
@@ -1008,9 +1019,9 @@ int pb_set_option(const char* key, long long v) {
     if (!strcmp(key, "walk_ctas")) { if (v < 1 || v > 148 * 16) return fail(PB_ERR_ARG, "walk_ctas must be in [1, 2368]"); E.opt_walk_ctas = (int)v; return PB_OK; }
     if (!strcmp(key, "ep_runs")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "ep_runs must be 0 or 1"); E.opt_ep_runs = (int)v; return PB_OK; }
     if (!strcmp(key, "walk_compact")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "walk_compact must be 0 or 1"); E.opt_walk_compact = (int)v; return PB_OK; }
-    if (!strcmp(key, "raw_upload")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "raw_upload must be 0 or 1"); E.opt_raw_upload = (int)v; return PB_OK; }
+    if (!strcmp(key, "raw_upload")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "raw_upload must be 0 or 1"); E.opt_raw_upload = (int)v; if (!v) release_registered(); return PB_OK; }
     if (!strcmp(key, "ws")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "ws must be 0 or 1"); E.opt_ws = (int)v; return PB_OK; }
-    if (!strcmp(key, "raw_result")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "raw_result must be 0 or 1"); E.opt_raw_result = (int)v; return PB_OK; }
+    if (!strcmp(key, "raw_result")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "raw_result must be 0 or 1"); E.opt_raw_result = (int)v; if (!v) release_registered(); return PB_OK; }
     if (!strcmp(key, "fuse_reduce")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "fuse_reduce must be 0 or 1"); E.opt_fuse_reduce = (int)v; return PB_OK; }
     if (!strcmp(key, "sp2i")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "sp2i must be 0 or 1"); E.opt_sp2i = (int)v; return PB_OK; }
     if (!strcmp(key, "chunk_tile")) { if (v < 0 || v > 1) return fail(PB_ERR_ARG, "chunk_tile must be 0 or 1"); E.opt_chunk_tile = (int)v; return PB_OK; }
