@@ -60,6 +60,8 @@ struct __align__(16) IBlock {
     int pad0, pad1, pad2;
 };
 
+static_assert(sizeof(Walk) == 64 && sizeof(Task) == 48 && sizeof(IBlock) == 32, "table records: sizes are part of the arena layout");
+
 // Result record, identical to PeTar's ForceSoft (reference src/soft_ptcl.hpp:4-15) so that the
 // D2H buffer can be memcpy'd straight into FDPS's force arrays.  40 B.
 struct ForceOut {

@@ -74,6 +74,10 @@ def test_options_validate():
     assert L.pb_set_option(b"coords", 3) == -3 and L.pb_get_option(b"nosuchkey", C.byref(v)) == -3
     assert L.pb_set_option(b"streams", 0) == -3
     assert L.pb_set_option(b"nosuchkey", 1) == -3
+    # kernel variants and the in-place options: documented defaults, range checks (no GPU needed to set them)
+    for key, default, bad in ((b"ws", 1, 2), (b"sp2i", 1, 2), (b"fuse_reduce", 1, 2), (b"raw_result", 0, 2), (b"raw_upload", 0, 2), (b"ep_runs", 0, 2)):
+        assert L.pb_get_option(key, C.byref(v)) == 0 and v.value == default, key
+        assert L.pb_set_option(key, bad) == -3 and L.pb_set_option(key, 1 - default) == 0 and L.pb_set_option(key, default) == 0, key
     assert L.pb_set_params(-1.0, 0.0, 1.0) == -3
 
 
