@@ -17,8 +17,8 @@ RUNS = [
     ("1 GPU, reference arm", "z_bench_ref.log", "python bench.py --impl reference --steps 3 --warmup 1"),
     ("2 GPUs", "s_bench_2gpu.log", "torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 8 --warmup 3"),
     ("4 GPUs", "s_bench_4gpu.log", "torchrun --nproc-per-node 4 bench.py --gpus 4 --steps 8 --warmup 3"),
-    ("8 GPUs, `raw_upload = 1` (default of the multi-rank stepper)", "g8_bench.log", "torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 8 --warmup 3"),
-    ("8 GPUs, `raw_upload = 0`", "g8_bench_raw0.log", "PETAR_B200_RAW_UPLOAD=0 torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 8 --warmup 3 --no-parity"),
+    ("8 GPUs, `raw_upload = 1` (default of the multi-rank stepper)", "s_bench_8gpu.log", "torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 8 --warmup 3"),
+    ("8 GPUs, `raw_upload = 0` (one commit earlier: the functor path's kernel without the fused reduction)", "g8_bench_raw0.log", "PETAR_B200_RAW_UPLOAD=0 torchrun --nproc-per-node 8 bench.py --gpus 8 --steps 8 --warmup 3 --no-parity"),
     ("1 GPU, BASELINE config 4 stand-in: N = 1e6 stars, 100 % binaries -> 7e6 tree particles", "c4_bench.log", "python bench.py --f-bin 1.0 --steps 3 --warmup 3 --no-cpu-baseline"),
     ("earlier in the round (before `sp2i`, fused reduction): 1 GPU, functor path with EP lists as plain indices (`ep_runs = 0`, the default)", "l_bench_runs0.log", "python bench.py --no-cpu-baseline --no-parity --opt ep_runs=0"),
     ("earlier in the round: 1 GPU, functor path with EP lists as runs (`ep_runs = 1`)", "l_bench_runs1.log", "python bench.py --no-cpu-baseline --no-parity --opt ep_runs=1"),
