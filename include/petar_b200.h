@@ -292,8 +292,8 @@ int  pb_tree_lists(int* n_ep, int* n_sp, int* id_ep, long long cap_ep, int* id_s
 
 /* Test hook, host only (needs no device): the task plan the library would make for ONE sub-batch of n_walk
  * walks with the given list lengths, as `n_streams_active` sub-batches run concurrently.  walks_out: 6 ints
- * per walk {i_off, ni, ej_off, nej, sj_off, nsj}; tasks_out: 8 ints per task {walk, i_first, nib, jsplit, kind,
- * j_begin, j_count, part_base} (at most cap_tasks are written); iblocks_out: 5 ints per 32-wide i-block
+ * per walk {i_off, ni, ej_off, nej, sj_off, nsj}; tasks_out: 10 ints per task {walk, i_first, nib, jsplit, kind,
+ * j_begin, j_count, part_base, blk0, n_chunks} (at most cap_tasks are written); iblocks_out: 5 ints per 32-wide i-block
  * {part_base, n_chunks, stride, out_off, n_valid} (at most cap_iblocks).  Returns the number of tasks, the
  * number of i-blocks in *n_iblocks and the number of partial-sum slots in *n_part. */
 int  pb_debug_plan(int n_walk, const int* n_epi, const int* n_epj, const int* n_spj, int n_streams_active,

@@ -1437,8 +1437,9 @@ int pb_debug_plan(int n_walk, const int* n_epi, const int* n_epj, const int* n_s
     }
     for (int t = 0; t < (int)hp.tasks.size() && t < cap_tasks && tasks_out; t++) {
         const Task& T = hp.tasks[t];
-        int* o = tasks_out + 8 * t;
+        int* o = tasks_out + 10 * t;
         o[0] = T.walk; o[1] = T.i_first; o[2] = T.nib; o[3] = T.jsplit; o[4] = T.kind; o[5] = T.j_begin; o[6] = T.j_count; o[7] = T.part_base;
+        o[8] = T.blk0; o[9] = T.n_chunks;
     }
     for (int b = 0; b < (int)hp.iblocks.size() && b < cap_iblocks && iblocks_out; b++) {
         const IBlock& B = hp.iblocks[b];

@@ -255,7 +255,7 @@ class SearchNeighborCUDAMultiWalk:
 
 
 def debug_plan(n_epi, n_epj, n_spj, n_streams_active=1):
-    """Host-only test hook: (walks[n_walk, 6], tasks[n_tasks, 8], iblocks[n_iblocks, 5], n_part) of the task
+    """Host-only test hook: (walks[n_walk, 6], tasks[n_tasks, 10], iblocks[n_iblocks, 5], n_part) of the task
     plan for one sub-batch with these list lengths (see pb_debug_plan in include/petar_b200.h)."""
     L = load()
     a = [np.ascontiguousarray(x, dtype=np.int32) for x in (n_epi, n_epj, n_spj)]
@@ -266,7 +266,7 @@ def debug_plan(n_epi, n_epj, n_spj, n_streams_active=1):
                          walks.ctypes.data, None, 0, None, 0, C.byref(nib), C.byref(npart))
     if nt < 0:
         check(nt, "pb_debug_plan")
-    tasks = np.zeros((max(nt, 1), 8), dtype=np.int32)
+    tasks = np.zeros((max(nt, 1), 10), dtype=np.int32)
     ibl = np.zeros((max(nib.value, 1), 5), dtype=np.int32)
     L.pb_debug_plan(nw, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, int(n_streams_active),
                     walks.ctypes.data, tasks.ctypes.data, nt, ibl.ctypes.data, nib.value, C.byref(nib), C.byref(npart))

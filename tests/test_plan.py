@@ -5,7 +5,9 @@ through the test hook pb_debug_plan.
 * chunk starts are multiples of the 256-entry j tile (hence of 8) and list offsets multiples of 4 entries: every index tile the force kernel
   fetches with a bulk (TMA) copy then starts on a 16-byte boundary;
 * nib * jsplit <= 8 warps, i_first a multiple of 32, groups follow the binary 8/4/2/1 decomposition;
-* partial-sum slots of different (task, i-block) pairs never overlap and the reduction tables point at them."""
+* partial-sum slots of different (task, i-block) pairs never overlap and the reduction tables point at them;
+* fused reduction: a task names its group's first i-block (`blk0`) and the number of partial sums each of the group's blocks
+  will receive (`n_chunks`) — the counter target of the warp that decides whether it delivered the last one."""
 import numpy as np
 import pytest
 
@@ -25,7 +27,16 @@ def _check(n_epi, n_epj, n_spj, n_streams):
         assert np.all(ends[:-1] <= walks[order, col][1:])
     used = np.zeros(n_part, dtype=np.int32)
     cover = {}
-    for walk, i_first, nib, jsplit, kind, j_begin, j_count, part_base in tasks:
+    delivered = np.zeros(len(ibl), dtype=np.int32)
+    for walk, i_first, nib, jsplit, kind, j_begin, j_count, part_base, blk0, n_chunks in tasks:
+        # fused reduction: this task delivers one partial sum to each of blocks blk0 .. blk0 + nib - 1, at a slot the
+        # block's reduction record reaches with one of its n_chunks strides
+        for b in range(nib):
+            bp, bn, bs, bo, bv = ibl[blk0 + b]
+            assert bn == n_chunks and bs == nib * 32
+            k, r = divmod(part_base + b * 32 - bp, bs)
+            assert r == 0 and 0 <= k < bn
+            delivered[blk0 + b] += 1
         assert 0 <= walk < nw and kind in (0, 1) and nib in (1, 2, 4, 8) and nib * jsplit == 8
         assert i_first % 32 == 0 and i_first < max(1, n_epi[walk]) and j_begin % 8 == 0 and j_count > 0
         nj = n_epj[walk] if kind == 0 else n_spj[walk]
@@ -46,6 +57,7 @@ def _check(n_epi, n_epj, n_spj, n_streams):
                 assert pos == nj
     # reduction tables: every i-block once, chunks = tasks that cover it, slots inside the partial array
     assert len(ibl) == sum((n + 31) // 32 for n in n_epi)
+    assert np.array_equal(delivered, ibl[:, 1]) if len(ibl) else True              # every block gets exactly n_chunks partial sums
     out_seen = set()
     for part_base, n_chunks, stride, out_off, n_valid in ibl:
         assert 1 <= n_valid <= 32 and out_off not in out_seen and (n_chunks == 0 or part_base + (n_chunks - 1) * stride + 32 <= n_part)
