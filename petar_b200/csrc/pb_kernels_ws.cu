@@ -13,8 +13,13 @@
 //     global loads at a task's start (task -> walk -> index list -> j records) overlap the previous task's arithmetic.
 //
 // mbarrier phases run on across tasks (both sides count tiles and tasks globally), nothing is re-initialised.
-// Launched with 2 CTAs per SM (320 threads, <= 96 registers).  Used by the device-resident tree step and by the
-// host-planned dispatches (kinds 0 and 1; the neighbour-search tasks of tree_nb keep pb::force_kernel).
+// Launched with 2 CTAs per SM (320 threads, <= 96 registers) by the device-resident tree step (pb_tree_force_resident);
+// the functor path's dispatches and the neighbour search keep pb::force_kernel.
+//
+// Template switches: TWOI — SP tasks of groups with >= 2 i-blocks give every compute warp two blocks (one particle of each
+// per lane, sp_pairs_2i) and half as much of every tile; FUSE — the warp that delivers the last partial sum of an i-block
+// reduces the block and writes its forces to page-locked host memory (finish_block in pb_pairs.cuh), so the launch is
+// followed by neither a reduction kernel nor a D2H copy.
 #include "pb_pairs.cuh"
 
 namespace pb {
